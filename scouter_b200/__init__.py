@@ -1,0 +1,28 @@
+"""scouter_b200 -- the SCOUTER (wbw520/scouter) forward hot path, rebuilt for B200 (sm_100a).
+
+Public surface = the reference's module API for that path:
+``SlotModel``, ``SlotAttention`` (alias ``ScouterAttention``), ``load_backbone``, ``Identical``,
+``build_position_encoding`` / ``PositionEmbeddingSine`` and ``create_model`` for the hot-path backbones.
+All arithmetic runs in ``libscouter_b200.so`` (hand-written CUDA behind the C ABI of
+``include/scouter_b200.h``); there is no CPU or torch-op fallback.
+"""
+import os
+
+from . import _lib
+from ._lib import ScouterError, MATH_FP32, MATH_TC
+from .backbone import Identical, create_model, list_models
+from .position_encode import PositionEmbeddingSine, build_position_encoding
+from .slot_attention import ScouterAttention, SlotAttention
+from .slot_model import SlotModel, load_backbone
+
+__all__ = ["SlotModel", "SlotAttention", "ScouterAttention", "load_backbone", "Identical", "create_model",
+           "list_models", "PositionEmbeddingSine", "build_position_encoding", "ScouterError", "default_math",
+           "MATH_FP32", "MATH_TC"]
+
+
+def default_math() -> int:
+    """SCOUTER_MATH=fp32 -> exact CUDA-core kernels; SCOUTER_MATH=tc (default) -> tcgen05 tensor-core kernels."""
+    v = os.environ.get("SCOUTER_MATH", "tc").lower()
+    if v not in ("fp32", "tc"):
+        raise ScouterError(f"SCOUTER_MATH={v!r}: expected 'fp32' or 'tc'")
+    return MATH_FP32 if v == "fp32" else MATH_TC

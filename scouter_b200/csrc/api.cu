@@ -1,0 +1,356 @@
+// C-ABI glue: error reporting, the backbone op-program executor (shape inference, arena placement,
+// kernel selection) and the fused-head entry point.  See include/scouter_b200.h for the contract.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "umma.cuh"
+#include "xslot.cuh"
+
+namespace scouter {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int xslot_loop_launch(const scouter_xslot_desc_t* d, const void* packed, const scouter_xslot_io_t* io, cudaStream_t s);
+
+struct Buf {
+    int B = 0, H = 0, W = 0, C = 0;
+    bool defined = false;
+    size_t offset = (size_t)-1, bytes = 0;
+    int first_def = -1, last_use = -1;
+};
+
+}  // namespace scouter
+
+using namespace scouter;
+
+struct scouter_plan {
+    std::vector<scouter_op_t> ops;
+    std::vector<Buf> bufs;
+    int math = SCOUTER_MATH_FP32;
+    bool bound = false;
+    size_t arena_bytes = 0;
+    int launches = 0;
+    std::vector<UmmaConvPlan> umma;  // per op; .valid says whether the tcgen05 kernel takes it
+};
+
+extern "C" int scouter_abi_version(void) { return SCOUTER_ABI_VERSION; }
+extern "C" const char* scouter_last_error(void) { return g_err; }
+
+extern "C" int scouter_device_check(int device) {
+    cudaDeviceProp prop;
+    SC_CUDA(cudaGetDeviceProperties(&prop, device));
+    SC_CHECK_ARG(prop.major == 10, SCOUTER_E_UNSUPPORTED,
+                 "device %d is sm_%d%d; libscouter_b200 carries sm_100a code only", device, prop.major, prop.minor);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plan
+// ------------------------------------------------------------------------------------------------
+extern "C" int scouter_plan_create(const scouter_op_t* ops, int n_ops, int n_buffers, int math, scouter_plan_t** out) {
+    SC_CHECK_ARG(ops && out && n_ops > 0 && n_buffers > 1, SCOUTER_E_INVALID, "plan_create: bad arguments");
+    SC_CHECK_ARG(math == SCOUTER_MATH_FP32 || math == SCOUTER_MATH_TC, SCOUTER_E_INVALID, "plan_create: math=%d", math);
+    for (int i = 0; i < n_ops; ++i) {
+        const scouter_op_t& o = ops[i];
+        SC_CHECK_ARG(o.kind >= SCOUTER_OP_STEM_CONV && o.kind <= SCOUTER_OP_TO_NCHW, SCOUTER_E_INVALID,
+                     "plan_create: op %d has unknown kind %d", i, o.kind);
+        SC_CHECK_ARG(o.src >= 0 && o.src < n_buffers && o.dst > 0 && o.dst < n_buffers && o.src2 < n_buffers,
+                     SCOUTER_E_INVALID, "plan_create: op %d references a buffer outside [0,%d)", i, n_buffers);
+        if (o.kind == SCOUTER_OP_STEM_CONV || o.kind == SCOUTER_OP_CONV)
+            SC_CHECK_ARG(o.w != nullptr, SCOUTER_E_INVALID, "plan_create: op %d (conv) has no weights", i);
+        if (o.kind == SCOUTER_OP_SPLAT_FC)
+            SC_CHECK_ARG(o.w && o.b && o.w2 && o.b2 && o.mid > 0, SCOUTER_E_INVALID, "plan_create: op %d (splat fc) incomplete", i);
+    }
+    scouter_plan* p = new (std::nothrow) scouter_plan();
+    SC_CHECK_ARG(p, SCOUTER_E_INVALID, "plan_create: out of host memory");
+    p->ops.assign(ops, ops + n_ops);
+    p->bufs.resize(n_buffers);
+    p->math = math;
+    *out = p;
+    return 0;
+}
+
+extern "C" void scouter_plan_destroy(scouter_plan_t* plan) { delete plan; }
+
+static int pool_out(int H, int k, int s, int p, bool ceil_mode) {
+    if (!ceil_mode) return (H + 2 * p - k) / s + 1;
+    int o = (H + 2 * p - k + s - 1) / s + 1;
+    if ((o - 1) * s >= H + p) --o;  // the last window must start inside the input or left padding
+    return o;
+}
+
+extern "C" int scouter_plan_bind(scouter_plan_t* plan, int batch, int cin, int h, int w) {
+    SC_CHECK_ARG(plan && batch > 0 && cin > 0 && h > 0 && w > 0, SCOUTER_E_INVALID, "plan_bind: bad arguments");
+    plan->bound = false;
+    for (auto& b : plan->bufs) b = Buf();
+    Buf& in = plan->bufs[0];
+    in.B = batch; in.H = h; in.W = w; in.C = cin; in.defined = true; in.first_def = -1;
+    const int n_ops = (int)plan->ops.size();
+    for (int i = 0; i < n_ops; ++i) {
+        const scouter_op_t& o = plan->ops[i];
+        const Buf s = plan->bufs[o.src];
+        SC_CHECK_ARG(s.defined, SCOUTER_E_STATE, "plan_bind: op %d reads buffer %d before it is written", i, o.src);
+        Buf d;
+        d.B = s.B;
+        switch (o.kind) {
+            case SCOUTER_OP_STEM_CONV:
+            case SCOUTER_OP_CONV:
+                SC_CHECK_ARG(s.C == o.cin, SCOUTER_E_INVALID, "plan_bind: op %d expects %d input channels, buffer %d has %d",
+                             i, o.cin, o.src, s.C);
+                SC_CHECK_ARG(o.stride >= 1 && o.kh >= 1 && o.kw >= 1 && o.groups >= 1, SCOUTER_E_INVALID, "plan_bind: op %d geometry", i);
+                d.H = (s.H + 2 * o.pad - o.kh) / o.stride + 1;
+                d.W = (s.W + 2 * o.pad - o.kw) / o.stride + 1;
+                d.C = o.cout;
+                break;
+            case SCOUTER_OP_MAXPOOL:
+                d.H = pool_out(s.H, o.kh, o.stride, o.pad, false);
+                d.W = pool_out(s.W, o.kw, o.stride, o.pad, false);
+                d.C = s.C;
+                break;
+            case SCOUTER_OP_AVGPOOL:
+                d.H = pool_out(s.H, o.kh, o.stride, o.pad, o.flags & SCOUTER_F_CEIL_MODE);
+                d.W = pool_out(s.W, o.kw, o.stride, o.pad, o.flags & SCOUTER_F_CEIL_MODE);
+                d.C = s.C;
+                break;
+            case SCOUTER_OP_SPLAT_GAP:
+                SC_CHECK_ARG(s.C == 2 * o.cout, SCOUTER_E_INVALID, "plan_bind: op %d (splat gap) wants %d channels, got %d", i, 2 * o.cout, s.C);
+                d.H = d.W = 1; d.C = o.cout;
+                break;
+            case SCOUTER_OP_SPLAT_FC:
+                SC_CHECK_ARG(s.C == o.cin && o.cout == 2 * o.cin, SCOUTER_E_INVALID, "plan_bind: op %d (splat fc) channel mismatch", i);
+                d.H = d.W = 1; d.C = o.cout;
+                break;
+            case SCOUTER_OP_SPLAT_APPLY:
+                SC_CHECK_ARG(s.C == 2 * o.cout && o.src2 >= 0, SCOUTER_E_INVALID, "plan_bind: op %d (splat apply) channel mismatch", i);
+                if (o.flags & SCOUTER_F_AVD_POOL) { d.H = pool_out(s.H, 3, 2, 1, false); d.W = pool_out(s.W, 3, 2, 1, false); }
+                else { d.H = s.H; d.W = s.W; }
+                d.C = o.cout;
+                break;
+            case SCOUTER_OP_GAP:
+                d.H = d.W = 1; d.C = s.C;
+                break;
+            case SCOUTER_OP_TO_NCHW:
+                d.H = s.H; d.W = s.W; d.C = s.C;
+                break;
+        }
+        SC_CHECK_ARG(d.H > 0 && d.W > 0, SCOUTER_E_INVALID, "plan_bind: op %d produces an empty %dx%d map (input too small)", i, d.H, d.W);
+        if (o.src2 >= 0) {
+            const Buf& r = plan->bufs[o.src2];
+            SC_CHECK_ARG(r.defined, SCOUTER_E_STATE, "plan_bind: op %d reads buffer %d before it is written", i, o.src2);
+            if (o.kind == SCOUTER_OP_CONV && (o.flags & SCOUTER_F_RESIDUAL))
+                SC_CHECK_ARG(r.H == d.H && r.W == d.W && r.C == d.C, SCOUTER_E_INVALID,
+                             "plan_bind: op %d residual buffer %d is %dx%dx%d, output is %dx%dx%d", i, o.src2, r.H, r.W, r.C, d.H, d.W, d.C);
+        }
+        SC_CHECK_ARG(!plan->bufs[o.dst].defined, SCOUTER_E_INVALID, "plan_bind: buffer %d written twice (op %d)", o.dst, i);
+        d.defined = true;
+        d.first_def = i;
+        d.bytes = align_up((size_t)d.B * d.H * d.W * d.C * sizeof(float), 1024);
+        plan->bufs[o.dst] = d;
+        plan->bufs[o.src].last_use = i;
+        if (o.src2 >= 0) plan->bufs[o.src2].last_use = i;
+    }
+    // Arena placement: first-fit over live intervals; buffers nobody reads are outputs and stay live.
+    struct Live { size_t off, bytes; int buf; };
+    std::vector<Live> live;
+    size_t high = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const int dst = plan->ops[i].dst;
+        Buf& d = plan->bufs[dst];
+        std::sort(live.begin(), live.end(), [](const Live& a, const Live& b) { return a.off < b.off; });
+        size_t off = 0;
+        for (const Live& l : live) {
+            if (off + d.bytes <= l.off) break;
+            off = std::max(off, l.off + l.bytes);
+        }
+        d.offset = off;
+        high = std::max(high, off + d.bytes);
+        live.push_back({off, d.bytes, dst});
+        // release buffers whose last reader is this op (never the one just written)
+        live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) {
+                       const Buf& b = plan->bufs[l.buf];
+                       return l.buf != dst && b.last_use >= 0 && b.last_use <= i;
+                   }), live.end());
+    }
+    plan->arena_bytes = high;
+    plan->launches = n_ops;
+    plan->umma.assign(n_ops, UmmaConvPlan());
+    plan->bound = true;
+    return 0;
+}
+
+extern "C" size_t scouter_plan_arena_bytes(const scouter_plan_t* plan) { return plan && plan->bound ? plan->arena_bytes : 0; }
+
+extern "C" int scouter_plan_buffer_shape(const scouter_plan_t* plan, int buffer, int32_t shape[4]) {
+    SC_CHECK_ARG(plan && plan->bound, SCOUTER_E_STATE, "plan_buffer_shape: plan is not bound");
+    SC_CHECK_ARG(buffer >= 0 && buffer < (int)plan->bufs.size() && plan->bufs[buffer].defined, SCOUTER_E_INVALID,
+                 "plan_buffer_shape: buffer %d undefined", buffer);
+    const Buf& b = plan->bufs[buffer];
+    shape[0] = b.B; shape[1] = b.H; shape[2] = b.W; shape[3] = b.C;
+    return 0;
+}
+
+extern "C" size_t scouter_plan_buffer_offset(const scouter_plan_t* plan, int buffer) {
+    if (!plan || !plan->bound || buffer <= 0 || buffer >= (int)plan->bufs.size()) return (size_t)-1;
+    return plan->bufs[buffer].offset;
+}
+
+extern "C" int scouter_plan_launch_count(const scouter_plan_t* plan) { return plan && plan->bound ? plan->launches : 0; }
+
+extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, void* arena, size_t arena_bytes,
+                                scouter_stream_t stream) {
+    SC_CHECK_ARG(plan && plan->bound, SCOUTER_E_STATE, "plan_run: plan is not bound");
+    SC_CHECK_ARG(input_nchw && arena, SCOUTER_E_INVALID, "plan_run: NULL input / arena");
+    SC_CHECK_ARG(arena_bytes >= plan->arena_bytes, SCOUTER_E_INVALID, "plan_run: arena of %zu bytes, need %zu", arena_bytes, plan->arena_bytes);
+    SC_CHECK_ARG(((uintptr_t)arena & 1023) == 0, SCOUTER_E_INVALID, "plan_run: arena is not 1024-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    char* base = (char*)arena;
+    auto ptr = [&](int id) -> float* { return id == 0 ? const_cast<float*>(input_nchw) : (float*)(base + plan->bufs[id].offset); };
+    for (size_t i = 0; i < plan->ops.size(); ++i) {
+        const scouter_op_t& o = plan->ops[i];
+        const Buf& sb = plan->bufs[o.src];
+        const Buf& db = plan->bufs[o.dst];
+        int rc = 0;
+        switch (o.kind) {
+            case SCOUTER_OP_STEM_CONV: {
+                SC_CHECK_ARG(o.kh == o.kw && o.groups == 1, SCOUTER_E_UNSUPPORTED, "stem conv: square, ungrouped kernels only");
+                StemArgs a{ptr(o.src), o.w, o.b, ptr(o.dst), sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.stride, o.pad,
+                           (o.flags & SCOUTER_F_RELU) ? 1 : 0};
+                rc = launch_stem_conv(a, s);
+                break;
+            }
+            case SCOUTER_OP_CONV: {
+                ConvArgs a{ptr(o.src), o.w, o.b, (o.flags & SCOUTER_F_RESIDUAL) ? ptr(o.src2) : nullptr, ptr(o.dst),
+                           sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.kw, o.stride, o.pad, o.groups,
+                           (o.flags & SCOUTER_F_RELU) ? 1 : 0};
+                if (plan->math == SCOUTER_MATH_TC && umma_conv_supported(a)) rc = launch_conv_umma(a, plan->umma[i], s);
+                else rc = launch_conv_simt(a, s);
+                break;
+            }
+            case SCOUTER_OP_MAXPOOL:
+                rc = launch_maxpool(ptr(o.src), ptr(o.dst), sb.B, sb.H, sb.W, sb.C, db.H, db.W, o.kh, o.stride, o.pad, s);
+                break;
+            case SCOUTER_OP_AVGPOOL:
+                rc = launch_avgpool(ptr(o.src), ptr(o.dst), sb.B, sb.H, sb.W, sb.C, db.H, db.W, o.kh, o.stride, o.pad,
+                                    (o.flags & SCOUTER_F_COUNT_INCLUDE_PAD) ? 1 : 0, s);
+                break;
+            case SCOUTER_OP_SPLAT_GAP:
+                rc = launch_splat_gap(ptr(o.src), ptr(o.dst), sb.B, sb.H * sb.W, o.cout, s);
+                break;
+            case SCOUTER_OP_SPLAT_FC:
+                rc = launch_splat_fc(ptr(o.src), o.w, o.b, o.w2, o.b2, ptr(o.dst), sb.B, o.cin, o.mid, s);
+                break;
+            case SCOUTER_OP_SPLAT_APPLY:
+                rc = launch_splat_apply(ptr(o.src), ptr(o.src2), ptr(o.dst), sb.B, sb.H, sb.W, o.cout, db.H, db.W,
+                                        (o.flags & SCOUTER_F_AVD_POOL) ? 1 : 0, s);
+                break;
+            case SCOUTER_OP_GAP:
+                rc = launch_gap(ptr(o.src), ptr(o.dst), sb.B, sb.H * sb.W, sb.C, s);
+                break;
+            case SCOUTER_OP_TO_NCHW:
+                rc = launch_nhwc_to_nchw(ptr(o.src), ptr(o.dst), sb.B, sb.H * sb.W, sb.C, s);
+                break;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused head
+// ------------------------------------------------------------------------------------------------
+static int validate_head(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io) {
+    if (int e = validate_xslot_desc(desc)) return e;
+    SC_CHECK_ARG(io, SCOUTER_E_INVALID, "head: io is NULL");
+    SC_CHECK_ARG(io->batch > 0 && io->h > 0 && io->w > 0 && io->channel > 0, SCOUTER_E_INVALID,
+                 "head: batch=%d h=%d w=%d channel=%d", io->batch, io->h, io->w, io->channel);
+    SC_CHECK_ARG(io->channel % 16 == 0, SCOUTER_E_UNSUPPORTED, "head: channel=%d is not a multiple of 16", io->channel);
+    SC_CHECK_ARG(io->layout == SCOUTER_LAYOUT_NHWC || io->layout == SCOUTER_LAYOUT_NCHW, SCOUTER_E_INVALID, "head: layout=%d", io->layout);
+    SC_CHECK_ARG(io->math == SCOUTER_MATH_FP32 || io->math == SCOUTER_MATH_TC, SCOUTER_E_INVALID, "head: math=%d", io->math);
+    return 0;
+}
+
+extern "C" size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io) {
+    if (validate_head(desc, io)) return 0;
+    size_t n = (size_t)io->h * io->w;
+    size_t bytes = align_up((size_t)io->batch * n * XD * sizeof(float), 1024);
+    if (io->layout == SCOUTER_LAYOUT_NCHW) bytes += align_up((size_t)io->batch * n * io->channel * sizeof(float), 1024);
+    return bytes;
+}
+
+extern "C" int scouter_head_forward(const scouter_xslot_desc_t* desc, const void* packed, const scouter_head_io_t* io,
+                                    void* workspace, size_t workspace_bytes, scouter_stream_t stream) {
+    if (int e = validate_head(desc, io)) return e;
+    SC_CHECK_ARG(packed && io->feat && io->conv_w && io->conv_b && io->pe && io->logits, SCOUTER_E_INVALID, "head: NULL pointer argument");
+    const size_t need = scouter_head_workspace_bytes(desc, io);
+    SC_CHECK_ARG(workspace && workspace_bytes >= need, SCOUTER_E_INVALID, "head: workspace of %zu bytes, need %zu", workspace_bytes, need);
+    SC_CHECK_ARG(((uintptr_t)workspace & 1023) == 0, SCOUTER_E_INVALID, "head: workspace is not 1024-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = io->h * io->w;
+    float* xbuf = (float*)workspace;
+    const float* feat = io->feat;
+    if (io->layout == SCOUTER_LAYOUT_NCHW) {
+        float* t = (float*)((char*)workspace + align_up((size_t)io->batch * n * XD * sizeof(float), 1024));
+        if (int e = launch_nchw_to_nhwc(io->feat, t, io->batch, io->channel, n, s)) return e;
+        feat = t;
+    }
+    float* x = io->x_out ? io->x_out : xbuf;
+    // conv1x1 + bias + ReLU (slot_model.py:108-109)
+    ConvArgs c{feat, io->conv_w, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, XD, 1, 1, 1, 0, 1, 1};
+    int rc;
+    if (io->math == SCOUTER_MATH_TC && umma_conv_supported(c)) {
+        UmmaConvPlan tmp;
+        rc = launch_conv_umma(c, tmp, s);
+    } else {
+        rc = launch_conv_simt(c, s);
+    }
+    if (rc) return rc;
+    scouter_xslot_io_t xi;
+    memset(&xi, 0, sizeof(xi));
+    xi.batch = io->batch; xi.n = n;
+    xi.x = x; xi.x_sb = (int64_t)n * XD; xi.x_sn = XD; xi.x_sd = 1;
+    xi.pe = io->pe;
+    xi.logits = io->logits; xi.attn = io->attn; xi.attn_sum = io->attn_sum;
+    return xslot_loop_launch(desc, packed, &xi, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a1 from host buffers (the end-to-end call)
+// ------------------------------------------------------------------------------------------------
+extern "C" int scouter_forward_host(const scouter_forward_host_args_t* a) {
+    SC_CHECK_ARG(a && a->plan && a->desc && a->packed, SCOUTER_E_INVALID, "forward_host: NULL plan/desc/packed");
+    SC_CHECK_ARG(a->input_host && a->input_dev && a->input_bytes > 0, SCOUTER_E_INVALID, "forward_host: NULL input");
+    SC_CHECK_ARG(a->log_probs_dev && a->log_probs_host, SCOUTER_E_INVALID, "forward_host: NULL log_probs");
+    SC_CHECK_ARG(a->plan->bound, SCOUTER_E_STATE, "forward_host: plan is not bound");
+    SC_CHECK_ARG(a->feat_buffer > 0 && a->feat_buffer < (int)a->plan->bufs.size() && a->plan->bufs[a->feat_buffer].defined,
+                 SCOUTER_E_INVALID, "forward_host: feat_buffer=%d undefined", a->feat_buffer);
+    cudaStream_t s = (cudaStream_t)a->stream;
+    SC_CUDA(cudaMemcpyAsync(a->input_dev, a->input_host, a->input_bytes, cudaMemcpyHostToDevice, s));
+    if (int e = scouter_plan_run(a->plan, a->input_dev, a->arena, a->arena_bytes, a->stream)) return e;
+    scouter_head_io_t h = a->head;
+    h.feat = (const float*)((char*)a->arena + a->plan->bufs[a->feat_buffer].offset);
+    h.layout = SCOUTER_LAYOUT_NHWC;
+    if (int e = scouter_head_forward(a->desc, a->packed, &h, a->head_workspace, a->head_workspace_bytes, a->stream)) return e;
+    const int S = a->desc->num_classes * a->desc->slots_per_class;
+    if (int e = scouter_head_finalize(h.logits, h.attn_sum, a->target_dev, h.batch, a->desc->num_classes, S, h.h * h.w,
+                                      a->desc->power, a->lambda_value, a->log_probs_dev,
+                                      h.attn_sum ? a->losses_dev : nullptr, a->stream))
+        return e;
+    SC_CUDA(cudaMemcpyAsync(a->log_probs_host, a->log_probs_dev, (size_t)h.batch * a->desc->num_classes * sizeof(float),
+                            cudaMemcpyDeviceToHost, s));
+    if (a->losses_host && a->losses_dev && h.attn_sum)
+        SC_CUDA(cudaMemcpyAsync(a->losses_host, a->losses_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SC_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}

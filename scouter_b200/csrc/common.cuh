@@ -1,0 +1,101 @@
+// Shared helpers for libscouter_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/scouter_b200.h"
+
+namespace scouter {
+
+void set_error(const char* fmt, ...);
+
+#define SC_CHECK_ARG(cond, code, ...)          \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::scouter::set_error(__VA_ARGS__); \
+            return (code);                     \
+        }                                      \
+    } while (0)
+
+#define SC_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::scouter::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                                 __FILE__, __LINE__);                                        \
+            return (int)_e;                                                                  \
+        }                                                                                    \
+    } while (0)
+
+#define SC_LAUNCH_CHECK()                                                                    \
+    do {                                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            ::scouter::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                                 __FILE__, __LINE__);                                        \
+            return (int)_e;                                                                  \
+        }                                                                                    \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Round-to-nearest fp32 -> tf32 (10-bit mantissa), result kept in an fp32 container.
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ---- launchers implemented in the .cu files (all return 0 / cudaError_t) -------------------------
+
+struct ConvArgs {
+    const float* in;    // NHWC (B,H,W,Cin)
+    const float* w;     // (Cout, kh, kw, Cin/groups)
+    const float* bias;  // (Cout) or null
+    const float* res;   // NHWC (B,Ho,Wo,Cout) or null
+    float* out;         // NHWC (B,Ho,Wo,Cout)
+    int B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, groups, relu;
+};
+int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
+
+struct StemArgs {
+    const float* in;   // NCHW (B,Cin,H,W)
+    const float* w;    // (Cout, kh, kw, Cin)
+    const float* bias;
+    float* out;        // NHWC
+    int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad, relu;
+};
+int launch_stem_conv(const StemArgs& a, cudaStream_t s);
+
+int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride,
+                   int pad, cudaStream_t s);
+int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride,
+                   int pad, int count_include_pad, cudaStream_t s);
+int launch_splat_gap(const float* in, float* gap, int B, int HW, int C /*per radix*/, cudaStream_t s);
+int launch_splat_fc(const float* gap, const float* w1, const float* b1, const float* w2, const float* b2,
+                    float* attn, int B, int C, int mid, cudaStream_t s);
+int launch_splat_apply(const float* in, const float* attn, float* out, int B, int H, int W, int C, int Ho, int Wo,
+                       int avd, cudaStream_t s);
+int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s);
+int launch_nhwc_to_nchw(const float* in, float* out, int B, int HW, int C, cudaStream_t s);
+int launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cudaStream_t s);
+
+}  // namespace scouter

@@ -1,0 +1,498 @@
+// Exact-fp32 backbone kernels on CUDA cores (SCOUTER_MATH_FP32): the bit-for-bit-auditable path that the
+// tensor-core kernels are checked against on the device, and the fallback for shapes the tcgen05 path
+// does not take (strided 3x3, tiny channel counts).  NHWC activations, OHWI weights, BN already folded.
+//
+// Reference ops replaced (eval mode): nn.Conv2d + BatchNorm2d + ReLU chains of timm/models/resnet.py:401-420,
+// resnest.py:111-143, split_attn.py:54-80, the pools at resnet.py:300,420 and resnest.py:101.
+#include "common.cuh"
+
+namespace scouter {
+
+// ------------------------------------------------------------------------------------------------
+// Generic implicit-GEMM convolution:  M = B*Ho*Wo, N = Cout/groups, K = kh*kw*Cin/groups.
+// 128x64 output tile per 256-thread CTA, 8x4 register micro-tile, K in chunks of 16 staged through
+// double-buffered shared memory.  Requires (Cin/groups) % 16 == 0 so a K-chunk sits inside one tap.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
+constexpr int LDA = BM + 4, LDB = BN + 4;
+
+__global__ void __launch_bounds__(256) conv_igemm_f32_kernel(ConvArgs p) {
+    __shared__ __align__(16) float As[2][BK][LDA];
+    __shared__ __align__(16) float Bs[2][BK][LDB];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int g = blockIdx.z;
+    const int cin_g = p.Cin / p.groups, cout_g = p.Cout / p.groups;
+    const int M = p.B * p.Ho * p.Wo;
+    const int K = p.kh * p.kw * cin_g;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    // A loader: 2 float4 per thread: rows (tid/4) and (tid/4 + 64), k-quad tid%4.
+    const int kq = tid % 4;
+    int a_hi0[2], a_wi0[2];
+    long long a_base[2];
+    bool a_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        int m = m0 + tid / 4 + i * 64;
+        a_ok[i] = m < M;
+        int mm = a_ok[i] ? m : 0;
+        int wo = mm % p.Wo;
+        int t = mm / p.Wo;
+        int ho = t % p.Ho;
+        int b = t / p.Ho;
+        a_hi0[i] = ho * p.stride - p.pad;
+        a_wi0[i] = wo * p.stride - p.pad;
+        a_base[i] = (long long)b * p.H * p.W * p.Cin + (long long)g * cin_g + kq * 4;
+    }
+    // B loader: 1 float4 per thread: n = tid/4, k-quad tid%4.
+    const int bn = n0 + tid / 4;
+    const bool b_ok = bn < cout_g;
+    const float* wrow = p.w + (long long)(g * cout_g + (b_ok ? bn : 0)) * K + kq * 4;
+
+    float4 ra[2], rb;
+    auto load_chunk = [&](int kc) {
+        int k0 = kc * BK;
+        int tap = k0 / cin_g;
+        int c0 = k0 - tap * cin_g;
+        int r = tap / p.kw, s = tap - r * p.kw;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int hi = a_hi0[i] + r, wi = a_wi0[i] + s;
+            bool ok = a_ok[i] && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            ra[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.in + a_base[i] + ((long long)hi * p.W + wi) * p.Cin + c0))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        rb = b_ok ? __ldg(reinterpret_cast<const float4*>(wrow + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int row = tid / 4 + i * 64;
+            As[buf][kq * 4 + 0][row] = ra[i].x;
+            As[buf][kq * 4 + 1][row] = ra[i].y;
+            As[buf][kq * 4 + 2][row] = ra[i].z;
+            As[buf][kq * 4 + 3][row] = ra[i].w;
+        }
+        int col = tid / 4;
+        Bs[buf][kq * 4 + 0][col] = rb.x;
+        Bs[buf][kq * 4 + 1][col] = rb.y;
+        Bs[buf][kq * 4 + 2][col] = rb.z;
+        Bs[buf][kq * 4 + 3][col] = rb.w;
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int nk = K / BK;
+    load_chunk(0);
+    store_chunk(0);
+    __syncthreads();
+    for (int kc = 0; kc < nk; ++kc) {
+        const int cur = kc & 1;
+        if (kc + 1 < nk) load_chunk(kc + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * TM]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][ty * TM + 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * TN]);
+            float a[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[TN] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kc + 1 < nk) store_chunk(cur ^ 1);
+        __syncthreads();
+    }
+
+    // Epilogue: + bias (+ residual) (ReLU), NHWC store.
+    const int n = n0 + tx * TN;
+    const bool vec = (cout_g % 4 == 0) && (n + 3 < cout_g);
+    float bv[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = (p.bias && n + j < cout_g) ? __ldg(p.bias + g * cout_g + n + j) : 0.f;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int m = m0 + ty * TM + i;
+        if (m >= M) continue;
+        long long o = (long long)m * p.Cout + g * cout_g + n;
+        float v[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) v[j] = acc[i][j] + bv[j];
+        if (vec) {
+            if (p.res) {
+                float4 r = __ldg(reinterpret_cast<const float4*>(p.res + o));
+                v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                if (n + j >= cout_g) continue;
+                float t = v[j];
+                if (p.res) t += __ldg(p.res + o + j);
+                if (p.relu) t = fmaxf(t, 0.f);
+                p.out[o + j] = t;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem convolution: NCHW input with <= 4 channels (3 RGB, 1 MNIST), k x k, writes NHWC.
+// One thread = one output pixel x 4 output channels; the (Cout,k,k,Cin) filter bank sits in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stem_conv_kernel(StemArgs p) {
+    extern __shared__ __align__(16) float sw[];  // [k*k*Cin][Cout]  (tap-major so a thread's 4 channels are contiguous)
+    const int taps = p.k * p.k * p.Cin;
+    for (int i = threadIdx.x; i < taps * p.Cout; i += blockDim.x) {
+        int co = i / taps, t = i - co * taps;  // source layout (Cout, k, k, Cin)
+        sw[t * p.Cout + co] = p.w[i];
+    }
+    __syncthreads();
+    const int cq = p.Cout / 4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)p.B * p.Ho * p.Wo * cq;
+    if (idx >= total) return;
+    int q = (int)(idx % cq);
+    long long pix = idx / cq;
+    int wo = (int)(pix % p.Wo);
+    long long t2 = pix / p.Wo;
+    int ho = (int)(t2 % p.Ho);
+    int b = (int)(t2 / p.Ho);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int hi0 = ho * p.stride - p.pad, wi0 = wo * p.stride - p.pad;
+    for (int r = 0; r < p.k; ++r) {
+        int hi = hi0 + r;
+        if (hi < 0 || hi >= p.H) continue;
+        for (int s = 0; s < p.k; ++s) {
+            int wi = wi0 + s;
+            if (wi < 0 || wi >= p.W) continue;
+            for (int c = 0; c < p.Cin; ++c) {
+                float v = __ldg(p.in + (((long long)b * p.Cin + c) * p.H + hi) * p.W + wi);
+                const float4 wv = *reinterpret_cast<const float4*>(&sw[((r * p.k + s) * p.Cin + c) * p.Cout + q * 4]);
+                acc[0] = fmaf(v, wv.x, acc[0]);
+                acc[1] = fmaf(v, wv.y, acc[1]);
+                acc[2] = fmaf(v, wv.z, acc[2]);
+                acc[3] = fmaf(v, wv.w, acc[3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (p.bias) acc[j] += __ldg(p.bias + q * 4 + j);
+        if (p.relu) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    *reinterpret_cast<float4*>(p.out + pix * p.Cout + q * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pools (NHWC, one thread = one output pixel x 4 channels).
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+                               int Ho, int Wo, int k, int stride, int pad) {
+    const int cq = C / 4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * Ho * Wo * cq;
+    if (idx >= total) return;
+    int q = (int)(idx % cq);
+    long long pix = idx / cq;
+    int wo = (int)(pix % Wo);
+    long long t2 = pix / Wo;
+    int ho = (int)(t2 % Ho);
+    int b = (int)(t2 / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < k; ++r) {
+        int hi = ho * stride - pad + r;
+        if (hi < 0 || hi >= H) continue;
+        for (int s = 0; s < k; ++s) {
+            int wi = wo * stride - pad + s;
+            if (wi < 0 || wi >= W) continue;
+            float4 v = __ldg(reinterpret_cast<const float4*>(in + (((long long)b * H + hi) * W + wi) * C + q * 4));
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    *reinterpret_cast<float4*>(out + pix * C + q * 4) = m;
+}
+
+// PyTorch avg_pool2d semantics: the window is first clipped to the padded extent (that size is the
+// divisor when count_include_pad), then to the real extent (that size is the divisor otherwise).
+__global__ void avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+                               int Ho, int Wo, int k, int stride, int pad, int count_include_pad) {
+    const int cq = C / 4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * Ho * Wo * cq;
+    if (idx >= total) return;
+    int q = (int)(idx % cq);
+    long long pix = idx / cq;
+    int wo = (int)(pix % Wo);
+    long long t2 = pix / Wo;
+    int ho = (int)(t2 % Ho);
+    int b = (int)(t2 / Ho);
+    int hs = ho * stride - pad, ws = wo * stride - pad;
+    int he = min(hs + k, H + pad), we = min(ws + k, W + pad);
+    int pool = (he - hs) * (we - ws);
+    hs = max(hs, 0); ws = max(ws, 0);
+    he = min(he, H); we = min(we, W);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int hi = hs; hi < he; ++hi)
+        for (int wi = ws; wi < we; ++wi) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(in + (((long long)b * H + hi) * W + wi) * C + q * 4));
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+    float div = (float)(count_include_pad ? pool : (he - hs) * (we - ws));
+    a.x /= div; a.y /= div; a.z /= div; a.w /= div;
+    *reinterpret_cast<float4*>(out + pix * C + q * 4) = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split attention (radix 2, cardinality 1).
+// ------------------------------------------------------------------------------------------------
+// gap[b][c] = mean_hw (x[b,hw,c] + x[b,hw,C+c]).  CTA = 32 channels x 8 hw-lanes, fixed-order reduction.
+__global__ void __launch_bounds__(256) splat_gap_kernel(const float* __restrict__ in, float* __restrict__ gap,
+                                                        int HW, int C) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x % 32, hy = threadIdx.x / 32;
+    const int b = blockIdx.y, c = blockIdx.x * 32 + cx;
+    const float* base = in + (long long)b * HW * 2 * C;
+    float s = 0.f;
+    if (c < C)
+        for (int hw = hy; hw < HW; hw += 8) s += __ldg(base + (long long)hw * 2 * C + c) + __ldg(base + (long long)hw * 2 * C + C + c);
+    red[hy][cx] = s;
+    __syncthreads();
+    if (hy == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][cx];
+        gap[(long long)b * C + c] = t / (float)HW;
+    }
+}
+
+// Plain global average pool (B,HW,C) -> (B,C) with the same CTA shape.
+__global__ void __launch_bounds__(256) gap_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x % 32, hy = threadIdx.x / 32;
+    const int b = blockIdx.y, c = blockIdx.x * 32 + cx;
+    const float* base = in + (long long)b * HW * C;
+    float s = 0.f;
+    if (c < C)
+        for (int hw = hy; hw < HW; hw += 8) s += __ldg(base + (long long)hw * C + c);
+    red[hy][cx] = s;
+    __syncthreads();
+    if (hy == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][cx];
+        out[(long long)b * C + c] = t / (float)HW;
+    }
+}
+
+// One CTA per image: h = relu(W1 gap + b1)  (bn1 folded), a = W2 h + b2, softmax over the radix pair.
+__global__ void __launch_bounds__(256) splat_fc_kernel(const float* __restrict__ gap, const float* __restrict__ w1,
+                                                       const float* __restrict__ b1, const float* __restrict__ w2,
+                                                       const float* __restrict__ b2, float* __restrict__ attn, int C,
+                                                       int mid) {
+    extern __shared__ float sm[];
+    float* sg = sm;       // [C]
+    float* sh = sm + C;   // [mid]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sg[i] = gap[(long long)b * C + i];
+    __syncthreads();
+    for (int a = warp; a < mid; a += nw) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w1 + (long long)a * C + c), sg[c], s);
+        s = warp_sum(s);
+        if (lane == 0) sh[a] = fmaxf(s + __ldg(b1 + a), 0.f);
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += nw) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int a = lane; a < mid; a += 32) {
+            float h = sh[a];
+            s0 = fmaf(__ldg(w2 + (long long)c * mid + a), h, s0);
+            s1 = fmaf(__ldg(w2 + (long long)(C + c) * mid + a), h, s1);
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) {
+            s0 += __ldg(b2 + c);
+            s1 += __ldg(b2 + C + c);
+            float mx = fmaxf(s0, s1);
+            float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
+            float inv = 1.f / (e0 + e1);
+            attn[(long long)b * 2 * C + c] = e0 * inv;
+            attn[(long long)b * 2 * C + C + c] = e1 * inv;
+        }
+    }
+}
+
+// out[b,ho,wo,c] = pool3x3s2p1?( x[b,h,w,c]*a0[b,c] + x[b,h,w,C+c]*a1[b,c] ); the pool divisor is 9 wherever
+// the padded window is full (count_include_pad=True, resnest.py:101) and follows avg_pool2d otherwise.
+__global__ void splat_apply_kernel(const float* __restrict__ in, const float* __restrict__ attn,
+                                   float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo, int avd) {
+    const int cq = C / 4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * Ho * Wo * cq;
+    if (idx >= total) return;
+    int q = (int)(idx % cq);
+    long long pix = idx / cq;
+    int wo = (int)(pix % Wo);
+    long long t2 = pix / Wo;
+    int ho = (int)(t2 % Ho);
+    int b = (int)(t2 / Ho);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(attn + (long long)b * 2 * C + q * 4));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(attn + (long long)b * 2 * C + C + q * 4));
+    auto at = [&](int hi, int wi) {
+        const float* p = in + (((long long)b * H + hi) * W + wi) * 2 * C + q * 4;
+        float4 x0 = __ldg(reinterpret_cast<const float4*>(p));
+        float4 x1 = __ldg(reinterpret_cast<const float4*>(p + C));
+        // the reference multiplies then sums over the radix axis: x0*a0 + x1*a1 (two roundings + add)
+        return make_float4(x0.x * a0.x + x1.x * a1.x, x0.y * a0.y + x1.y * a1.y, x0.z * a0.z + x1.z * a1.z,
+                           x0.w * a0.w + x1.w * a1.w);
+    };
+    float4 r;
+    if (!avd) {
+        r = at(ho, wo);
+    } else {
+        int hs = ho * 2 - 1, ws = wo * 2 - 1;
+        int he = min(hs + 3, H + 1), we = min(ws + 3, W + 1);
+        float div = (float)((he - hs) * (we - ws));
+        hs = max(hs, 0); ws = max(ws, 0);
+        he = min(he, H); we = min(we, W);
+        r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int hi = hs; hi < he; ++hi)
+            for (int wi = ws; wi < we; ++wi) {
+                float4 v = at(hi, wi);
+                r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+            }
+        r.x /= div; r.y /= div; r.z /= div; r.w /= div;
+    }
+    *reinterpret_cast<float4*>(out + pix * C + q * 4) = r;
+}
+
+// Tiled transposes between (B, HW, C) and (B, C, HW).
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Ccols) {
+    // in: (B, R, Ccols) -> out: (B, Ccols, R)
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const float* src = in + (long long)b * R * Ccols;
+    float* dst = out + (long long)b * R * Ccols;
+    int c = blockIdx.x * 32 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = blockIdx.y * 32 + i;
+        if (r < R && c < Ccols) tile[i][threadIdx.x] = src[(long long)r * Ccols + c];
+    }
+    __syncthreads();
+    int r2 = blockIdx.y * 32 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c2 = blockIdx.x * 32 + i;
+        if (r2 < R && c2 < Ccols) dst[(long long)c2 * R + r2] = tile[threadIdx.x][i];
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------------------
+int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
+    SC_CHECK_ARG(a.groups >= 1 && a.Cin % a.groups == 0 && a.Cout % a.groups == 0, SCOUTER_E_INVALID,
+                 "conv: channels (%d,%d) not divisible by groups %d", a.Cin, a.Cout, a.groups);
+    const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
+    SC_CHECK_ARG(cin_g % 16 == 0, SCOUTER_E_UNSUPPORTED, "conv: Cin/groups = %d is not a multiple of 16", cin_g);
+    const long long M = (long long)a.B * a.Ho * a.Wo;
+    SC_CHECK_ARG(M > 0 && M < (1ll << 31), SCOUTER_E_INVALID, "conv: M = %lld out of range", M);
+    dim3 grid(cdiv((int)M, BM), cdiv(cout_g, BN), a.groups);
+    conv_igemm_f32_kernel<<<grid, 256, 0, s>>>(a);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_stem_conv(const StemArgs& a, cudaStream_t s) {
+    SC_CHECK_ARG(a.Cin >= 1 && a.Cin <= 4, SCOUTER_E_UNSUPPORTED, "stem conv: Cin = %d (supports 1..4)", a.Cin);
+    SC_CHECK_ARG(a.Cout % 4 == 0, SCOUTER_E_UNSUPPORTED, "stem conv: Cout = %d not a multiple of 4", a.Cout);
+    size_t smem = (size_t)a.k * a.k * a.Cin * a.Cout * sizeof(float);
+    SC_CHECK_ARG(smem <= 48 * 1024, SCOUTER_E_UNSUPPORTED, "stem conv: filter bank of %zu bytes exceeds 48 KB", smem);
+    long long total = (long long)a.B * a.Ho * a.Wo * (a.Cout / 4);
+    stem_conv_kernel<<<(unsigned)((total + 255) / 256), 256, smem, s>>>(a);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
+                   cudaStream_t s) {
+    SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "maxpool: C = %d not a multiple of 4", C);
+    long long total = (long long)B * Ho * Wo * (C / 4);
+    maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W, C, Ho, Wo, k, stride, pad);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
+                   int count_include_pad, cudaStream_t s) {
+    SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "avgpool: C = %d not a multiple of 4", C);
+    long long total = (long long)B * Ho * Wo * (C / 4);
+    avgpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W, C, Ho, Wo, k, stride, pad,
+                                                                  count_include_pad);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_splat_gap(const float* in, float* gap, int B, int HW, int C, cudaStream_t s) {
+    dim3 grid(cdiv(C, 32), B);
+    splat_gap_kernel<<<grid, 256, 0, s>>>(in, gap, HW, C);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s) {
+    dim3 grid(cdiv(C, 32), B);
+    gap_kernel<<<grid, 256, 0, s>>>(in, out, HW, C);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_splat_fc(const float* gap, const float* w1, const float* b1, const float* w2, const float* b2, float* attn,
+                    int B, int C, int mid, cudaStream_t s) {
+    size_t smem = (size_t)(C + mid) * sizeof(float);
+    splat_fc_kernel<<<B, 256, smem, s>>>(gap, w1, b1, w2, b2, attn, C, mid);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_splat_apply(const float* in, const float* attn, float* out, int B, int H, int W, int C, int Ho, int Wo,
+                       int avd, cudaStream_t s) {
+    SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "splat apply: C = %d not a multiple of 4", C);
+    long long total = (long long)B * Ho * Wo * (C / 4);
+    splat_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, attn, out, B, H, W, C, Ho, Wo, avd);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_nhwc_to_nchw(const float* in, float* out, int B, int HW, int C, cudaStream_t s) {
+    dim3 grid(cdiv(C, 32), cdiv(HW, 32), B);
+    transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(in, out, HW, C);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cudaStream_t s) {
+    dim3 grid(cdiv(HW, 32), cdiv(C, 32), B);
+    transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(in, out, C, HW);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace scouter

@@ -1,0 +1,238 @@
+"""Lowering of the module tree to the library's op program, and the runners that execute it.
+
+* ``lower_backbone``   walks a ``backbone.ResNet`` (mirror of timm/models/resnet.py:491-509,
+                       resnest.py:111-143, split_attn.py:54-80), folds eval-mode BatchNorm into every conv
+                        and emits ``scouter_op_t`` records + the packed OHWI weights.
+* ``BackboneRunner``   ``backbone(x)`` standalone: same return value as the reference's
+                       ``ResNet.forward`` (classifier output, or the NCHW-flattened features once
+                       pool/fc are ``Identical``).
+* ``SlotModelRunner``  the whole ``SlotModel.forward`` (slot_model.py:105-127): backbone program + fused
+                       xSlot head + finalize, optionally captured in a CUDA graph, plus the
+                       host-buffer entry (``forward_host``) that bench.py times end to end.
+
+All device memory (arena, workspaces, outputs) is torch-allocated and cached per input shape; the
+library only sees raw pointers.  Weight packs are rebuilt when any parameter/buffer version changes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+
+def _require_cuda(x: torch.Tensor, what: str):
+    if not x.is_cuda:
+        raise L.ScouterError(f"{what}: input is on {x.device}; scouter_b200 runs on CUDA (sm_100a) only, there is no CPU path")
+    if x.dtype != torch.float32:
+        raise L.ScouterError(f"{what}: input dtype {x.dtype}; the reference casts to float32 (engine.py:25) and so must the caller")
+
+
+def _version_signature(module: nn.Module):
+    sig = 0
+    for t in list(module.parameters()) + list(module.buffers()):
+        sig = (sig * 1000003 + t._version + (t.data_ptr() & 0xFFFF)) & 0xFFFFFFFFFFFF
+    return sig
+
+
+def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
+    """(Cout, kh, kw, Cin/g) fp32 OHWI weight and (Cout) bias with eval-mode BN folded (fp64 fold, fp32 store)."""
+    w = conv.weight.detach().double()
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64, device=w.device)
+    if bn is not None:
+        s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = w * s[:, None, None, None]
+        b = (b - bn.running_mean.detach().double()) * s + bn.bias.detach().double()
+    return w.permute(0, 2, 3, 1).contiguous().float(), b.float().contiguous()
+
+
+class Program:
+    """Accumulates ops; keeps every packed tensor alive."""
+
+    def __init__(self):
+        self.ops: list[L.Op] = []
+        self.keep: list[torch.Tensor] = []
+        self.nbuf = 1  # buffer 0 = network input
+
+    def buf(self) -> int:
+        self.nbuf += 1
+        return self.nbuf - 1
+
+    def _t(self, t):
+        if t is None:
+            return 0
+        self.keep.append(t)
+        return t.data_ptr()
+
+    def emit(self, kind, src, dst, *, src2=-1, cin=0, cout=0, k=1, stride=1, pad=0, groups=1, flags=0, mid=0,
+             w=None, b=None, w2=None, b2=None):
+        self.ops.append(L.Op(kind=kind, src=src, src2=src2, dst=dst, cin=cin, cout=cout, kh=k, kw=k, stride=stride,
+                             pad=pad, groups=groups, flags=flags, mid=mid, reserved=0,
+                             w=self._t(w), b=self._t(b), w2=self._t(w2), b2=self._t(b2)))
+        return dst
+
+    def conv(self, src, conv: nn.Conv2d, bn, *, relu, residual=-1, stem=False):
+        w, b = fold_conv_bn(conv, bn)
+        flags = (L.F_RELU if relu else 0) | (L.F_RESIDUAL if residual >= 0 else 0)
+        return self.emit(L.OP_STEM_CONV if stem else L.OP_CONV, src, self.buf(), src2=residual,
+                         cin=conv.in_channels, cout=conv.out_channels, k=conv.kernel_size[0], stride=conv.stride[0],
+                         pad=conv.padding[0], groups=conv.groups, flags=flags, w=w, b=b)
+
+
+def _lower_resnest_block(p: Program, blk, x: int) -> int:
+    t = p.conv(x, blk.conv1, blk.bn1, relu=True)
+    sa = blk.conv2
+    c = sa.conv.out_channels // 2
+    t2 = p.conv(t, sa.conv, sa.bn0, relu=True)                                   # (B,H,W,2C)
+    gap = p.emit(L.OP_SPLAT_GAP, t2, p.buf(), cout=c)
+    w1, b1 = fold_conv_bn(sa.fc1, sa.bn1)
+    w2, b2 = fold_conv_bn(sa.fc2, None)
+    mid = sa.fc1.out_channels
+    av = p.emit(L.OP_SPLAT_FC, gap, p.buf(), cin=c, cout=2 * c, mid=mid,
+                w=w1.reshape(mid, c).contiguous(), b=b1, w2=w2.reshape(2 * c, mid).contiguous(), b2=b2)
+    t3 = p.emit(L.OP_SPLAT_APPLY, t2, p.buf(), src2=av, cout=c, flags=L.F_AVD_POOL if blk.avd_last is not None else 0)
+    res = x
+    if blk.downsample is not None:
+        pool, dconv, dbn = blk.downsample[0], blk.downsample[1], blk.downsample[2]
+        r = x
+        if isinstance(pool, nn.AvgPool2d):
+            r = p.emit(L.OP_AVGPOOL, x, p.buf(), k=2, stride=pool.stride if isinstance(pool.stride, int) else pool.stride[0],
+                       pad=0, flags=L.F_CEIL_MODE)
+        res = p.conv(r, dconv, dbn, relu=False)
+    return p.conv(t3, blk.conv3, blk.bn3, relu=True, residual=res)
+
+
+def _lower_basic_block(p: Program, blk, x: int) -> int:
+    t = p.conv(x, blk.conv1, blk.bn1, relu=True)
+    res = x
+    if blk.downsample is not None:
+        res = p.conv(x, blk.downsample[0], blk.downsample[1], relu=False)
+    return p.conv(t, blk.conv2, blk.bn2, relu=True, residual=res)
+
+
+def lower_backbone(net, p: Program | None = None):
+    """Returns (program, feature_buffer_id) for ``forward_features`` (resnet.py:491-501)."""
+    from .backbone import BasicBlock, ResNestBottleneck
+    p = p or Program()
+    if isinstance(net.conv1, nn.Sequential):                                    # deep stem
+        x = p.conv(0, net.conv1[0], net.conv1[1], relu=True, stem=True)
+        x = p.conv(x, net.conv1[3], net.conv1[4], relu=True)
+        x = p.conv(x, net.conv1[6], net.bn1, relu=True)
+    else:
+        x = p.conv(0, net.conv1, net.bn1, relu=True, stem=True)
+    x = p.emit(L.OP_MAXPOOL, x, p.buf(), k=3, stride=2, pad=1)
+    for li in range(1, 5):
+        for blk in getattr(net, f"layer{li}"):
+            if isinstance(blk, ResNestBottleneck):
+                x = _lower_resnest_block(p, blk, x)
+            elif isinstance(blk, BasicBlock):
+                x = _lower_basic_block(p, blk, x)
+            else:
+                raise L.ScouterError(f"cannot lower block type {type(blk).__name__}")
+    return p, x
+
+
+class CompiledProgram:
+    """A ``scouter_plan_t`` plus its bound arena for one input shape."""
+
+    def __init__(self, program: Program, math: int):
+        self.program = program
+        arr = (L.Op * len(program.ops))(*program.ops)
+        h = C.c_void_p()
+        L.check(L.lib().scouter_plan_create(arr, len(program.ops), program.nbuf, math, C.byref(h)), "scouter_plan_create")
+        self.handle = h
+        self.shape = None
+        self.arena = None
+
+    def bind(self, b, cin, h, w, device):
+        if self.shape == (b, cin, h, w) and self.arena is not None and self.arena.device == device:
+            return
+        L.check(L.lib().scouter_plan_bind(self.handle, b, cin, h, w), "scouter_plan_bind")
+        nbytes = L.lib().scouter_plan_arena_bytes(self.handle)
+        self.arena = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        self.arena_off = (-self.arena.data_ptr()) % 1024
+        self.arena_bytes = nbytes
+        self.shape = (b, cin, h, w)
+
+    @property
+    def arena_ptr(self):
+        return self.arena.data_ptr() + self.arena_off
+
+    def buffer_shape(self, buf):
+        s = (C.c_int32 * 4)()
+        L.check(L.lib().scouter_plan_buffer_shape(self.handle, buf, C.byref(s)), "scouter_plan_buffer_shape")
+        return tuple(s)
+
+    def buffer_view(self, buf) -> torch.Tensor:
+        """fp32 view (B,H,W,C) of a plan buffer inside the arena (valid until the next run overwrites it)."""
+        b, h, w, c = self.buffer_shape(buf)
+        off = L.lib().scouter_plan_buffer_offset(self.handle, buf)
+        n = b * h * w * c
+        return self.arena[self.arena_off + off: self.arena_off + off + 4 * n].view(torch.float32).view(b, h, w, c)
+
+    def run(self, x: torch.Tensor):
+        L.check(L.lib().scouter_plan_run(self.handle, x.data_ptr(), self.arena_ptr, self.arena_bytes, L.stream_ptr()),
+                "scouter_plan_run")
+
+    @property
+    def launches(self):
+        return L.lib().scouter_plan_launch_count(self.handle)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().scouter_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _check_inference(module: nn.Module, what: str):
+    if module.training:
+        raise NotImplementedError(
+            f"{what}: train-mode forward (batch-statistics BatchNorm + backward) is SURVEY.md row f1 and is not "
+            "implemented; call .eval() -- scouter_b200 accelerates the eval-mode forward hot path")
+
+
+class BackboneRunner:
+    """``ResNet.forward`` (resnet.py:503-509) on the CUDA library."""
+
+    def __init__(self, net, math: int | None = None):
+        self.net = net
+        self.math = math
+        self.sig = None
+        self.cp = None
+
+    def _compile(self):
+        from .backbone import Identical
+        from . import default_math
+        net = self.net
+        p, feat = lower_backbone(net)
+        self.flatten_nchw = isinstance(net.global_pool, Identical)
+        if self.flatten_nchw:
+            out = p.emit(L.OP_TO_NCHW, feat, p.buf())
+        else:
+            out = p.emit(L.OP_GAP, feat, p.buf())
+            if not isinstance(net.fc, Identical):
+                fc = net.fc
+                w = fc.weight.detach().float().contiguous()
+                b = fc.bias.detach().float().contiguous()
+                out = p.emit(L.OP_CONV, out, p.buf(), cin=fc.in_features, cout=fc.out_features, k=1, w=w, b=b)
+        self.out_buf = out
+        self.cp = CompiledProgram(p, default_math() if self.math is None else self.math)
+        self.sig = _version_signature(net)
+
+    def __call__(self, x):
+        _require_cuda(x, "backbone")
+        _check_inference(self.net, "backbone")
+        if self.cp is None or self.sig != _version_signature(self.net):
+            self._compile()
+        x = x.contiguous()
+        b, cin, h, w = x.shape
+        with torch.cuda.device(x.device):
+            self.cp.bind(b, cin, h, w, x.device)
+            self.cp.run(x)
+            out = self.cp.buffer_view(self.out_buf)
+            # (B,H,W,C) view of a TO_NCHW buffer is really (B,C,H,W) memory; flatten(1) either way
+            return out.reshape(b, -1).clone()

@@ -1,0 +1,293 @@
+"""``SlotModel`` / ``load_backbone`` / ``Identical`` -- drop-in for reference ``sloter/slot_model.py:10-127``.
+
+Same ``args`` contract (the attributes of train.py:18-79 the reference reads), same attribute names
+(``backbone, conv1x1, slot, position_emb, use_slot, channel, slots_per_class, feature_size,
+lambda_value``), same ``state_dict`` keys and the same return values:
+``forward(x)`` -> (B,C) log-probabilities; ``forward(x, target)`` -> ``[output, [loss, nll, attn_loss]]``
+(``[output, [loss]]`` without slots).  The forward itself is the library's op program + fused head.
+
+Differences, all deliberate:
+* ``feature_size`` is derived from the real feature map instead of being hard-wired to 9 (the reference
+  crashes on anything but 260x260 inputs); the attribute is updated after each forward.
+* eval-mode forward only (train-mode BatchNorm / backward = SURVEY.md row f1).
+* ``pre_trained=True`` is refused (it downloads weights); ``use_pre`` loads the stage-1 checkpoint exactly
+  like the reference (:26-33).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .backbone import Identical, create_model
+from .plan import CompiledProgram, _check_inference, _require_cuda, _version_signature, lower_backbone
+from .position_encode import build_position_encoding
+from .slot_attention import SlotAttention
+
+
+def load_backbone(args):
+    bone = create_model(args.model, pretrained=args.pre_trained, num_classes=args.num_classes)
+    if args.dataset == "MNIST":                                           # slot_model.py:23-24
+        bone.conv1 = nn.Conv2d(1, 64, 3, stride=2, padding=1, bias=False)
+    if args.use_slot:
+        if args.use_pre:                                                  # :26-33
+            checkpoint = torch.load(f"saved_model/{args.dataset}_no_slot_checkpoint.pth", map_location="cpu")
+            new_state_dict = OrderedDict((k[9:], v) for k, v in checkpoint["model"].items())  # strip `backbone.`
+            bone.load_state_dict(new_state_dict)
+            print("load pre dataset parameter over")
+        if not args.grad:                                                 # :34-40 ('res' family)
+            if "res" in args.model:
+                bone.global_pool = Identical()
+                bone.fc = Identical()
+            else:
+                raise NotImplementedError(f"head stripping for {args.model} (only the 'res*' family is implemented)")
+    return bone
+
+
+class _ShapeState:
+    """Everything bound to one (B,Cin,H,W,device): plan arena, head workspace, outputs, optional graph."""
+    pass
+
+
+class SlotModel(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.use_slot = args.use_slot
+        self.backbone = load_backbone(args)
+        if self.use_slot:
+            self.feature_size = 8 if "densenet" in args.model else 9     # informational; see module docstring
+            self.channel = args.channel
+            self.slots_per_class = args.slots_per_class
+            self.conv1x1 = nn.Conv2d(self.channel, args.hidden_dim, kernel_size=(1, 1), stride=(1, 1))
+            if args.pre_trained:
+                self.dfs_freeze(self.backbone, args.freeze_layers)
+            self.slot = SlotAttention(args.num_classes, self.slots_per_class, args.hidden_dim, vis=args.vis,
+                                      vis_id=args.vis_id, loss_status=args.loss_status, power=args.power,
+                                      to_k_layer=args.to_k_layer)
+            self.position_emb = build_position_encoding("sine", hidden_dim=args.hidden_dim)
+            self.lambda_value = float(args.lambda_value)
+        else:
+            if args.pre_trained:
+                self.dfs_freeze(self.backbone, args.freeze_layers)
+        self.num_classes = args.num_classes
+        self.math = None              # None -> scouter_b200.default_math()
+        self.use_cuda_graph = False
+        self.keep_attn = False        # retain the final attention maps in .last_attn (first-class output)
+        self.last_attn = None
+        self._states = OrderedDict()
+        self._prog = None
+        self._sig = None
+
+    # -- reference helpers (slot_model.py:79-103) -----------------------------------------------
+    def dfs_freeze(self, model, freeze_layer_num):
+        if freeze_layer_num == 0:
+            return
+        unfreeze_layers = ["layer4", "layer3", "layer2", "layer1"][:4 - freeze_layer_num]
+        for name, child in model.named_children():
+            if any(u in name for u in unfreeze_layers):
+                continue
+            for param in child.parameters():
+                param.requires_grad = False
+            self.dfs_freeze(child, freeze_layer_num)
+
+    def dfs_freeze_bnorm(self, model):
+        for name, child in model.named_children():
+            if "bn" not in name:
+                self.dfs_freeze_bnorm(child)
+                continue
+            for param in child.parameters():
+                param.requires_grad = False
+            self.dfs_freeze_bnorm(child)
+
+    # -- compiled state -------------------------------------------------------------------------
+    def _math(self):
+        from . import default_math
+        return default_math() if self.math is None else self.math
+
+    def _program(self):
+        sig = (_version_signature(self.backbone), self._math())
+        if self._prog is None or sig != self._sig:
+            prog, feat = lower_backbone(self.backbone)
+            self._prog = (prog, feat)
+            self._sig = sig
+            self._states.clear()
+        return self._prog
+
+    def _state(self, x) -> _ShapeState:
+        prog, feat = self._program()
+        key = (tuple(x.shape), x.device, self.keep_attn or self.slot.vis)
+        st = self._states.get(key)
+        if st is not None:
+            self._states.move_to_end(key)
+            return st
+        b, cin, h, w = x.shape
+        dev = x.device
+        st = _ShapeState()
+        st.cp = CompiledProgram(prog, self._math())
+        st.cp.bind(b, cin, h, w, dev)
+        st.feat_buf = feat
+        _, fh, fw, fc = st.cp.buffer_shape(feat)
+        if fc != self.channel:
+            raise L.ScouterError(f"SlotModel: backbone produces {fc} channels but args.channel={self.channel} "
+                                 "(the reference's x.view(B, channel, fs, fs) would fail the same way)")
+        st.fh, st.fw, st.n = fh, fw, fh * fw
+        s, c = self.slot.num_slots, self.slot.num_classes
+        f32 = dict(dtype=torch.float32, device=dev)
+        st.logits = torch.empty(b, c, **f32)
+        st.log_probs = torch.empty(b, c, **f32)
+        st.attn_sum = torch.empty(b, **f32)
+        st.losses = torch.zeros(3, **f32)
+        st.attn = torch.empty(b, s, st.n, **f32) if key[2] else None
+        st.pe = self.position_emb.table(fh, fw, dev)
+        io = L.HeadIO()
+        io.batch, io.h, io.w, io.channel = b, fh, fw, self.channel
+        io.layout, io.math = L.LAYOUT_NHWC, self._math()
+        off = L.lib().scouter_plan_buffer_offset(st.cp.handle, feat)
+        io.feat = st.cp.arena_ptr + off
+        io.pe = st.pe.data_ptr()
+        io.logits, io.attn, io.attn_sum, io.x_out = st.logits.data_ptr(), L.ptr(st.attn), st.attn_sum.data_ptr(), 0
+        st.io = io
+        st.ws = None
+        st.ws_bytes = 0
+        st.graph = None
+        st.static_in = None
+        self._states[key] = st
+        while len(self._states) > 4:
+            self._states.popitem(last=False)
+        return st
+
+    def _head_params(self, st, dev):
+        """Refresh the parameter pointers in the head io block (cheap; parameters may be re-assigned)."""
+        for p in (self.conv1x1.weight, self.conv1x1.bias):
+            if p.device != dev or p.dtype != torch.float32 or not p.is_contiguous():
+                raise L.ScouterError("SlotModel: conv1x1 parameters must be contiguous fp32 on the input's device")
+        st.io.conv_w = self.conv1x1.weight.data_ptr()
+        st.io.conv_b = self.conv1x1.bias.data_ptr()
+        desc, packed = self.slot.desc_and_pack(dev)
+        if st.ws is None:
+            nbytes = L.lib().scouter_head_workspace_bytes(C.byref(desc), C.byref(st.io))
+            st.ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            st.ws_off = (-st.ws.data_ptr()) % 1024
+            st.ws_bytes = nbytes
+        return desc, packed
+
+    def _launch(self, st, x, target):
+        """Enqueue backbone program + head + finalize on the current stream (no sync, graph-capturable)."""
+        desc, packed = self._head_params(st, x.device)
+        st.cp.run(x)
+        lib = L.lib()
+        L.check(lib.scouter_head_forward(C.byref(desc), packed.data_ptr(), C.byref(st.io), st.ws.data_ptr() + st.ws_off,
+                                         st.ws_bytes, L.stream_ptr()), "scouter_head_forward")
+        L.check(lib.scouter_head_finalize(st.logits.data_ptr(), st.attn_sum.data_ptr(), L.ptr(target), x.shape[0],
+                                          self.slot.num_classes, self.slot.num_slots, st.n, float(self.slot.power),
+                                          self.lambda_value, st.log_probs.data_ptr(), st.losses.data_ptr(), L.stream_ptr()),
+                "scouter_head_finalize")
+
+    def launches_per_forward(self, x_shape, device="cuda") -> int:
+        """Kernel launches one forward issues (bench.py's gpu_launches)."""
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            st = self._state(_MetaLike(x_shape, dev))
+        return st.cp.launches + 3    # + conv1x1 projection, xSlot loop, finalize
+
+    # -- forward --------------------------------------------------------------------------------
+    def forward(self, x, target=None):
+        _require_cuda(x, "SlotModel")
+        _check_inference(self, "SlotModel")
+        x = x.contiguous()
+        if not self.use_slot:
+            return self._forward_no_slot(x, target)
+        with torch.cuda.device(x.device):
+            st = self._state(x)
+            self.feature_size = st.fh
+            if target is not None:
+                target = target.to(device=x.device, dtype=torch.int64).contiguous()
+            if self.use_cuda_graph and target is None:
+                self._replay(st, x)
+            else:
+                self._launch(st, x, target)
+            output = st.log_probs.clone()
+            if st.attn is not None:
+                self.last_attn = st.attn
+                self.slot.last_attn = st.attn
+            if self.slot.vis:
+                self.slot.emit_vis(st.attn, st.logits)
+            if target is not None:
+                ls = st.losses.clone()
+                return [output, [ls[0], ls[1], ls[2]]]
+            return output
+
+    def _replay(self, st, x):
+        if st.graph is None:
+            st.static_in = x.clone()
+            self._launch(st, st.static_in, None)          # warm-up outside capture (lazy module init, attributes)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(st, st.static_in, None)
+            st.graph = g
+        if x.data_ptr() != st.static_in.data_ptr():
+            st.static_in.copy_(x)
+        st.graph.replay()
+
+    def _forward_no_slot(self, x, target):
+        logits = self.backbone(x)                                          # (B, num_classes)
+        b, c = logits.shape
+        out = torch.empty_like(logits)
+        losses = torch.zeros(3, dtype=torch.float32, device=x.device)
+        tgt = None if target is None else target.to(device=x.device, dtype=torch.int64).contiguous()
+        with torch.cuda.device(x.device):
+            L.check(L.lib().scouter_head_finalize(logits.data_ptr(), 0, L.ptr(tgt), b, c, 1, 1, 1.0, 0.0, out.data_ptr(),
+                                                  losses.data_ptr(), L.stream_ptr()), "scouter_head_finalize")
+        if target is not None:
+            return [out, [losses[1]]]
+        return out
+
+    # -- end-to-end from host memory (bench.py e2e; engine.py:25-30 in one C call) ------------------
+    def forward_host(self, x_host: torch.Tensor, device="cuda") -> torch.Tensor:
+        """``x_host``: pinned fp32 (B,Cin,H,W) CPU tensor.  Returns pinned (B,C) log-probs, valid on return."""
+        if x_host.is_cuda or x_host.dtype != torch.float32 or not x_host.is_contiguous():
+            raise L.ScouterError("forward_host: expects a contiguous fp32 host tensor")
+        _check_inference(self, "SlotModel")
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            st = self._state(_MetaLike(x_host.shape, dev))
+            if st.static_in is None:
+                st.static_in = torch.empty(x_host.shape, dtype=torch.float32, device=dev)
+            if getattr(st, "host_out", None) is None:
+                st.host_out = torch.empty(st.log_probs.shape, dtype=torch.float32).pin_memory()
+                st.host_losses = torch.empty(3, dtype=torch.float32).pin_memory()
+            desc, packed = self._head_params(st, dev)
+            a = L.ForwardHostArgs()
+            a.plan = st.cp.handle
+            a.desc = C.pointer(desc)
+            a.packed = packed.data_ptr()
+            a.head = st.io
+            a.feat_buffer = st.feat_buf
+            a.input_host = x_host.data_ptr()
+            a.input_dev = st.static_in.data_ptr()
+            a.input_bytes = x_host.numel() * 4
+            a.arena, a.arena_bytes = st.cp.arena_ptr, st.cp.arena_bytes
+            a.head_workspace, a.head_workspace_bytes = st.ws.data_ptr() + st.ws_off, st.ws_bytes
+            a.target_dev = 0
+            a.lambda_value = self.lambda_value
+            a.log_probs_dev, a.losses_dev = st.log_probs.data_ptr(), st.losses.data_ptr()
+            a.log_probs_host, a.losses_host = st.host_out.data_ptr(), st.host_losses.data_ptr()
+            a.stream = L.stream_ptr()
+            L.check(L.lib().scouter_forward_host(C.byref(a)), "scouter_forward_host")
+            return st.host_out
+
+
+class _MetaLike:
+    """Shape/device carrier so ``_state`` can be keyed without allocating a device batch."""
+
+    def __init__(self, shape, device):
+        self.shape = torch.Size(shape)
+        self.device = device

@@ -1,0 +1,51 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"])) if "meta" in z.files else {}
+    return z, meta
+
+
+def golden_names(kind):
+    out = []
+    for f in sorted(os.listdir(GOLDEN)):
+        if f.endswith(".npz") and f != "pe_sine.npz":
+            if (kind == "head") == f.startswith("head_"):
+                out.append(f[:-4])
+    return out
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Build libscouter_b200.so once if it is absent (nvcc cross-compiles without a GPU)."""
+    import shutil
+    from scouter_b200 import _lib
+    if shutil.which("nvcc") or not os.path.exists(_lib.LIB_PATH):
+        _lib.build()          # no-op when the .so is newer than every source
+    yield
+
+
+def model_args(meta_args):
+    from oracle.refshim import make_args
+    return make_args(**meta_args)
+
+
+def rel_err(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

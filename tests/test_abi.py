@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library builds, loads and exports exactly what include/scouter_b200.h declares."""
+import ctypes
+import re
+
+from scouter_b200 import _lib as L
+
+
+def declared_functions():
+    src = open("include/scouter_b200.h").read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(scouter_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_functions() == sorted(L.SIGNATURES)
+
+
+def test_library_loads_and_exports_every_symbol():
+    lib = L.lib()
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+    assert lib.scouter_abi_version() == 1
+
+
+def test_argument_errors_without_gpu():
+    lib = L.lib()
+    assert lib.scouter_pe_sine(0, 64, 7, 7, 0) == -1
+    assert b"pe_sine" in lib.scouter_last_error()
+    d = L.XSlotDesc()
+    d.d = 32
+    assert lib.scouter_xslot_packed_bytes(ctypes.byref(d)) == 0            # hidden dim 32 unsupported
+    assert b"hidden dim" in lib.scouter_last_error()
+    h = ctypes.c_void_p()
+    assert lib.scouter_plan_create(None, 0, 0, 0, ctypes.byref(h)) == -1
+
+
+def test_plan_shape_inference_on_cpu():
+    """Shape inference and arena placement are host code: check both geometries without a GPU."""
+    import scouter_b200 as sb
+    from oracle.refshim import make_args
+    from scouter_b200.plan import CompiledProgram, lower_backbone
+    m = sb.SlotModel(make_args())
+    prog, feat = lower_backbone(m.backbone)
+    for p in prog.ops:   # weights are CPU tensors here; only pointers are recorded, nothing is launched
+        pass
+    cp = CompiledProgram(prog, L.MATH_FP32)
+    for size, fs in ((224, 7), (260, 9)):
+        L.check(L.lib().scouter_plan_bind(cp.handle, 4, 3, size, size))
+        s = (ctypes.c_int32 * 4)()
+        L.check(L.lib().scouter_plan_buffer_shape(cp.handle, feat, ctypes.byref(s)))
+        assert tuple(s) == (4, fs, fs, 2048)
+        assert L.lib().scouter_plan_arena_bytes(cp.handle) > 0
+        assert L.lib().scouter_plan_launch_count(cp.handle) == len(prog.ops)

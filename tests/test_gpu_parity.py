@@ -1,0 +1,224 @@
+"""GPU (-m gpu): parity of the CUDA path -- called through the C ABI via the module mirror -- against
+(a) the goldens dumped from the unmodified reference and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star: 1e-3 relative, fp32):
+  logits / log-probs : max|a-b| <= TOL * max(1, max|b|)   (SURVEY.md C.3 acceptance (i); TOL below)
+  attention maps     : abs <= max(1e-3, 4 x the reference's own fp32-vs-fp64 floor)   (acceptance (ii))
+The exact-fp32 mode (SCOUTER_MATH_FP32) is held to 2e-5; the tensor-core mode to 1e-3.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_err
+from oracle import head as oh
+from oracle.make_golden import head_inputs
+from oracle.refshim import make_args
+import scouter_b200 as sb
+from scouter_b200 import _lib as L
+from scouter_b200.synth import fill_state_dict, synth_images
+
+pytestmark = pytest.mark.gpu
+TOL = {L.MATH_FP32: 2e-5, L.MATH_TC: 1e-3}
+MATHS = [L.MATH_FP32, L.MATH_TC]
+
+
+def scaled_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    L.check(L.lib().scouter_device_check(0))
+    return torch.device("cuda", 0)
+
+
+def test_pe_table(dev):
+    z = np.load("tests/golden/pe_sine.npz")
+    pe = sb.build_position_encoding("sine", 64)
+    for k in z.files:
+        h, w = map(int, k[3:].split("x"))
+        got = pe(torch.zeros(2, 64, h, w, device=dev))
+        assert got.shape == (2, 64, h, w)
+        assert float((got[1].cpu() - torch.from_numpy(z[k])).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("name", golden_names("head"))
+def test_slot_attention_vs_reference_golden(dev, name):
+    z, meta = load_golden(name)
+    c = meta["case"]
+    m = sb.SlotAttention(c["C"], c["spc"], 64, loss_status=c["ls"], power=c["power"], to_k_layer=c["L"])
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=3))
+    m = m.to(dev).eval()
+    m.keep_attn = True
+    x_pe, x = head_inputs(c)
+    with torch.no_grad():
+        logits, loss = m(x_pe.to(dev), x.to(dev))
+    floor = rel_err(z["logits"], z["logits64"])
+    assert scaled_err(logits, z["logits"]) < max(2e-5, 20 * floor)
+    afloor = float(np.abs(z["attn"] - z["attn64"]).max())
+    assert float((m.last_attn.cpu() - torch.from_numpy(z["attn"])).abs().max()) < max(2e-5, 20 * afloor)
+    assert abs(float(loss) - float(z["loss"])) < 1e-5
+
+
+def test_slot_attention_permuted_views_like_slot_model(dev):
+    """The reference passes (B,n,d) permute-views of (B,d,n) memory (slot_model.py:113-115)."""
+    z, meta = load_golden("head_s10_n81_l3")
+    c = meta["case"]
+    m = sb.SlotAttention(c["C"], c["spc"], 64, loss_status=c["ls"], power=c["power"], to_k_layer=c["L"])
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=3))
+    m = m.to(dev).eval()
+    x_pe, x = head_inputs(c)
+    xp = x_pe.to(dev).permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    xx = x.to(dev).permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    assert not xp.is_contiguous()
+    with torch.no_grad():
+        logits, _ = m(xp, xx)
+    assert scaled_err(logits, z["logits"]) < 2e-5
+
+
+def test_vis_maps_u8(dev):
+    z, meta = load_golden("head_s90_spc3_n81")
+    c = meta["case"]
+    attn = torch.from_numpy(z["attn"]).to(dev)
+    maps = torch.empty(c["C"], c["n"], dtype=torch.uint8, device=dev)
+    L.check(L.lib().scouter_vis_maps_u8(attn.data_ptr(), attn.shape[0], c["C"], c["spc"], c["n"], 0, maps.data_ptr(), 0))
+    got = maps.cpu().numpy().reshape(c["C"], 9, 9).astype(np.int32)
+    ref = z["vis"].astype(np.int32)
+    assert np.abs(got - ref).max() <= 1 and (got != ref).mean() < 0.01     # truncation: off-by-one at exact ties only
+
+
+def build(meta, dev, math):
+    m = sb.SlotModel(make_args(**meta["args"]))
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=0))
+    m = m.to(dev).eval()
+    m.math = math
+    m.keep_attn = True
+    return m
+
+
+@pytest.mark.parametrize("math", MATHS)
+@pytest.mark.parametrize("name", golden_names("model"))
+def test_slot_model_vs_reference_golden(dev, name, math):
+    z, meta = load_golden(name)
+    m = build(meta, dev, math)
+    x = synth_images(meta["batch"], meta["cin"], meta["size"], meta["size"]).to(dev)
+    tgt = torch.from_numpy(z["target"]).to(dev)
+    with torch.no_grad():
+        out, (loss, nll, attn_loss) = m(x, tgt)
+        out2 = m(x)
+    tol = TOL[math]
+    assert m.feature_size == meta["fs"]
+    assert torch.equal(out, out2)
+    e_lp = scaled_err(out, z["log_probs"])
+    afloor = 0.0
+    e_at = float((m.last_attn.cpu() - torch.from_numpy(z["attn"])).abs().max())
+    print(f"{name} math={math}: log_probs err {e_lp:.2e} attn err {e_at:.2e} "
+          f"(reference fp32-vs-fp64 floor {rel_err(z['log_probs'], z['log_probs64']):.2e})")
+    assert e_lp < tol
+    assert e_at < max(tol, 4 * afloor)
+    got = np.array([float(loss), float(nll), float(attn_loss)])
+    assert np.allclose(got, z["losses"], rtol=5 * tol, atol=5 * tol)
+
+
+@pytest.mark.parametrize("math", MATHS)
+def test_backbone_features_vs_golden(dev, math):
+    """backbone(x) standalone returns the reference's NCHW-flattened features (resnet.py:503-509)."""
+    z, meta = load_golden("cfg2_resnest26d_pos_224")
+    m = build(meta, dev, math)
+    m.backbone._runner = None
+    x = synth_images(meta["batch"], meta["cin"], meta["size"], meta["size"]).to(dev)
+    from scouter_b200.plan import BackboneRunner
+    object.__setattr__(m.backbone, "_runner", BackboneRunner(m.backbone, math))
+    with torch.no_grad():
+        f = m.backbone(x)
+    f = f.view(meta["batch"], 2048, 7, 7)[:, ::64].cpu()
+    ref = torch.from_numpy(z["feat_sample"])
+    err = float((f - ref).abs().max() / ref.abs().max())
+    print(f"backbone features math={math}: max err / max|ref| = {err:.2e}")
+    assert err < (1e-5 if math == L.MATH_FP32 else 2e-3)
+
+
+@pytest.mark.parametrize("math", MATHS)
+def test_slot_model_vs_cpu_oracle_fresh_inputs(dev, math):
+    """Same seeded inputs through the CPU oracle and the CUDA path (not a stored vector)."""
+    from oracle import backbone as ob
+    a = dict(model="resnest26d", num_classes=10, slots_per_class=1, power=2, to_k_layer=3, loss_status=1, channel=2048)
+    m = build(dict(args=a), dev, math)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    x = synth_images(2, 3, 192, 160, seed=99)            # non-square, neither 224 nor 260 (D6: any geometry)
+    o = ob.slot_model_forward("resnest26d", sd, x, num_classes=10, slots_per_class=1, loss_status=1, power=2,
+                              return_attn=True)
+    with torch.no_grad():
+        out = m(x.to(dev))
+    assert scaled_err(out, o["log_probs"]) < TOL[math]
+    assert float((m.last_attn.cpu() - o["attn"]).abs().max()) < max(TOL[math], 1e-4)
+
+
+def test_no_slot_classifier_path(dev):
+    from oracle import backbone as ob
+    import torch.nn.functional as F
+    a = make_args(use_slot=False, model="resnet18", dataset="MNIST", num_classes=10)
+    m = sb.SlotModel(a)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=0))
+    m = m.to(dev).eval()
+    m.backbone._runner = None
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    x = synth_images(3, 1, 130, 130, seed=5)
+    feat = ob.resnet18_features(sd, x)
+    logits = feat.mean((2, 3)) @ sd["backbone.fc.weight"].t() + sd["backbone.fc.bias"]
+    ref = F.log_softmax(logits, dim=1)
+    tgt = torch.tensor([1, 2, 3])
+    import os
+    os.environ["SCOUTER_MATH"] = "fp32"
+    try:
+        with torch.no_grad():
+            out, (loss,) = m(x.to(dev), tgt.to(dev))
+    finally:
+        os.environ.pop("SCOUTER_MATH")
+    assert scaled_err(out, ref) < 2e-5
+    assert abs(float(loss) - float(F.nll_loss(ref, tgt))) < 1e-4
+
+
+def test_forward_host_and_cuda_graph_agree_with_eager(dev):
+    z, meta = load_golden("cfg2_resnest26d_pos_224")
+    m = build(meta, dev, L.MATH_TC)
+    m.keep_attn = False
+    x = synth_images(meta["batch"], meta["cin"], meta["size"], meta["size"])
+    with torch.no_grad():
+        eager = m(x.to(dev)).cpu()
+        host = m.forward_host(x.pin_memory()).clone()
+        m.use_cuda_graph = True
+        g1 = m(x.to(dev)).cpu()
+        g2 = m(x.to(dev)).cpu()
+    assert torch.equal(eager, host) and torch.equal(eager, g1) and torch.equal(g1, g2)
+
+
+def test_training_mode_raises_not_falls_back(dev):
+    m = sb.SlotModel(make_args()).to(dev).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 224, 224, device=dev))
+
+
+def test_full_size_properties_cfg3(dev):
+    """BASELINE size (B=256, 224^2): size-independent properties instead of a stored vector --
+    batch-order equivariance, log-probs normalise, per-image results independent of batch mates."""
+    z, meta = load_golden("cfg3_resnest26d_neg_224")
+    m = build(meta, dev, L.MATH_TC)
+    m.keep_attn = False
+    g = torch.Generator(device=dev).manual_seed(1234)
+    x = torch.randn(256, 3, 224, 224, device=dev, generator=g)
+    small = synth_images(meta["batch"], 3, 224, 224).to(dev)
+    x[:meta["batch"]] = small
+    with torch.no_grad():
+        out = m(x)
+        perm = torch.randperm(256, device=dev)
+        out_p = m(x[perm].contiguous())
+    assert torch.isfinite(out).all()
+    assert float((out.exp().sum(1) - 1).abs().max()) < 1e-4
+    assert torch.equal(out[perm], out_p)                                   # bitwise: no cross-image coupling
+    assert scaled_err(out[:meta["batch"]], z["log_probs"]) < 1e-3          # golden images inside a big batch

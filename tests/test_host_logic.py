@@ -1,0 +1,101 @@
+"""CPU: host-side mirror of the reference module API -- state_dict contract, constructor arguments,
+error behaviour, op-program lowering.  No compute calls (there is no GPU here)."""
+import json
+import re
+
+import pytest
+import torch
+from torch import nn
+
+import scouter_b200 as sb
+from oracle.refshim import make_args
+from scouter_b200 import _lib as L
+from scouter_b200.plan import fold_conv_bn, lower_backbone
+from scouter_b200.synth import fill_state_dict
+
+KEYS = json.load(open("tests/golden/state_dict_keys.json"))
+CASES = {
+    "cfg1_mnist_resnet18_260": dict(model="resnet18", dataset="MNIST", channel=512, num_classes=10, slots_per_class=1,
+                                    power=1, to_k_layer=1),
+    "cfg2_resnest26d_pos_224": dict(),
+    "cfg5_cub200x2_224": dict(num_classes=200, slots_per_class=2),
+    "no_slot_resnest26d": dict(use_slot=False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_state_dict_keys_and_shapes_match_reference(name):
+    m = sb.SlotModel(make_args(**CASES[name]))
+    got = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert got == KEYS[name]
+    assert list(got) == list(KEYS[name])            # same order too
+
+
+def test_param_counts():
+    m = sb.SlotModel(make_args())
+    assert sum(p.numel() for p in m.parameters()) == 15193824          # 15.194 M
+    assert sum(p.numel() for n, p in m.named_parameters() if not n.startswith("backbone.")) == 173376
+    m = sb.SlotModel(make_args(**CASES["cfg1_mnist_resnet18_260"]))
+    assert sum(p.numel() for p in m.parameters()) == 11234432
+
+
+def test_attributes_and_aliases():
+    m = sb.SlotModel(make_args())
+    for a in ("backbone", "conv1x1", "slot", "position_emb", "use_slot", "channel", "slots_per_class", "feature_size",
+              "lambda_value"):
+        assert hasattr(m, a)
+    assert sb.ScouterAttention is sb.SlotAttention
+    assert isinstance(m.backbone.global_pool, sb.Identical) and isinstance(m.backbone.fc, sb.Identical)
+    assert m.slot.num_slots == 10 and m.slot.scale == 0.125
+    # to_q is constructed but unused, like the reference (slot_attention.py:27-29, 52-53)
+    assert "slot.to_q.0.weight" in m.state_dict()
+
+
+def test_synthetic_state_dict_roundtrip_is_strict():
+    m = sb.SlotModel(make_args())
+    sd = fill_state_dict(m.state_dict(), seed=0)
+    m.load_state_dict(sd, strict=True)
+    sd2 = fill_state_dict(m.state_dict(), seed=0)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)               # deterministic in (name, shape, seed)
+
+
+def test_dfs_freeze_matches_reference_semantics():
+    m = sb.SlotModel(make_args())
+    m.dfs_freeze(m.backbone, 2)                                       # layer4, layer3 stay trainable
+    assert all(p.requires_grad for p in m.backbone.layer4.parameters())
+    assert not any(p.requires_grad for p in m.backbone.layer1.parameters())
+    assert not any(p.requires_grad for p in m.backbone.conv1.parameters())
+
+
+def test_errors_are_loud_not_fallbacks():
+    m = sb.SlotModel(make_args()).eval()
+    with pytest.raises(sb.ScouterError):                              # CPU tensors: no CPU path
+        m(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(RuntimeError):
+        sb.create_model("densenet121")
+    with pytest.raises(RuntimeError):
+        sb.create_model("resnest26d", pretrained=True)
+    with pytest.raises(ValueError):
+        sb.build_position_encoding("nope", 64)
+
+
+def test_bn_folding_matches_conv_bn():
+    torch.manual_seed(0)
+    conv = nn.Conv2d(8, 6, 3, padding=1, groups=2, bias=True)
+    bn = nn.BatchNorm2d(6).eval()
+    bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2); bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_()
+    x = torch.randn(2, 8, 5, 5)
+    w, b = fold_conv_bn(conv, bn)
+    y = torch.nn.functional.conv2d(x, w.permute(0, 3, 1, 2), b, padding=1, groups=2)
+    assert torch.allclose(y, bn(conv(x)), atol=1e-5)
+
+
+def test_lowering_op_counts_resnest26d():
+    m = sb.SlotModel(make_args())
+    prog, feat = lower_backbone(m.backbone)
+    kinds = [o.kind for o in prog.ops]
+    # 47 convs in the backbone = 3 stem + 8*(conv1, conv2.conv, conv3) + 4 shortcuts + 16 fc1/fc2
+    assert kinds.count(L.OP_STEM_CONV) == 1 and kinds.count(L.OP_CONV) == 2 + 24 + 4
+    assert kinds.count(L.OP_SPLAT_FC) == 8 and kinds.count(L.OP_SPLAT_GAP) == 8 and kinds.count(L.OP_SPLAT_APPLY) == 8
+    assert kinds.count(L.OP_MAXPOOL) == 1 and kinds.count(L.OP_AVGPOOL) == 3
+    assert feat == prog.ops[-1].dst

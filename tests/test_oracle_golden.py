@@ -1,0 +1,59 @@
+"""CPU: the oracle restatement reproduces the goldens dumped from the unmodified reference
+(oracle/make_golden.py).  This is what pins the oracle -- the reference has no tests of its own."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_err
+from oracle import backbone as ob
+from oracle import head as oh
+from oracle.make_golden import head_inputs
+from scouter_b200.synth import fill_state_dict, synth_images
+import scouter_b200 as sb
+from oracle.refshim import make_args
+
+
+def test_pe_table_matches_reference():
+    z = np.load("tests/golden/pe_sine.npz")
+    for k in z.files:
+        h, w = map(int, k[3:].split("x"))
+        assert float(np.abs(oh.sine_pe(64, h, w).numpy() - z[k]).max()) < 1e-6
+
+
+@pytest.mark.parametrize("name", golden_names("head"))
+def test_head_oracle_vs_reference_golden(name):
+    z, meta = load_golden(name)
+    c = meta["case"]
+    m = sb.SlotAttention(c["C"], c["spc"], 64, loss_status=c["ls"], power=c["power"], to_k_layer=c["L"])
+    sd = fill_state_dict(m.state_dict(), seed=3)
+    x_pe, x = head_inputs(c)
+    logits, loss, attn = oh.xslot_forward(sd, x_pe, x, num_classes=c["C"], slots_per_class=c["spc"], loss_status=c["ls"],
+                                          power=c["power"], return_attn=True)
+    floor = rel_err(z["logits"], z["logits64"])
+    assert rel_err(logits, z["logits"]) < max(1e-5, 20 * floor)
+    assert abs(float(loss) - float(z["loss"])) < 1e-5
+    afloor = float(np.abs(z["attn"] - z["attn64"]).max())
+    assert float((attn - torch.from_numpy(z["attn"])).abs().max()) < max(1e-5, 20 * afloor)
+    if z["vis"].size:
+        v = oh.vis_maps_u8(torch.from_numpy(z["attn"]), num_classes=c["C"], slots_per_class=c["spc"])
+        assert np.array_equal(v, z["vis"])
+
+
+@pytest.mark.parametrize("name", golden_names("model"))
+def test_model_oracle_vs_reference_golden(name):
+    z, meta = load_golden(name)
+    a = meta["args"]
+    m = sb.SlotModel(make_args(**a))
+    sd = fill_state_dict(m.state_dict(), seed=0)
+    x = synth_images(meta["batch"], meta["cin"], meta["size"], meta["size"])
+    tgt = torch.from_numpy(z["target"])
+    o = ob.slot_model_forward(a["model"], sd, x, num_classes=a["num_classes"], slots_per_class=a["slots_per_class"],
+                              loss_status=a["loss_status"], power=a["power"], lambda_value=a["lambda_value"], target=tgt,
+                              return_attn=True)
+    feat = ob.backbone_features(a["model"], sd, x)
+    assert rel_err(feat[:, ::64], z["feat_sample"]) < 1e-5
+    assert rel_err(o["logits"], z["logits"]) < 1e-4
+    assert rel_err(o["log_probs"], z["log_probs"]) < 1e-4
+    assert float((o["attn"] - torch.from_numpy(z["attn"])).abs().max()) < 1e-3
+    got = np.array([float(o["loss"]), float(o["nll"]), float(o["attn_loss"])])
+    assert np.allclose(got, z["losses"], rtol=1e-4, atol=1e-5)
