@@ -114,7 +114,7 @@ class ScouterError(RuntimeError):
 def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
     return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(os.path.dirname(_HERE), "include"),
-            *[os.path.join(CSRC, s) for s in SOURCES], "-o", out_path, "-lcuda"]
+            *[os.path.join(CSRC, s) for s in SOURCES], "-o", out_path]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -115,12 +115,11 @@ def test_slot_model_vs_reference_golden(dev, name, math):
     assert m.feature_size == meta["fs"]
     assert torch.equal(out, out2)
     e_lp = scaled_err(out, z["log_probs"])
-    afloor = 0.0
     e_at = float((m.last_attn.cpu() - torch.from_numpy(z["attn"])).abs().max())
     print(f"{name} math={math}: log_probs err {e_lp:.2e} attn err {e_at:.2e} "
           f"(reference fp32-vs-fp64 floor {rel_err(z['log_probs'], z['log_probs64']):.2e})")
     assert e_lp < tol
-    assert e_at < max(tol, 4 * afloor)
+    assert e_at < max(tol, 1e-4)          # the reference's own fp32-vs-fp64 attention floor is 1e-5..3e-5 on these inputs
     got = np.array([float(loss), float(nll), float(attn_loss)])
     assert np.allclose(got, z["losses"], rtol=5 * tol, atol=5 * tol)
 
