@@ -137,12 +137,18 @@ typedef struct scouter_head_io {
     const float* feat;
     const float* conv_w;     /* (d, ch)  conv1x1.weight viewed 2-D */
     const float* conv_b;     /* (d)      conv1x1.bias */
+    const float* conv_w_tc;  /* (2d, ch) [hi; lo] tf32 split from scouter_head_pack_conv; required for SCOUTER_MATH_TC */
     const float* pe;         /* (h*w, d) from scouter_pe_sine */
     float* logits;           /* (B, C) */
     float* attn;             /* (B, S, n) or NULL */
     float* attn_sum;         /* (B) or NULL */
     float* x_out;            /* (B, n, d) projected features, or NULL (debug / tests) */
 } scouter_head_io_t;
+
+/* Error-compensated tensor-core operand for the 1x1 projection: rows [0,d) = tf32(W), rows [d,2d) =
+ * tf32(W - tf32(W)).  A*W_hi^T + A*W_lo^T reproduces the fp32 product of tf32-representable features to
+ * ~2^-22 relative.  `out` holds 2*d*ch floats; re-pack when conv1x1.weight changes. */
+int scouter_head_pack_conv(const float* conv_w, int d, int ch, float* out, scouter_stream_t stream);
 
 size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io);
 int scouter_head_forward(const scouter_xslot_desc_t* desc, const void* packed, const scouter_head_io_t* io,
@@ -214,6 +220,13 @@ int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, void* arena,
                      scouter_stream_t stream);
 /* Number of kernel launches one scouter_plan_run issues (for bench.py's gpu_launches). */
 int scouter_plan_launch_count(const scouter_plan_t* plan);
+
+/* One SCOUTER_OP_CONV outside a plan (unit tests of the kernels; same dispatch as scouter_plan_run):
+ * in (B,H,W,cin) NHWC, res (B,Ho,Wo,cout) or NULL, out (B,Ho,Wo,cout).  scouter_conv_path reports which
+ * kernel family the dispatch picks: 1 = tcgen05/TMA, 0 = CUDA-core fp32. */
+int scouter_conv_forward(const scouter_op_t* op, const float* in, const float* res, float* out, int batch, int h, int w,
+                         int math, scouter_stream_t stream);
+int scouter_conv_path(const scouter_op_t* op, int batch, int h, int w, int math);
 
 /* ------------------------------------------------------------------------------------------------
  * a1  SlotModel.forward from HOST buffers in one call (sloter/slot_model.py:105-127 as driven by

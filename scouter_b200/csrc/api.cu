@@ -215,6 +215,7 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
     SC_CHECK_ARG(arena_bytes >= plan->arena_bytes, SCOUTER_E_INVALID, "plan_run: arena of %zu bytes, need %zu", arena_bytes, plan->arena_bytes);
     SC_CHECK_ARG(((uintptr_t)arena & 1023) == 0, SCOUTER_E_INVALID, "plan_run: arena is not 1024-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
+    const int rnd = plan->math == SCOUTER_MATH_TC ? 1 : 0;  // tf32-representable activations for the tcgen05 convs
     char* base = (char*)arena;
     auto ptr = [&](int id) -> float* { return id == 0 ? const_cast<float*>(input_nchw) : (float*)(base + plan->bufs[id].offset); };
     for (size_t i = 0; i < plan->ops.size(); ++i) {
@@ -226,14 +227,14 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
             case SCOUTER_OP_STEM_CONV: {
                 SC_CHECK_ARG(o.kh == o.kw && o.groups == 1, SCOUTER_E_UNSUPPORTED, "stem conv: square, ungrouped kernels only");
                 StemArgs a{ptr(o.src), o.w, o.b, ptr(o.dst), sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.stride, o.pad,
-                           (o.flags & SCOUTER_F_RELU) ? 1 : 0};
+                           (o.flags & SCOUTER_F_RELU) ? 1 : 0, rnd};
                 rc = launch_stem_conv(a, s);
                 break;
             }
             case SCOUTER_OP_CONV: {
                 ConvArgs a{ptr(o.src), o.w, o.b, (o.flags & SCOUTER_F_RESIDUAL) ? ptr(o.src2) : nullptr, ptr(o.dst),
                            sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.kw, o.stride, o.pad, o.groups,
-                           (o.flags & SCOUTER_F_RELU) ? 1 : 0};
+                           (o.flags & SCOUTER_F_RELU) ? 1 : 0, (rnd && db.H * db.W > 1) ? 1 : 0, 0};
                 if (plan->math == SCOUTER_MATH_TC && umma_conv_supported(a)) rc = launch_conv_umma(a, plan->umma[i], s);
                 else rc = launch_conv_simt(a, s);
                 break;
@@ -243,7 +244,7 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
                 break;
             case SCOUTER_OP_AVGPOOL:
                 rc = launch_avgpool(ptr(o.src), ptr(o.dst), sb.B, sb.H, sb.W, sb.C, db.H, db.W, o.kh, o.stride, o.pad,
-                                    (o.flags & SCOUTER_F_COUNT_INCLUDE_PAD) ? 1 : 0, s);
+                                    (o.flags & SCOUTER_F_COUNT_INCLUDE_PAD) ? 1 : 0, rnd, s);
                 break;
             case SCOUTER_OP_SPLAT_GAP:
                 rc = launch_splat_gap(ptr(o.src), ptr(o.dst), sb.B, sb.H * sb.W, o.cout, s);
@@ -253,7 +254,7 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
                 break;
             case SCOUTER_OP_SPLAT_APPLY:
                 rc = launch_splat_apply(ptr(o.src), ptr(o.src2), ptr(o.dst), sb.B, sb.H, sb.W, o.cout, db.H, db.W,
-                                        (o.flags & SCOUTER_F_AVD_POOL) ? 1 : 0, s);
+                                        (o.flags & SCOUTER_F_AVD_POOL) ? 1 : 0, rnd, s);
                 break;
             case SCOUTER_OP_GAP:
                 rc = launch_gap(ptr(o.src), ptr(o.dst), sb.B, sb.H * sb.W, sb.C, s);
@@ -307,12 +308,17 @@ extern "C" int scouter_head_forward(const scouter_xslot_desc_t* desc, const void
     }
     float* x = io->x_out ? io->x_out : xbuf;
     // conv1x1 + bias + ReLU (slot_model.py:108-109)
-    ConvArgs c{feat, io->conv_w, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, XD, 1, 1, 1, 0, 1, 1};
     int rc;
-    if (io->math == SCOUTER_MATH_TC && umma_conv_supported(c)) {
+    if (io->math == SCOUTER_MATH_TC) {
+        // features are tf32-representable (the backbone rounds on store); W = W_hi + W_lo, two MMAs, summed in the epilogue
+        SC_CHECK_ARG(io->conv_w_tc, SCOUTER_E_INVALID, "head: SCOUTER_MATH_TC needs conv_w_tc (scouter_head_pack_conv)");
+        ConvArgs c{feat, io->conv_w_tc, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, 2 * XD,
+                   1, 1, 1, 0, 1, 1, 0, 1};
+        SC_CHECK_ARG(umma_conv_supported(c), SCOUTER_E_UNSUPPORTED, "head: channel=%d not supported by the tcgen05 projection", io->channel);
         UmmaConvPlan tmp;
         rc = launch_conv_umma(c, tmp, s);
     } else {
+        ConvArgs c{feat, io->conv_w, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, XD, 1, 1, 1, 0, 1, 1, 0, 0};
         rc = launch_conv_simt(c, s);
     }
     if (rc) return rc;
@@ -353,4 +359,56 @@ extern "C" int scouter_forward_host(const scouter_forward_host_args_t* a) {
         SC_CUDA(cudaMemcpyAsync(a->losses_host, a->losses_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
     SC_CUDA(cudaStreamSynchronize(s));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hi/lo tf32 split of the 1x1 projection weights, and single-op test entries
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = w[i];
+    float hi = to_tf32(v);
+    out[i] = hi;
+    out[n + i] = to_tf32(v - hi);
+}
+}  // namespace
+
+extern "C" int scouter_head_pack_conv(const float* conv_w, int d, int ch, float* out, scouter_stream_t stream) {
+    SC_CHECK_ARG(conv_w && out && d > 0 && ch > 0, SCOUTER_E_INVALID, "head_pack_conv: bad arguments");
+    int n = d * ch;
+    split_tf32_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(conv_w, out, n);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+static int conv_args_from_op(const scouter_op_t* o, const float* in, const float* res, float* out, int B, int H, int W, int math,
+                             ConvArgs* a) {
+    SC_CHECK_ARG(o && o->kind == SCOUTER_OP_CONV && B > 0 && H > 0 && W > 0, SCOUTER_E_INVALID, "conv_forward: bad arguments");
+    SC_CHECK_ARG(o->stride >= 1 && o->kh >= 1 && o->kw >= 1 && o->groups >= 1, SCOUTER_E_INVALID, "conv_forward: geometry");
+    int Ho = (H + 2 * o->pad - o->kh) / o->stride + 1, Wo = (W + 2 * o->pad - o->kw) / o->stride + 1;
+    SC_CHECK_ARG(Ho > 0 && Wo > 0, SCOUTER_E_INVALID, "conv_forward: empty output");
+    *a = ConvArgs{in, o->w, o->b, (o->flags & SCOUTER_F_RESIDUAL) ? res : nullptr, out, B, H, W, o->cin, Ho, Wo, o->cout,
+                  o->kh, o->kw, o->stride, o->pad, o->groups, (o->flags & SCOUTER_F_RELU) ? 1 : 0,
+                  math == SCOUTER_MATH_TC ? 1 : 0, 0};
+    return 0;
+}
+
+extern "C" int scouter_conv_path(const scouter_op_t* op, int batch, int h, int w, int math) {
+    ConvArgs a;
+    if (int e = conv_args_from_op(op, nullptr, nullptr, nullptr, batch, h, w, math, &a)) return e;
+    return (math == SCOUTER_MATH_TC && umma_conv_supported(a)) ? 1 : 0;
+}
+
+extern "C" int scouter_conv_forward(const scouter_op_t* op, const float* in, const float* res, float* out, int batch, int h, int w,
+                                    int math, scouter_stream_t stream) {
+    ConvArgs a;
+    if (int e = conv_args_from_op(op, in, res, out, batch, h, w, math, &a)) return e;
+    SC_CHECK_ARG(in && out && op->w, SCOUTER_E_INVALID, "conv_forward: NULL pointer");
+    if (math == SCOUTER_MATH_TC && umma_conv_supported(a)) {
+        UmmaConvPlan tmp;
+        return launch_conv_umma(a, tmp, (cudaStream_t)stream);
+    }
+    return launch_conv_simt(a, (cudaStream_t)stream);
 }

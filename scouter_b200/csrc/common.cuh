@@ -73,6 +73,8 @@ struct ConvArgs {
     const float* res;   // NHWC (B,Ho,Wo,Cout) or null
     float* out;         // NHWC (B,Ho,Wo,Cout)
     int B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, groups, relu;
+    int round_out;  // round the stored activations to tf32 (SCOUTER_MATH_TC: the next conv's MMA reads them as tf32)
+    int fold_halves;  // tcgen05 only: W holds [hi; lo] tf32 splits of Cout/2 filters; out[c] = acc[c] + acc[c + Cout/2]
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 
@@ -82,18 +84,19 @@ struct StemArgs {
     const float* bias;
     float* out;        // NHWC
     int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad, relu;
+    int round_out;
 };
 int launch_stem_conv(const StemArgs& a, cudaStream_t s);
 
 int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride,
                    int pad, cudaStream_t s);
 int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride,
-                   int pad, int count_include_pad, cudaStream_t s);
+                   int pad, int count_include_pad, int round_out, cudaStream_t s);
 int launch_splat_gap(const float* in, float* gap, int B, int HW, int C /*per radix*/, cudaStream_t s);
 int launch_splat_fc(const float* gap, const float* w1, const float* b1, const float* w2, const float* b2,
                     float* attn, int B, int C, int mid, cudaStream_t s);
 int launch_splat_apply(const float* in, const float* attn, float* out, int B, int H, int W, int C, int Ho, int Wo,
-                       int avd, cudaStream_t s);
+                       int avd, int round_out, cudaStream_t s);
 int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s);
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int HW, int C, cudaStream_t s);
 int launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cudaStream_t s);

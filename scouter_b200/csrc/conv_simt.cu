@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(256) conv_igemm_f32_kernel(ConvArgs p) {
 #pragma unroll
                 for (int j = 0; j < TN; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+            if (p.round_out) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) v[j] = to_tf32(v[j]);
+            }
             *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
 #pragma unroll
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(256) conv_igemm_f32_kernel(ConvArgs p) {
                 float t = v[j];
                 if (p.res) t += __ldg(p.res + o + j);
                 if (p.relu) t = fmaxf(t, 0.f);
+                if (p.round_out) t = to_tf32(t);
                 p.out[o + j] = t;
             }
         }
@@ -193,6 +198,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(StemArgs p) {
     for (int j = 0; j < 4; ++j) {
         if (p.bias) acc[j] += __ldg(p.bias + q * 4 + j);
         if (p.relu) acc[j] = fmaxf(acc[j], 0.f);
+        if (p.round_out) acc[j] = to_tf32(acc[j]);
     }
     *reinterpret_cast<float4*>(p.out + pix * p.Cout + q * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
@@ -229,7 +235,7 @@ __global__ void maxpool_kernel(const float* __restrict__ in, float* __restrict__
 // PyTorch avg_pool2d semantics: the window is first clipped to the padded extent (that size is the
 // divisor when count_include_pad), then to the real extent (that size is the divisor otherwise).
 __global__ void avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
-                               int Ho, int Wo, int k, int stride, int pad, int count_include_pad) {
+                               int Ho, int Wo, int k, int stride, int pad, int count_include_pad, int round_out) {
     const int cq = C / 4;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * Ho * Wo * cq;
@@ -253,6 +259,7 @@ __global__ void avgpool_kernel(const float* __restrict__ in, float* __restrict__
         }
     float div = (float)(count_include_pad ? pool : (he - hs) * (we - ws));
     a.x /= div; a.y /= div; a.z /= div; a.w /= div;
+    if (round_out) { a.x = to_tf32(a.x); a.y = to_tf32(a.y); a.z = to_tf32(a.z); a.w = to_tf32(a.w); }
     *reinterpret_cast<float4*>(out + pix * C + q * 4) = a;
 }
 
@@ -341,7 +348,8 @@ __global__ void __launch_bounds__(256) splat_fc_kernel(const float* __restrict__
 // out[b,ho,wo,c] = pool3x3s2p1?( x[b,h,w,c]*a0[b,c] + x[b,h,w,C+c]*a1[b,c] ); the pool divisor is 9 wherever
 // the padded window is full (count_include_pad=True, resnest.py:101) and follows avg_pool2d otherwise.
 __global__ void splat_apply_kernel(const float* __restrict__ in, const float* __restrict__ attn,
-                                   float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo, int avd) {
+                                   float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo, int avd,
+                                   int round_out) {
     const int cq = C / 4;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)B * Ho * Wo * cq;
@@ -379,6 +387,7 @@ __global__ void splat_apply_kernel(const float* __restrict__ in, const float* __
             }
         r.x /= div; r.y /= div; r.z /= div; r.w /= div;
     }
+    if (round_out) { r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w); }
     *reinterpret_cast<float4*>(out + pix * C + q * 4) = r;
 }
 
@@ -441,11 +450,11 @@ int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int 
 }
 
 int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
-                   int count_include_pad, cudaStream_t s) {
+                   int count_include_pad, int round_out, cudaStream_t s) {
     SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "avgpool: C = %d not a multiple of 4", C);
     long long total = (long long)B * Ho * Wo * (C / 4);
     avgpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W, C, Ho, Wo, k, stride, pad,
-                                                                  count_include_pad);
+                                                                  count_include_pad, round_out);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -473,10 +482,10 @@ int launch_splat_fc(const float* gap, const float* w1, const float* b1, const fl
 }
 
 int launch_splat_apply(const float* in, const float* attn, float* out, int B, int H, int W, int C, int Ho, int Wo,
-                       int avd, cudaStream_t s) {
+                       int avd, int round_out, cudaStream_t s) {
     SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "splat apply: C = %d not a multiple of 4", C);
     long long total = (long long)B * Ho * Wo * (C / 4);
-    splat_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, attn, out, B, H, W, C, Ho, Wo, avd);
+    splat_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, attn, out, B, H, W, C, Ho, Wo, avd, round_out);
     SC_LAUNCH_CHECK();
     return 0;
 }

@@ -1,12 +1,22 @@
 // tcgen05 (UMMA) + TMA implicit-GEMM convolution: interface used by the plan executor.
 #pragma once
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scouter {
 
-// Per-op cached launch state (tensor maps etc.); filled lazily by launch_conv_umma.
+// Per-op cached launch state: the two TMA descriptors and the spatial tile they were built for.
 struct UmmaConvPlan {
     bool valid = false;
+    CUtensorMap tmA, tmB;
+    const float* in = nullptr;
+    const float* w = nullptr;
+    int B = 0, H = 0, W = 0, Cin = 0, Cout = 0, kh = 0, groups = 0, BN = 0;
+    int Wb = 0, Hb = 0, Nb = 0;
 };
 
 bool umma_conv_supported(const ConvArgs& a);

@@ -1,11 +1,361 @@
+// tcgen05 + TMA implicit-GEMM convolution for sm_100a (SCOUTER_MATH_TC).
+//
+//   D[M = B*H*W, N = Cout/groups] = A[M, K = kh*kw*Cin/groups] * W[N, K]^T     (stride 1, 1x1 or 3x3 pad 1)
+//
+// * Activations are NHWC fp32 whose values are already tf32-representable (every producer rounds with
+//   cvt.rna on store), weights are OHWI fp32 pre-rounded on the host: kind::tf32 MMAs then multiply exactly
+//   the stored values and accumulate in fp32 in TMEM.
+// * No im2col buffer: for a 3x3 conv the K loop walks the 9 taps and each tap is ONE 4-D TMA box load
+//   {32 channels, Wb, Hb, Nb} of the input shifted by (r-1, s-1); TMA's out-of-bound zero fill is the padding.
+//   A 1x1 conv uses a flat 2-D map {32 channels, 128 rows}.  Both land as 128-byte rows in SWIZZLE_128B
+//   layout, i.e. a K-major UMMA operand tile of 128 rows x 32 tf32.
+// * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+//   thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias/residual/ReLU/tf32
+//   round -> global).  smem ring of STAGES {A 16 KB, B BN*128 B}; two TMEM accumulators so the epilogue of
+//   tile i overlaps the MMAs of tile i+1.
+//
+// Reference ops replaced: the nn.Conv2d+BatchNorm2d(+ReLU)(+residual) chains of timm/models/resnest.py:111-143,
+// split_attn.py:43-45,56-60 and resnet.py:403-408 (eval mode, BN folded).
+#include "ptx.cuh"
 #include "umma.cuh"
 
 namespace scouter {
+using namespace ptx;
 
-bool umma_conv_supported(const ConvArgs&) { return false; }
+namespace {
 
-int launch_conv_umma(const ConvArgs&, UmmaConvPlan&, cudaStream_t) {
-    set_error("tcgen05 convolution is not built in");
+struct UmmaArgs {
+    const float* bias;
+    const float* res;
+    float* out;
+    int mode;  // 0 = flat rows (1x1), 1 = spatial boxes
+    int M;     // flat: B*H*W
+    int B, H, W;
+    int Wb, Hb, Nb, tw, th;
+    int m_tiles, n_tiles, groups;
+    int cin_g, cout_g, Cout;
+    int kw, pad, kblocks, cblocks;
+    int relu, round_out, fold;
+    int a_bytes;
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr int A_BYTES = 128 * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN <= 64) ? 8 : (BN == 128 ? 6 : 4);
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaArgs p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+    uint64_t* empty = full + C::STAGES;
+    uint64_t* tfull = empty + C::STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int total = p.m_tiles * p.n_tiles * p.groups;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int nt = t % p.n_tiles;
+                const int mt = (t / p.n_tiles) % p.m_tiles;
+                const int g = t / (p.n_tiles * p.m_tiles);
+                int w0 = 0, h0 = 0, b0 = 0;
+                if (p.mode) {
+                    w0 = (mt % p.tw) * p.Wb;
+                    h0 = ((mt / p.tw) % p.th) * p.Hb;
+                    b0 = (mt / (p.tw * p.th)) * p.Nb;
+                }
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * C::STAGE;
+                    uint8_t* sb = sa + C::A_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + C::B_BYTES));
+                    const int tap = kb / p.cblocks;
+                    const int c0 = p.cin_g * g + (kb - tap * p.cblocks) * 32;
+                    if (p.mode) {
+                        const int r = tap / p.kw, s = tap - r * p.kw;
+                        tma_load_4d(sa, &tmA, &full[stage], c0, w0 + s - p.pad, h0 + r - p.pad, b0);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full[stage], c0, mt * 128);
+                    }
+                    tma_load_2d(sb, &tmB, &full[stage], kb * 32, g * p.cout_g + nt * BN);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = idesc_tf32(128, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+                    const uint64_t da = smem_desc_sw128(sa);
+                    const uint64_t db = smem_desc_sw128(sa + C::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom
+                        umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = one output row, 32 TMEM lanes per warp =====
+        const int q = warp - 4;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+            const int nt = t % p.n_tiles;
+            const int mt = (t / p.n_tiles) % p.m_tiles;
+            const int g = t / (p.n_tiles * p.m_tiles);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            bool valid;
+            long long orow;
+            if (p.mode) {
+                const int hw = p.Hb * p.Wb;
+                const int nb = row / hw, rem = row - nb * hw;
+                const int hb = rem / p.Wb, wb = rem - hb * p.Wb;
+                const int b = (mt / (p.tw * p.th)) * p.Nb + nb;
+                const int h = ((mt / p.tw) % p.th) * p.Hb + hb;
+                const int w = (mt % p.tw) * p.Wb + wb;
+                valid = nb < p.Nb && b < p.B && h < p.H && w < p.W;
+                orow = ((long long)b * p.H + h) * p.W + w;
+            } else {
+                orow = (long long)mt * 128 + row;
+                valid = orow < p.M;
+            }
+            const int NOUT = p.fold ? BN / 2 : BN;       // fold: columns [0,BN/2) are A*W_hi, [BN/2,BN) are A*W_lo
+            const int ch0 = p.fold ? 0 : g * p.cout_g + nt * BN;
+            float* op = p.out + orow * p.Cout + ch0;
+            const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < NOUT / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32;
+                tmem_ld_32x32(taddr, r);
+                if (p.fold) {
+                    uint32_t r2[32];
+                    tmem_ld_32x32(taddr + BN / 2, r2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                } else {
+                    tmem_ld_wait();
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                        if (p.bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 32 + 4 * j));
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        }
+                        if (rp) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + c * 32 + 4 * j));
+                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                        }
+                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (p.round_out) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                        *reinterpret_cast<float4*>(op + c * 32 + 4 * j) = v;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+    }
+    return fn;
+}
+
+void choose_tile(int B, int H, int W, int& Wb, int& Hb, int& Nb) {
+    double best = -1.0;
+    Wb = Hb = Nb = 1;
+    for (int wb = 1; wb <= W && wb <= 128; ++wb)
+        for (int hb = 1; hb <= H && wb * hb <= 128; ++hb) {
+            int nbmax = (wb == W && hb == H) ? std::min(B, 128 / (wb * hb)) : 1;
+            for (int nb = 1; nb <= nbmax; ++nb) {
+                long long tiles = (long long)cdiv(W, wb) * cdiv(H, hb) * cdiv(B, nb);
+                double util = (double)B * H * W / (tiles * 128.0) + 1e-6 * wb;  // tie -> longer contiguous runs
+                if (util > best) { best = util; Wb = wb; Hb = hb; Nb = nb; }
+            }
+        }
+}
+
+int pick_bn(int cout_g) {
+    static int cap = [] { const char* e = getenv("SCOUTER_UMMA_BN"); return e ? atoi(e) : 128; }();
+    for (int bn : {256, 128, 64, 32})
+        if (bn <= cap && cout_g % bn == 0) return bn;
+    return 0;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const UmmaArgs& u, int grid, cudaStream_t s) {
+    SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    conv_umma_kernel<BN><<<grid, 256, Cfg<BN>::SMEM, s>>>(tA, tB, u);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+bool umma_conv_supported(const ConvArgs& a) {
+    if (a.stride != 1 || a.kh != a.kw) return false;
+    if (!((a.kh == 1 && a.pad == 0) || (a.kh == 3 && a.pad == 1))) return false;
+    if (a.Cin % a.groups || a.Cout % a.groups) return false;
+    const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
+    if (cin_g % 32 || pick_bn(cout_g) == 0) return false;
+    if ((long long)a.B * a.H * a.W >= (1ll << 31)) return false;
+    if (a.fold_halves && (a.groups != 1 || a.Cout > 256 || a.Cout % 64)) return false;
+    return true;
+}
+
+int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
+    SC_CHECK_ARG(umma_conv_supported(a), SCOUTER_E_UNSUPPORTED, "conv_umma: unsupported geometry");
+    EncodeTiledFn enc = encode_fn();
+    SC_CHECK_ARG(enc, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled is not available from the driver");
+    const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
+    const int BN = a.fold_halves ? a.Cout : pick_bn(cout_g);
+    UmmaArgs u;
+    u.bias = a.bias; u.res = a.res; u.out = a.out;
+    u.mode = a.kh == 3 ? 1 : 0;
+    u.M = a.B * a.H * a.W;
+    u.B = a.B; u.H = a.H; u.W = a.W;
+    u.groups = a.groups; u.cin_g = cin_g; u.cout_g = cout_g; u.Cout = a.fold_halves ? a.Cout / 2 : a.Cout;
+    u.fold = a.fold_halves;
+    u.kw = a.kw; u.pad = a.pad;
+    u.cblocks = cin_g / 32;
+    u.kblocks = a.kh * a.kw * u.cblocks;
+    u.relu = a.relu; u.round_out = a.round_out;
+    u.n_tiles = cout_g / BN;
+
+    const bool reuse = plan.valid && plan.in == a.in && plan.w == a.w && plan.B == a.B && plan.H == a.H && plan.W == a.W &&
+                       plan.Cin == a.Cin && plan.Cout == a.Cout && plan.kh == a.kh && plan.groups == a.groups && plan.BN == BN;
+    if (!reuse) {
+        CUresult r;
+        if (u.mode) {
+            choose_tile(a.B, a.H, a.W, plan.Wb, plan.Hb, plan.Nb);
+            cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+            cuuint64_t strides[3] = {(cuuint64_t)a.Cin * 4, (cuuint64_t)a.W * a.Cin * 4, (cuuint64_t)a.H * a.W * a.Cin * 4};
+            cuuint32_t box[4] = {32, (cuuint32_t)plan.Wb, (cuuint32_t)plan.Hb, (cuuint32_t)plan.Nb};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            r = enc(&plan.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            plan.Wb = plan.Hb = plan.Nb = 0;
+            cuuint64_t dims[2] = {(cuuint64_t)a.Cin, (cuuint64_t)u.M};
+            cuuint64_t strides[1] = {(cuuint64_t)a.Cin * 4};
+            cuuint32_t box[2] = {32, 128};
+            cuuint32_t es[2] = {1, 1};
+            r = enc(&plan.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+        const cuuint64_t Kt = (cuuint64_t)a.kh * a.kw * cin_g;
+        cuuint64_t dimsB[2] = {Kt, (cuuint64_t)a.Cout};
+        cuuint64_t stridesB[1] = {Kt * 4};
+        cuuint32_t boxB[2] = {32, (cuuint32_t)BN};
+        cuuint32_t esB[2] = {1, 1};
+        r = enc(&plan.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.w, dimsB, stridesB, boxB, esB, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+        plan.valid = true;
+        plan.in = a.in; plan.w = a.w; plan.B = a.B; plan.H = a.H; plan.W = a.W; plan.Cin = a.Cin; plan.Cout = a.Cout;
+        plan.kh = a.kh; plan.groups = a.groups; plan.BN = BN;
+    }
+    if (u.mode) {
+        u.Wb = plan.Wb; u.Hb = plan.Hb; u.Nb = plan.Nb;
+        u.tw = cdiv(a.W, u.Wb); u.th = cdiv(a.H, u.Hb);
+        u.m_tiles = u.tw * u.th * cdiv(a.B, u.Nb);
+        u.a_bytes = u.Wb * u.Hb * u.Nb * 128;
+    } else {
+        u.Wb = u.Hb = u.Nb = u.tw = u.th = 1;
+        u.m_tiles = cdiv(u.M, 128);
+        u.a_bytes = 128 * 128;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        SC_CUDA(cudaGetDevice(&dev));
+        SC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long total = (long long)u.m_tiles * u.n_tiles * u.groups;
+    const int grid = (int)std::min<long long>(total, sms);
+    switch (BN) {
+        case 32: return launch_bn<32>(plan.tmA, plan.tmB, u, grid, s);
+        case 64: return launch_bn<64>(plan.tmA, plan.tmB, u, grid, s);
+        case 128: return launch_bn<128>(plan.tmA, plan.tmB, u, grid, s);
+        case 256: return launch_bn<256>(plan.tmA, plan.tmB, u, grid, s);
+    }
     return SCOUTER_E_UNSUPPORTED;
 }
 

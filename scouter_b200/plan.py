@@ -48,10 +48,17 @@ def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d | None):
     return w.permute(0, 2, 3, 1).contiguous().float(), b.float().contiguous()
 
 
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest tf32 (ties away, like cvt.rna.tf32.f32), kept in fp32 storage."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 class Program:
     """Accumulates ops; keeps every packed tensor alive."""
 
-    def __init__(self):
+    def __init__(self, math: int = L.MATH_FP32):
+        self.math = math
         self.ops: list[L.Op] = []
         self.keep: list[torch.Tensor] = []
         self.nbuf = 1  # buffer 0 = network input
@@ -75,6 +82,8 @@ class Program:
 
     def conv(self, src, conv: nn.Conv2d, bn, *, relu, residual=-1, stem=False):
         w, b = fold_conv_bn(conv, bn)
+        if self.math == L.MATH_TC and not stem:
+            w = round_tf32(w)        # kind::tf32 MMAs read the top 19 bits: make that exact instead of a truncation
         flags = (L.F_RELU if relu else 0) | (L.F_RESIDUAL if residual >= 0 else 0)
         return self.emit(L.OP_STEM_CONV if stem else L.OP_CONV, src, self.buf(), src2=residual,
                          cin=conv.in_channels, cout=conv.out_channels, k=conv.kernel_size[0], stride=conv.stride[0],
@@ -112,10 +121,10 @@ def _lower_basic_block(p: Program, blk, x: int) -> int:
     return p.conv(t, blk.conv2, blk.bn2, relu=True, residual=res)
 
 
-def lower_backbone(net, p: Program | None = None):
+def lower_backbone(net, math: int = L.MATH_FP32):
     """Returns (program, feature_buffer_id) for ``forward_features`` (resnet.py:491-501)."""
     from .backbone import BasicBlock, ResNestBottleneck
-    p = p or Program()
+    p = Program(math)
     if isinstance(net.conv1, nn.Sequential):                                    # deep stem
         x = p.conv(0, net.conv1[0], net.conv1[1], relu=True, stem=True)
         x = p.conv(x, net.conv1[3], net.conv1[4], relu=True)
@@ -208,7 +217,8 @@ class BackboneRunner:
         from .backbone import Identical
         from . import default_math
         net = self.net
-        p, feat = lower_backbone(net)
+        math = default_math() if self.math is None else self.math
+        p, feat = lower_backbone(net, math)
         self.flatten_nchw = isinstance(net.global_pool, Identical)
         if self.flatten_nchw:
             out = p.emit(L.OP_TO_NCHW, feat, p.buf())
@@ -220,7 +230,7 @@ class BackboneRunner:
                 b = fc.bias.detach().float().contiguous()
                 out = p.emit(L.OP_CONV, out, p.buf(), cin=fc.in_features, cout=fc.out_features, k=1, w=w, b=b)
         self.out_buf = out
-        self.cp = CompiledProgram(p, default_math() if self.math is None else self.math)
+        self.cp = CompiledProgram(p, math)
         self.sig = _version_signature(net)
 
     def __call__(self, x):

@@ -1,0 +1,119 @@
+"""GPU (-m gpu): the convolution kernels one op at a time, through the C ABI (scouter_conv_forward),
+against torch's CPU conv2d on the same seeded inputs (the oracle's primitive, oracle/backbone.py:_conv).
+
+tcgen05 path: operands are made tf32-representable first, so the only difference to the fp32 oracle is
+accumulation order -> 2e-5 relative; the same kernel with unrounded weights stays inside 2e-3.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from scouter_b200 import _lib as L
+from scouter_b200.plan import round_tf32
+
+pytestmark = pytest.mark.gpu
+
+# (B, H, W, Cin, Cout, k, groups, residual, relu)   -- every distinct conv geometry of resnest26d at 224 and 260,
+# ragged tiles, multi-image boxes, and the head projection
+CASES = [
+    (2, 56, 56, 64, 64, 1, 1, False, True),        # layer1.0.conv1
+    (2, 56, 56, 64, 128, 3, 2, False, True),       # layer1.x.conv2.conv (grouped 3x3, N=64 per group)
+    (3, 56, 56, 64, 256, 1, 1, True, True),        # layer1.x.conv3 + residual
+    (2, 112, 112, 32, 32, 3, 1, False, True),      # stem conv1.3
+    (1, 112, 112, 32, 64, 3, 1, False, True),      # stem conv1.6
+    (2, 28, 28, 256, 512, 3, 2, False, True),      # layer3.0.conv2.conv
+    (5, 14, 14, 512, 1024, 3, 2, False, True),     # layer4.0.conv2.conv
+    (9, 7, 7, 512, 1024, 3, 2, False, True),       # layer4.1.conv2.conv: 2 images per 98-row box, odd batch
+    (4, 7, 7, 2048, 512, 1, 1, False, True),       # layer4.1.conv1 (K = 2048)
+    (4, 7, 7, 512, 2048, 1, 1, True, True),        # layer4.1.conv3 + residual (16 n-tiles)
+    (2, 65, 65, 64, 128, 3, 2, False, True),       # 260^2 geometry: odd maps, ragged boxes
+    (2, 33, 33, 128, 256, 3, 2, False, False),
+    (3, 9, 9, 512, 1024, 3, 2, False, True),
+    (1, 17, 17, 1024, 256, 1, 1, False, True),
+    (1, 5, 3, 32, 32, 3, 1, False, False),         # tiny map, smaller than one box
+    (300, 1, 1, 64, 64, 1, 1, False, False),       # M = 300: partial last flat tile
+]
+
+
+def run_conv(dev, x, w, b, res, k, groups, relu, math):
+    """x NCHW cpu, w (Cout,Cin/g,k,k) cpu -> out NCHW cpu via the library."""
+    Bn, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    wd = w.permute(0, 2, 3, 1).contiguous().to(dev)
+    bd = b.to(dev)
+    rd = res.permute(0, 2, 3, 1).contiguous().to(dev) if res is not None else None
+    out = torch.full((Bn, H, W, Cout), float("nan"), device=dev)
+    op = L.Op(kind=L.OP_CONV, src=0, src2=-1, dst=1, cin=Cin, cout=Cout, kh=k, kw=k, stride=1, pad=k // 2, groups=groups,
+              flags=(L.F_RELU if relu else 0) | (L.F_RESIDUAL if res is not None else 0), mid=0, reserved=0,
+              w=wd.data_ptr(), b=bd.data_ptr(), w2=0, b2=0)
+    path = L.lib().scouter_conv_path(C.byref(op), Bn, H, W, math)
+    L.check(L.lib().scouter_conv_forward(C.byref(op), xd.data_ptr(), L.ptr(rd), out.data_ptr(), Bn, H, W, math, 0))
+    torch.cuda.synchronize()
+    return out.permute(0, 3, 1, 2).cpu(), path
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"B{c[0]}_{c[1]}x{c[2]}_c{c[3]}-{c[4]}_k{c[5]}g{c[6]}" for c in CASES])
+@pytest.mark.parametrize("math", [L.MATH_FP32, L.MATH_TC])
+def test_conv_vs_torch_cpu(case, math):
+    dev = torch.device("cuda", 0)
+    Bn, H, W, Cin, Cout, k, groups, use_res, relu = case
+    r = np.random.RandomState(hash(case) & 0xFFFF)
+    x = torch.from_numpy(r.standard_normal((Bn, Cin, H, W)).astype(np.float32))
+    w = torch.from_numpy((r.standard_normal((Cout, Cin // groups, k, k)) * np.sqrt(2.0 / (Cin // groups * k * k))).astype(np.float32))
+    b = torch.from_numpy(0.1 * r.standard_normal(Cout).astype(np.float32))
+    res = torch.from_numpy(r.standard_normal((Bn, Cout, H, W)).astype(np.float32)) if use_res else None
+    if math == L.MATH_TC:
+        x, w = round_tf32(x), round_tf32(w)
+    ref = F.conv2d(x, w, b, 1, k // 2, 1, groups)
+    if res is not None:
+        ref = ref + res
+    if relu:
+        ref = torch.relu(ref)
+    out, path = run_conv(dev, x, w, b, res, k, groups, relu, math)
+    assert path == (1 if math == L.MATH_TC else 0), "the tcgen05 kernel must be the one that runs in TC mode"
+    assert torch.isfinite(out).all()
+    if math == L.MATH_TC:
+        # the TC epilogue rounds its output to tf32 for the next layer: compare against the rounded oracle
+        err = float((out - ref).abs().max() / ref.abs().max())
+        assert err < 2.0 ** -11 * 1.5, err
+        assert torch.all((out.view(torch.int32) & 0x1FFF) == 0)
+    else:
+        err = float((out - ref).abs().max() / ref.abs().max())
+        assert err < 2e-5, err
+
+
+def test_head_projection_hi_lo_split_is_fp32_accurate():
+    """conv1x1 in TC mode: features tf32-representable, W = W_hi + W_lo -> matches the fp32 product to ~1e-6."""
+    import scouter_b200 as sb
+    dev = torch.device("cuda", 0)
+    r = np.random.RandomState(11)
+    Bn, n, ch = 37, 49, 2048
+    feat = round_tf32(torch.from_numpy(np.maximum(r.standard_normal((Bn, n, ch)), 0).astype(np.float32)))
+    w = torch.from_numpy((r.standard_normal((64, ch)) / np.sqrt(ch)).astype(np.float32))
+    b = torch.from_numpy(0.1 * r.standard_normal(64).astype(np.float32))
+    ref = torch.relu(feat.double() @ w.double().t() + b.double())
+    m = sb.SlotAttention(10, 1, 64, to_k_layer=3, power=2).to(dev).eval()
+    desc, packed = m.desc_and_pack(dev)
+    for math, tol in ((L.MATH_FP32, 2e-6), (L.MATH_TC, 2e-6)):
+        io = L.HeadIO()
+        io.batch, io.h, io.w, io.channel, io.layout, io.math = Bn, 7, 7, ch, L.LAYOUT_NHWC, math
+        fd, wd, bd = feat.to(dev), w.to(dev), b.to(dev)
+        wtc = torch.empty(128, ch, device=dev)
+        L.check(L.lib().scouter_head_pack_conv(wd.data_ptr(), 64, ch, wtc.data_ptr(), 0))
+        pe = sb.build_position_encoding("sine", 64).table(7, 7, dev)
+        logits = torch.empty(Bn, 10, device=dev)
+        xo = torch.empty(Bn, n, 64, device=dev)
+        io.feat, io.conv_w, io.conv_b, io.conv_w_tc, io.pe = fd.data_ptr(), wd.data_ptr(), bd.data_ptr(), wtc.data_ptr(), pe.data_ptr()
+        io.logits, io.attn, io.attn_sum, io.x_out = logits.data_ptr(), 0, 0, xo.data_ptr()
+        nbytes = L.lib().scouter_head_workspace_bytes(C.byref(desc), C.byref(io))
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 1024
+        L.check(L.lib().scouter_head_forward(C.byref(desc), packed.data_ptr(), C.byref(io), ws.data_ptr() + off, nbytes, 0))
+        torch.cuda.synchronize()
+        err = float((xo.cpu().double() - ref).abs().max() / ref.abs().max())
+        print(f"head projection math={math}: rel err {err:.2e}")
+        assert err < tol

@@ -93,9 +93,19 @@ def test_bn_folding_matches_conv_bn():
 def test_lowering_op_counts_resnest26d():
     m = sb.SlotModel(make_args())
     prog, feat = lower_backbone(m.backbone)
+    assert lower_backbone(m.backbone, L.MATH_TC)[0].ops[1].w != 0
     kinds = [o.kind for o in prog.ops]
     # 47 convs in the backbone = 3 stem + 8*(conv1, conv2.conv, conv3) + 4 shortcuts + 16 fc1/fc2
     assert kinds.count(L.OP_STEM_CONV) == 1 and kinds.count(L.OP_CONV) == 2 + 24 + 4
     assert kinds.count(L.OP_SPLAT_FC) == 8 and kinds.count(L.OP_SPLAT_GAP) == 8 and kinds.count(L.OP_SPLAT_APPLY) == 8
     assert kinds.count(L.OP_MAXPOOL) == 1 and kinds.count(L.OP_AVGPOOL) == 3
     assert feat == prog.ops[-1].dst
+
+
+def test_round_tf32_is_round_to_nearest_ties_away():
+    from scouter_b200.plan import round_tf32
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -11 + 2 ** -20, -1.0 - 2 ** -11, 3.14159265, -2.5e-7, 0.0])
+    r = round_tf32(x)
+    assert torch.all((r.view(torch.int32) & 0x1FFF) == 0)                     # 13 low mantissa bits cleared
+    assert r[0] == 1.0 and r[1] == 1.0 + 2 ** -10 and r[3] == -1.0 - 2 ** -10   # ties away from zero
+    assert float((r - x).abs().max() / x.abs().max()) <= 2 ** -11
