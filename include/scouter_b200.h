@@ -126,8 +126,10 @@ int scouter_vis_maps_u8(const float* attn /* (B,S,n) */, int batch, int num_clas
 #define SCOUTER_LAYOUT_NHWC 0 /* (B, h*w, ch): this library's backbone output */
 #define SCOUTER_LAYOUT_NCHW 1 /* (B, ch, h*w): the reference backbone's flattened output (slot_model.py:108) */
 
-#define SCOUTER_MATH_FP32 0   /* CUDA-core fp32 FMA everywhere (exact mode) */
-#define SCOUTER_MATH_TC 1     /* tcgen05 tensor cores: tf32 operands, error-compensated where needed */
+#define SCOUTER_MATH_FP32 0    /* CUDA-core fp32 FMA everywhere (exact mode) */
+#define SCOUTER_MATH_TC 1      /* tcgen05 tensor cores, error-compensated 3xTF32 (fp32-class results; default) */
+#define SCOUTER_MATH_TC_FAST 2 /* tcgen05 tensor cores, single tf32 pass on tf32-rounded activations/weights
+                                  (cuDNN-TF32 class accuracy: ~3e-3 on the log-probs; opt-in) */
 
 typedef struct scouter_head_io {
     int32_t batch, h, w;     /* feature map is h x w (feature_size; derived from the input, D6) */
@@ -137,18 +139,12 @@ typedef struct scouter_head_io {
     const float* feat;
     const float* conv_w;     /* (d, ch)  conv1x1.weight viewed 2-D */
     const float* conv_b;     /* (d)      conv1x1.bias */
-    const float* conv_w_tc;  /* (2d, ch) [hi; lo] tf32 split from scouter_head_pack_conv; required for SCOUTER_MATH_TC */
     const float* pe;         /* (h*w, d) from scouter_pe_sine */
     float* logits;           /* (B, C) */
     float* attn;             /* (B, S, n) or NULL */
     float* attn_sum;         /* (B) or NULL */
     float* x_out;            /* (B, n, d) projected features, or NULL (debug / tests) */
 } scouter_head_io_t;
-
-/* Error-compensated tensor-core operand for the 1x1 projection: rows [0,d) = tf32(W), rows [d,2d) =
- * tf32(W - tf32(W)).  A*W_hi^T + A*W_lo^T reproduces the fp32 product of tf32-representable features to
- * ~2^-22 relative.  `out` holds 2*d*ch floats; re-pack when conv1x1.weight changes. */
-int scouter_head_pack_conv(const float* conv_w, int d, int ch, float* out, scouter_stream_t stream);
 
 size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io);
 int scouter_head_forward(const scouter_xslot_desc_t* desc, const void* packed, const scouter_head_io_t* io,

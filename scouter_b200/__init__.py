@@ -9,7 +9,7 @@ All arithmetic runs in ``libscouter_b200.so`` (hand-written CUDA behind the C AB
 import os
 
 from . import _lib
-from ._lib import ScouterError, MATH_FP32, MATH_TC
+from ._lib import ScouterError, MATH_FP32, MATH_TC, MATH_TC_FAST
 from .backbone import Identical, create_model, list_models
 from .position_encode import PositionEmbeddingSine, build_position_encoding
 from .slot_attention import ScouterAttention, SlotAttention
@@ -17,12 +17,14 @@ from .slot_model import SlotModel, load_backbone
 
 __all__ = ["SlotModel", "SlotAttention", "ScouterAttention", "load_backbone", "Identical", "create_model",
            "list_models", "PositionEmbeddingSine", "build_position_encoding", "ScouterError", "default_math",
-           "MATH_FP32", "MATH_TC"]
+           "MATH_FP32", "MATH_TC", "MATH_TC_FAST"]
 
 
 def default_math() -> int:
-    """SCOUTER_MATH=fp32 -> exact CUDA-core kernels; SCOUTER_MATH=tc (default) -> tcgen05 tensor-core kernels."""
+    """SCOUTER_MATH=tc (default): tcgen05 tensor cores, error-compensated 3xTF32 (fp32-class results);
+    fp32: exact CUDA-core kernels; tc_fast: single-pass tf32 (cuDNN-TF32-class accuracy)."""
     v = os.environ.get("SCOUTER_MATH", "tc").lower()
-    if v not in ("fp32", "tc"):
-        raise ScouterError(f"SCOUTER_MATH={v!r}: expected 'fp32' or 'tc'")
-    return MATH_FP32 if v == "fp32" else MATH_TC
+    table = {"fp32": MATH_FP32, "tc": MATH_TC, "tc_fast": MATH_TC_FAST}
+    if v not in table:
+        raise ScouterError(f"SCOUTER_MATH={v!r}: expected one of {sorted(table)}")
+    return table[v]

@@ -16,7 +16,7 @@ SOURCES = ["api.cu", "conv_simt.cu", "xslot.cu", "umma_conv.cu"]
 
 OK = 0
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
-MATH_FP32, MATH_TC = 0, 1
+MATH_FP32, MATH_TC, MATH_TC_FAST = 0, 1, 2
 MAX_TO_K_LAYERS = 8
 
 OP_STEM_CONV, OP_CONV, OP_MAXPOOL, OP_AVGPOOL = 1, 2, 3, 4
@@ -50,7 +50,7 @@ class HeadIO(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("channel", C.c_int32),
         ("layout", C.c_int32), ("math", C.c_int32),
-        ("feat", _fp), ("conv_w", _fp), ("conv_b", _fp), ("conv_w_tc", _fp), ("pe", _fp),
+        ("feat", _fp), ("conv_w", _fp), ("conv_b", _fp), ("pe", _fp),
         ("logits", _fp), ("attn", _fp), ("attn_sum", _fp), ("x_out", _fp),
     ]
 
@@ -91,7 +91,6 @@ SIGNATURES = {
     "scouter_head_finalize": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                         _fp, _fp, _fp]),
     "scouter_vis_maps_u8": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp]),
-    "scouter_head_pack_conv": (C.c_int, [_fp, C.c_int, C.c_int, _fp, _fp]),
     "scouter_conv_forward": (C.c_int, [C.POINTER(Op), _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "scouter_conv_path": (C.c_int, [C.POINTER(Op), C.c_int, C.c_int, C.c_int, C.c_int]),
     "scouter_head_workspace_bytes": (C.c_size_t, [C.POINTER(XSlotDesc), C.POINTER(HeadIO)]),

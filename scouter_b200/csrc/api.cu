@@ -61,7 +61,7 @@ extern "C" int scouter_device_check(int device) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int scouter_plan_create(const scouter_op_t* ops, int n_ops, int n_buffers, int math, scouter_plan_t** out) {
     SC_CHECK_ARG(ops && out && n_ops > 0 && n_buffers > 1, SCOUTER_E_INVALID, "plan_create: bad arguments");
-    SC_CHECK_ARG(math == SCOUTER_MATH_FP32 || math == SCOUTER_MATH_TC, SCOUTER_E_INVALID, "plan_create: math=%d", math);
+    SC_CHECK_ARG(math >= SCOUTER_MATH_FP32 && math <= SCOUTER_MATH_TC_FAST, SCOUTER_E_INVALID, "plan_create: math=%d", math);
     for (int i = 0; i < n_ops; ++i) {
         const scouter_op_t& o = ops[i];
         SC_CHECK_ARG(o.kind >= SCOUTER_OP_STEM_CONV && o.kind <= SCOUTER_OP_TO_NCHW, SCOUTER_E_INVALID,
@@ -215,7 +215,8 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
     SC_CHECK_ARG(arena_bytes >= plan->arena_bytes, SCOUTER_E_INVALID, "plan_run: arena of %zu bytes, need %zu", arena_bytes, plan->arena_bytes);
     SC_CHECK_ARG(((uintptr_t)arena & 1023) == 0, SCOUTER_E_INVALID, "plan_run: arena is not 1024-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    const int rnd = plan->math == SCOUTER_MATH_TC ? 1 : 0;  // tf32-representable activations for the tcgen05 convs
+    const int rnd = plan->math == SCOUTER_MATH_TC_FAST ? 1 : 0;  // tf32-representable activations for the 1-pass tcgen05 convs
+    const int split = plan->math == SCOUTER_MATH_TC ? 1 : 0;     // error-compensated 3xTF32
     char* base = (char*)arena;
     auto ptr = [&](int id) -> float* { return id == 0 ? const_cast<float*>(input_nchw) : (float*)(base + plan->bufs[id].offset); };
     for (size_t i = 0; i < plan->ops.size(); ++i) {
@@ -234,8 +235,8 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
             case SCOUTER_OP_CONV: {
                 ConvArgs a{ptr(o.src), o.w, o.b, (o.flags & SCOUTER_F_RESIDUAL) ? ptr(o.src2) : nullptr, ptr(o.dst),
                            sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.kw, o.stride, o.pad, o.groups,
-                           (o.flags & SCOUTER_F_RELU) ? 1 : 0, (rnd && db.H * db.W > 1) ? 1 : 0, 0};
-                if (plan->math == SCOUTER_MATH_TC && umma_conv_supported(a)) rc = launch_conv_umma(a, plan->umma[i], s);
+                           (o.flags & SCOUTER_F_RELU) ? 1 : 0, (rnd && db.H * db.W > 1) ? 1 : 0, split};
+                if (plan->math != SCOUTER_MATH_FP32 && umma_conv_supported(a)) rc = launch_conv_umma(a, plan->umma[i], s);
                 else rc = launch_conv_simt(a, s);
                 break;
             }
@@ -278,7 +279,7 @@ static int validate_head(const scouter_xslot_desc_t* desc, const scouter_head_io
                  "head: batch=%d h=%d w=%d channel=%d", io->batch, io->h, io->w, io->channel);
     SC_CHECK_ARG(io->channel % 16 == 0, SCOUTER_E_UNSUPPORTED, "head: channel=%d is not a multiple of 16", io->channel);
     SC_CHECK_ARG(io->layout == SCOUTER_LAYOUT_NHWC || io->layout == SCOUTER_LAYOUT_NCHW, SCOUTER_E_INVALID, "head: layout=%d", io->layout);
-    SC_CHECK_ARG(io->math == SCOUTER_MATH_FP32 || io->math == SCOUTER_MATH_TC, SCOUTER_E_INVALID, "head: math=%d", io->math);
+    SC_CHECK_ARG(io->math >= SCOUTER_MATH_FP32 && io->math <= SCOUTER_MATH_TC_FAST, SCOUTER_E_INVALID, "head: math=%d", io->math);
     return 0;
 }
 
@@ -308,17 +309,14 @@ extern "C" int scouter_head_forward(const scouter_xslot_desc_t* desc, const void
     }
     float* x = io->x_out ? io->x_out : xbuf;
     // conv1x1 + bias + ReLU (slot_model.py:108-109)
+    // The projection always runs error-compensated on the tensor cores (it is HBM-bound: the extra MMAs are free).
+    ConvArgs c{feat, io->conv_w, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, XD,
+               1, 1, 1, 0, 1, 1, 0, 1};
     int rc;
-    if (io->math == SCOUTER_MATH_TC) {
-        // features are tf32-representable (the backbone rounds on store); W = W_hi + W_lo, two MMAs, summed in the epilogue
-        SC_CHECK_ARG(io->conv_w_tc, SCOUTER_E_INVALID, "head: SCOUTER_MATH_TC needs conv_w_tc (scouter_head_pack_conv)");
-        ConvArgs c{feat, io->conv_w_tc, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, 2 * XD,
-                   1, 1, 1, 0, 1, 1, 0, 1};
-        SC_CHECK_ARG(umma_conv_supported(c), SCOUTER_E_UNSUPPORTED, "head: channel=%d not supported by the tcgen05 projection", io->channel);
+    if (io->math != SCOUTER_MATH_FP32 && umma_conv_supported(c)) {
         UmmaConvPlan tmp;
         rc = launch_conv_umma(c, tmp, s);
     } else {
-        ConvArgs c{feat, io->conv_w, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, XD, 1, 1, 1, 0, 1, 1, 0, 0};
         rc = launch_conv_simt(c, s);
     }
     if (rc) return rc;
@@ -362,27 +360,8 @@ extern "C" int scouter_forward_host(const scouter_forward_host_args_t* a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// hi/lo tf32 split of the 1x1 projection weights, and single-op test entries
+// single-op test entries
 // ------------------------------------------------------------------------------------------------
-namespace {
-__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ out, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float v = w[i];
-    float hi = to_tf32(v);
-    out[i] = hi;
-    out[n + i] = to_tf32(v - hi);
-}
-}  // namespace
-
-extern "C" int scouter_head_pack_conv(const float* conv_w, int d, int ch, float* out, scouter_stream_t stream) {
-    SC_CHECK_ARG(conv_w && out && d > 0 && ch > 0, SCOUTER_E_INVALID, "head_pack_conv: bad arguments");
-    int n = d * ch;
-    split_tf32_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(conv_w, out, n);
-    SC_LAUNCH_CHECK();
-    return 0;
-}
-
 static int conv_args_from_op(const scouter_op_t* o, const float* in, const float* res, float* out, int B, int H, int W, int math,
                              ConvArgs* a) {
     SC_CHECK_ARG(o && o->kind == SCOUTER_OP_CONV && B > 0 && H > 0 && W > 0, SCOUTER_E_INVALID, "conv_forward: bad arguments");
@@ -391,14 +370,14 @@ static int conv_args_from_op(const scouter_op_t* o, const float* in, const float
     SC_CHECK_ARG(Ho > 0 && Wo > 0, SCOUTER_E_INVALID, "conv_forward: empty output");
     *a = ConvArgs{in, o->w, o->b, (o->flags & SCOUTER_F_RESIDUAL) ? res : nullptr, out, B, H, W, o->cin, Ho, Wo, o->cout,
                   o->kh, o->kw, o->stride, o->pad, o->groups, (o->flags & SCOUTER_F_RELU) ? 1 : 0,
-                  math == SCOUTER_MATH_TC ? 1 : 0, 0};
+                  math == SCOUTER_MATH_TC_FAST ? 1 : 0, math == SCOUTER_MATH_TC ? 1 : 0};
     return 0;
 }
 
 extern "C" int scouter_conv_path(const scouter_op_t* op, int batch, int h, int w, int math) {
     ConvArgs a;
     if (int e = conv_args_from_op(op, nullptr, nullptr, nullptr, batch, h, w, math, &a)) return e;
-    return (math == SCOUTER_MATH_TC && umma_conv_supported(a)) ? 1 : 0;
+    return (math != SCOUTER_MATH_FP32 && umma_conv_supported(a)) ? 1 : 0;
 }
 
 extern "C" int scouter_conv_forward(const scouter_op_t* op, const float* in, const float* res, float* out, int batch, int h, int w,
@@ -406,7 +385,7 @@ extern "C" int scouter_conv_forward(const scouter_op_t* op, const float* in, con
     ConvArgs a;
     if (int e = conv_args_from_op(op, in, res, out, batch, h, w, math, &a)) return e;
     SC_CHECK_ARG(in && out && op->w, SCOUTER_E_INVALID, "conv_forward: NULL pointer");
-    if (math == SCOUTER_MATH_TC && umma_conv_supported(a)) {
+    if (math != SCOUTER_MATH_FP32 && umma_conv_supported(a)) {
         UmmaConvPlan tmp;
         return launch_conv_umma(a, tmp, (cudaStream_t)stream);
     }

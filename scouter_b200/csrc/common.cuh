@@ -74,7 +74,7 @@ struct ConvArgs {
     float* out;         // NHWC (B,Ho,Wo,Cout)
     int B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, groups, relu;
     int round_out;  // round the stored activations to tf32 (SCOUTER_MATH_TC: the next conv's MMA reads them as tf32)
-    int fold_halves;  // tcgen05 only: W holds [hi; lo] tf32 splits of Cout/2 filters; out[c] = acc[c] + acc[c + Cout/2]
+    int split;      // tcgen05 only: error-compensated 3xTF32 (operands split on the fly into trunc19 + remainder)
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 

@@ -2,17 +2,22 @@
 //
 //   D[M = B*H*W, N = Cout/groups] = A[M, K = kh*kw*Cin/groups] * W[N, K]^T     (stride 1, 1x1 or 3x3 pad 1)
 //
-// * Activations are NHWC fp32 whose values are already tf32-representable (every producer rounds with
-//   cvt.rna on store), weights are OHWI fp32 pre-rounded on the host: kind::tf32 MMAs then multiply exactly
-//   the stored values and accumulate in fp32 in TMEM.
+// * Two precisions of the same kernel (template SPLIT):
+//     SPLIT=true  (SCOUTER_MATH_TC, default): error-compensated "3xTF32".  kind::tf32 reads the top 19 bits of an
+//       fp32 word, i.e. x_t = trunc19(x) EXACTLY; four splitter warps compute the remainder x_r = x - x_t (exact in
+//       fp32, tf32-representable to 2^-21|x|) for both the activation and the weight tile into sibling smem tiles,
+//       and the issuer accumulates  A_t*W_r + A_r*W_t + A_t*W_t  in the fp32 TMEM accumulator.  Operands stay plain
+//       fp32 in HBM (no extra traffic); the dropped term is <= 2^-20 relative: fp32-class results.
+//     SPLIT=false (SCOUTER_MATH_TC_FAST): one tf32 MMA; producers round stored activations with cvt.rna and
+//       weights are pre-rounded on the host, so the MMA multiplies exactly the stored values (cuDNN-TF32 class).
 // * No im2col buffer: for a 3x3 conv the K loop walks the 9 taps and each tap is ONE 4-D TMA box load
 //   {32 channels, Wb, Hb, Nb} of the input shifted by (r-1, s-1); TMA's out-of-bound zero fill is the padding.
 //   A 1x1 conv uses a flat 2-D map {32 channels, 128 rows}.  Both land as 128-byte rows in SWIZZLE_128B
 //   layout, i.e. a K-major UMMA operand tile of 128 rows x 32 tf32.
 // * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
-//   thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias/residual/ReLU/tf32
-//   round -> global).  smem ring of STAGES {A 16 KB, B BN*128 B}; two TMEM accumulators so the epilogue of
-//   tile i overlaps the MMAs of tile i+1.
+//   thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias/residual/ReLU -> global),
+//   warps 8-11 = operand splitters (SPLIT only).  smem ring of STAGES {A 16 KB, B BN*128 B [, A_r, B_r]}; two TMEM
+//   accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Reference ops replaced: the nn.Conv2d+BatchNorm2d(+ReLU)(+residual) chains of timm/models/resnest.py:111-143,
 // split_attn.py:43-45,56-60 and resnet.py:403-408 (eval mode, BN folded).
@@ -35,31 +40,34 @@ struct UmmaArgs {
     int m_tiles, n_tiles, groups;
     int cin_g, cout_g, Cout;
     int kw, pad, kblocks, cblocks;
-    int relu, round_out, fold;
+    int relu, round_out;
     int a_bytes;
 };
 
-template <int BN>
+template <int BN, bool SPLIT>
 struct Cfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN <= 64) ? 8 : (BN == 128 ? 6 : 4);
+    static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
+    static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | B | A_r | B_r]
+    static constexpr int STAGES = (200 * 1024 / STAGE) > 8 ? 8 : (200 * 1024 / STAGE);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int THREADS = SPLIT ? 384 : 256;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(Cfg<BN, SPLIT>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaArgs p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* split_done = tempty + 2;  // [STAGES], SPLIT only: remainders written, stage ready for the issuer
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(split_done + C::STAGES);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (warp == 0 && elect_one()) {
@@ -70,6 +78,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < C::STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
+            mbar_init(&split_done[i], 128);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
@@ -132,14 +141,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(SPLIT ? &split_done[stage] : &full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * C::STAGE);
                     const uint64_t da = smem_desc_sw128(sa);
                     const uint64_t db = smem_desc_sw128(sa + C::A_BYTES);
+                    // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom (+2 in 16-byte units)
+                    if constexpr (SPLIT) {
+                        const uint64_t dar = smem_desc_sw128(sa + C::RAW);
+                        const uint64_t dbr = smem_desc_sw128(sa + C::RAW + C::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom
-                        umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k) {
+                            umma_tf32(d_tmem, da + 2 * k, dbr + 2 * k, idesc, (kb | k) != 0);  // A_t * W_r
+                            umma_tf32(d_tmem, dar + 2 * k, db + 2 * k, idesc, 1);              // A_r * W_t
+                            umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);               // A_t * W_t
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -172,26 +192,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 orow = (long long)mt * 128 + row;
                 valid = orow < p.M;
             }
-            const int NOUT = p.fold ? BN / 2 : BN;       // fold: columns [0,BN/2) are A*W_hi, [BN/2,BN) are A*W_lo
-            const int ch0 = p.fold ? 0 : g * p.cout_g + nt * BN;
+            const int ch0 = g * p.cout_g + nt * BN;
             float* op = p.out + orow * p.Cout + ch0;
             const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < NOUT / 32; ++c) {
+            for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32;
-                tmem_ld_32x32(taddr, r);
-                if (p.fold) {
-                    uint32_t r2[32];
-                    tmem_ld_32x32(taddr + BN / 2, r2);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-                } else {
-                    tmem_ld_wait();
-                }
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+                tmem_ld_wait();
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -213,6 +223,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
+        }
+    }
+    if constexpr (SPLIT) {
+        if (warp >= 8) {
+            // ===== operand splitters: x_r = x - trunc19(x) for the A and B tiles, same (swizzled) offsets =====
+            const int tid = threadIdx.x - 256;  // 0..127
+            constexpr int VEC = C::RAW / 16;    // float4 per stage (A then B, contiguous)
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    const float4* src = reinterpret_cast<const float4*>(smem + stage * C::STAGE);
+                    float4* dst = reinterpret_cast<float4*>(smem + stage * C::STAGE + C::RAW);
+#pragma unroll 4
+                    for (int i = tid; i < VEC; i += 128) {
+                        float4 v = src[i];
+                        v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                        v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                        v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                        v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                        dst[i] = v;
+                    }
+                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    mbar_arrive(&split_done[stage]);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
         }
     }
     tc_fence_before();
@@ -252,16 +290,18 @@ void choose_tile(int B, int H, int W, int& Wb, int& Hb, int& Nb) {
 }
 
 int pick_bn(int cout_g) {
-    static int cap = [] { const char* e = getenv("SCOUTER_UMMA_BN"); return e ? atoi(e) : 128; }();
-    for (int bn : {256, 128, 64, 32})
+    static int cap = [] { const char* e = getenv("SCOUTER_UMMA_BN"); int v = e ? atoi(e) : 128; return v > 128 ? 128 : v; }();
+    for (int bn : {128, 64, 32})
         if (bn <= cap && cout_g % bn == 0) return bn;
     return 0;
 }
 
-template <int BN>
+template <int BN, bool SPLIT>
 int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const UmmaArgs& u, int grid, cudaStream_t s) {
-    SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
-    conv_umma_kernel<BN><<<grid, 256, Cfg<BN>::SMEM, s>>>(tA, tB, u);
+    using C = Cfg<BN, SPLIT>;
+    static_assert(C::STAGES >= 2, "pipeline too shallow");
+    SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    conv_umma_kernel<BN, SPLIT><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -275,7 +315,6 @@ bool umma_conv_supported(const ConvArgs& a) {
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
     if (cin_g % 32 || pick_bn(cout_g) == 0) return false;
     if ((long long)a.B * a.H * a.W >= (1ll << 31)) return false;
-    if (a.fold_halves && (a.groups != 1 || a.Cout > 256 || a.Cout % 64)) return false;
     return true;
 }
 
@@ -284,14 +323,13 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     EncodeTiledFn enc = encode_fn();
     SC_CHECK_ARG(enc, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled is not available from the driver");
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
-    const int BN = a.fold_halves ? a.Cout : pick_bn(cout_g);
+    const int BN = pick_bn(cout_g);
     UmmaArgs u;
     u.bias = a.bias; u.res = a.res; u.out = a.out;
     u.mode = a.kh == 3 ? 1 : 0;
     u.M = a.B * a.H * a.W;
     u.B = a.B; u.H = a.H; u.W = a.W;
-    u.groups = a.groups; u.cin_g = cin_g; u.cout_g = cout_g; u.Cout = a.fold_halves ? a.Cout / 2 : a.Cout;
-    u.fold = a.fold_halves;
+    u.groups = a.groups; u.cin_g = cin_g; u.cout_g = cout_g; u.Cout = a.Cout;
     u.kw = a.kw; u.pad = a.pad;
     u.cblocks = cin_g / 32;
     u.kblocks = a.kh * a.kw * u.cblocks;
@@ -350,11 +388,18 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     }
     const long long total = (long long)u.m_tiles * u.n_tiles * u.groups;
     const int grid = (int)std::min<long long>(total, sms);
-    switch (BN) {
-        case 32: return launch_bn<32>(plan.tmA, plan.tmB, u, grid, s);
-        case 64: return launch_bn<64>(plan.tmA, plan.tmB, u, grid, s);
-        case 128: return launch_bn<128>(plan.tmA, plan.tmB, u, grid, s);
-        case 256: return launch_bn<256>(plan.tmA, plan.tmB, u, grid, s);
+    if (a.split) {
+        switch (BN) {
+            case 32: return launch_bn<32, true>(plan.tmA, plan.tmB, u, grid, s);
+            case 64: return launch_bn<64, true>(plan.tmA, plan.tmB, u, grid, s);
+            case 128: return launch_bn<128, true>(plan.tmA, plan.tmB, u, grid, s);
+        }
+    } else {
+        switch (BN) {
+            case 32: return launch_bn<32, false>(plan.tmA, plan.tmB, u, grid, s);
+            case 64: return launch_bn<64, false>(plan.tmA, plan.tmB, u, grid, s);
+            case 128: return launch_bn<128, false>(plan.tmA, plan.tmB, u, grid, s);
+        }
     }
     return SCOUTER_E_UNSUPPORTED;
 }

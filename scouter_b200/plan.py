@@ -82,8 +82,8 @@ class Program:
 
     def conv(self, src, conv: nn.Conv2d, bn, *, relu, residual=-1, stem=False):
         w, b = fold_conv_bn(conv, bn)
-        if self.math == L.MATH_TC and not stem:
-            w = round_tf32(w)        # kind::tf32 MMAs read the top 19 bits: make that exact instead of a truncation
+        if self.math == L.MATH_TC_FAST and not stem:
+            w = round_tf32(w)        # 1-pass kind::tf32 reads the top 19 bits: make that a rounding, not a truncation
         flags = (L.F_RELU if relu else 0) | (L.F_RESIDUAL if residual >= 0 else 0)
         return self.emit(L.OP_STEM_CONV if stem else L.OP_CONV, src, self.buf(), src2=residual,
                          cin=conv.in_channels, cout=conv.out_channels, k=conv.kernel_size[0], stride=conv.stride[0],

@@ -166,16 +166,6 @@ class SlotModel(nn.Module):
                 raise L.ScouterError("SlotModel: conv1x1 parameters must be contiguous fp32 on the input's device")
         st.io.conv_w = self.conv1x1.weight.data_ptr()
         st.io.conv_b = self.conv1x1.bias.data_ptr()
-        if st.io.math == L.MATH_TC:
-            w = self.conv1x1.weight
-            sig = (w._version, w.data_ptr())
-            if getattr(self, "_conv_tc_sig", None) != sig or self._conv_tc.device != dev:
-                d, ch = w.shape[0], w.shape[1]
-                self._conv_tc = torch.empty(2 * d, ch, dtype=torch.float32, device=dev)
-                L.check(L.lib().scouter_head_pack_conv(w.data_ptr(), d, ch, self._conv_tc.data_ptr(), L.stream_ptr()),
-                        "scouter_head_pack_conv")
-                self._conv_tc_sig = sig
-            st.io.conv_w_tc = self._conv_tc.data_ptr()
         desc, packed = self.slot.desc_and_pack(dev)
         if st.ws is None:
             nbytes = L.lib().scouter_head_workspace_bytes(C.byref(desc), C.byref(st.io))

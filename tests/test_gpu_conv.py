@@ -1,8 +1,9 @@
 """GPU (-m gpu): the convolution kernels one op at a time, through the C ABI (scouter_conv_forward),
 against torch's CPU conv2d on the same seeded inputs (the oracle's primitive, oracle/backbone.py:_conv).
 
-tcgen05 path: operands are made tf32-representable first, so the only difference to the fp32 oracle is
-accumulation order -> 2e-5 relative; the same kernel with unrounded weights stays inside 2e-3.
+SCOUTER_MATH_TC (3xTF32, operands split on the fly) is held to the same 2e-5 as the exact CUDA-core kernel on
+arbitrary fp32 operands; SCOUTER_MATH_TC_FAST (one tf32 pass) gets tf32-representable operands, as its producers
+guarantee, and is checked to the tf32 rounding of its output.
 """
 import ctypes as C
 
@@ -57,7 +58,7 @@ def run_conv(dev, x, w, b, res, k, groups, relu, math):
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"B{c[0]}_{c[1]}x{c[2]}_c{c[3]}-{c[4]}_k{c[5]}g{c[6]}" for c in CASES])
-@pytest.mark.parametrize("math", [L.MATH_FP32, L.MATH_TC])
+@pytest.mark.parametrize("math", [L.MATH_FP32, L.MATH_TC, L.MATH_TC_FAST])
 def test_conv_vs_torch_cpu(case, math):
     dev = torch.device("cuda", 0)
     Bn, H, W, Cin, Cout, k, groups, use_res, relu = case
@@ -66,48 +67,46 @@ def test_conv_vs_torch_cpu(case, math):
     w = torch.from_numpy((r.standard_normal((Cout, Cin // groups, k, k)) * np.sqrt(2.0 / (Cin // groups * k * k))).astype(np.float32))
     b = torch.from_numpy(0.1 * r.standard_normal(Cout).astype(np.float32))
     res = torch.from_numpy(r.standard_normal((Bn, Cout, H, W)).astype(np.float32)) if use_res else None
-    if math == L.MATH_TC:
-        x, w = round_tf32(x), round_tf32(w)
-    ref = F.conv2d(x, w, b, 1, k // 2, 1, groups)
+    if math == L.MATH_TC_FAST:
+        x, w = round_tf32(x), round_tf32(w)          # what the producers of this mode hand to the kernel
+    ref = F.conv2d(x.double(), w.double(), b.double(), 1, k // 2, 1, groups)
     if res is not None:
-        ref = ref + res
+        ref = ref + res.double()
     if relu:
         ref = torch.relu(ref)
     out, path = run_conv(dev, x, w, b, res, k, groups, relu, math)
-    assert path == (1 if math == L.MATH_TC else 0), "the tcgen05 kernel must be the one that runs in TC mode"
+    assert path == (0 if math == L.MATH_FP32 else 1), "the tcgen05 kernel must be the one that runs in the TC modes"
     assert torch.isfinite(out).all()
-    if math == L.MATH_TC:
-        # the TC epilogue rounds its output to tf32 for the next layer: compare against the rounded oracle
-        err = float((out - ref).abs().max() / ref.abs().max())
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    if math == L.MATH_TC_FAST:
+        # the epilogue of this mode rounds its output to tf32 for the next layer
         assert err < 2.0 ** -11 * 1.5, err
         assert torch.all((out.view(torch.int32) & 0x1FFF) == 0)
     else:
-        err = float((out - ref).abs().max() / ref.abs().max())
+        # exact fp32 FMA, and error-compensated 3xTF32 on arbitrary fp32 operands: both fp32-class
         assert err < 2e-5, err
 
 
-def test_head_projection_hi_lo_split_is_fp32_accurate():
-    """conv1x1 in TC mode: features tf32-representable, W = W_hi + W_lo -> matches the fp32 product to ~1e-6."""
+def test_head_projection_is_fp32_accurate_on_tensor_cores():
+    """conv1x1 + ReLU of the fused head (K = 2048) with the 3xTF32 kernel on raw fp32 features."""
     import scouter_b200 as sb
     dev = torch.device("cuda", 0)
     r = np.random.RandomState(11)
     Bn, n, ch = 37, 49, 2048
-    feat = round_tf32(torch.from_numpy(np.maximum(r.standard_normal((Bn, n, ch)), 0).astype(np.float32)))
+    feat = torch.from_numpy(np.maximum(r.standard_normal((Bn, n, ch)), 0).astype(np.float32))
     w = torch.from_numpy((r.standard_normal((64, ch)) / np.sqrt(ch)).astype(np.float32))
     b = torch.from_numpy(0.1 * r.standard_normal(64).astype(np.float32))
     ref = torch.relu(feat.double() @ w.double().t() + b.double())
     m = sb.SlotAttention(10, 1, 64, to_k_layer=3, power=2).to(dev).eval()
     desc, packed = m.desc_and_pack(dev)
-    for math, tol in ((L.MATH_FP32, 2e-6), (L.MATH_TC, 2e-6)):
+    for math in (L.MATH_FP32, L.MATH_TC):
         io = L.HeadIO()
         io.batch, io.h, io.w, io.channel, io.layout, io.math = Bn, 7, 7, ch, L.LAYOUT_NHWC, math
         fd, wd, bd = feat.to(dev), w.to(dev), b.to(dev)
-        wtc = torch.empty(128, ch, device=dev)
-        L.check(L.lib().scouter_head_pack_conv(wd.data_ptr(), 64, ch, wtc.data_ptr(), 0))
         pe = sb.build_position_encoding("sine", 64).table(7, 7, dev)
         logits = torch.empty(Bn, 10, device=dev)
         xo = torch.empty(Bn, n, 64, device=dev)
-        io.feat, io.conv_w, io.conv_b, io.conv_w_tc, io.pe = fd.data_ptr(), wd.data_ptr(), bd.data_ptr(), wtc.data_ptr(), pe.data_ptr()
+        io.feat, io.conv_w, io.conv_b, io.pe = fd.data_ptr(), wd.data_ptr(), bd.data_ptr(), pe.data_ptr()
         io.logits, io.attn, io.attn_sum, io.x_out = logits.data_ptr(), 0, 0, xo.data_ptr()
         nbytes = L.lib().scouter_head_workspace_bytes(C.byref(desc), C.byref(io))
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
@@ -116,4 +115,4 @@ def test_head_projection_hi_lo_split_is_fp32_accurate():
         torch.cuda.synchronize()
         err = float((xo.cpu().double() - ref).abs().max() / ref.abs().max())
         print(f"head projection math={math}: rel err {err:.2e}")
-        assert err < tol
+        assert err < 2e-5

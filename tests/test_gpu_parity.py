@@ -4,7 +4,9 @@
 Tolerances (BASELINE.json north_star: 1e-3 relative, fp32):
   logits / log-probs : max|a-b| <= TOL * max(1, max|b|)   (SURVEY.md C.3 acceptance (i); TOL below)
   attention maps     : abs <= max(1e-3, 4 x the reference's own fp32-vs-fp64 floor)   (acceptance (ii))
-The exact-fp32 mode (SCOUTER_MATH_FP32) is held to 2e-5; the tensor-core mode to 1e-3.
+The exact-fp32 mode (SCOUTER_MATH_FP32) is held to 2e-5; the default tensor-core mode (SCOUTER_MATH_TC, error-
+compensated 3xTF32) to 1e-3 -- north_star's bar; the opt-in single-pass tf32 mode is only sanity-checked (5e-2),
+its error being the documented cuDNN-TF32-class rounding amplified by the sum-normalisation.
 """
 import ctypes as C
 
@@ -21,7 +23,7 @@ from scouter_b200 import _lib as L
 from scouter_b200.synth import fill_state_dict, synth_images
 
 pytestmark = pytest.mark.gpu
-TOL = {L.MATH_FP32: 2e-5, L.MATH_TC: 1e-3}
+TOL = {L.MATH_FP32: 2e-5, L.MATH_TC: 1e-3, L.MATH_TC_FAST: 5e-2}
 MATHS = [L.MATH_FP32, L.MATH_TC]
 
 
@@ -139,7 +141,7 @@ def test_backbone_features_vs_golden(dev, math):
     ref = torch.from_numpy(z["feat_sample"])
     err = float((f - ref).abs().max() / ref.abs().max())
     print(f"backbone features math={math}: max err / max|ref| = {err:.2e}")
-    assert err < (1e-5 if math == L.MATH_FP32 else 2e-3)
+    assert err < (1e-5 if math == L.MATH_FP32 else 2e-5)
 
 
 @pytest.mark.parametrize("math", MATHS)
@@ -156,6 +158,17 @@ def test_slot_model_vs_cpu_oracle_fresh_inputs(dev, math):
         out = m(x.to(dev))
     assert scaled_err(out, o["log_probs"]) < TOL[math]
     assert float((m.last_attn.cpu() - o["attn"]).abs().max()) < max(TOL[math], 1e-4)
+
+
+def test_tc_fast_mode_is_tf32_class(dev):
+    z, meta = load_golden("cfg2_resnest26d_pos_224")
+    m = build(meta, dev, L.MATH_TC_FAST)
+    x = synth_images(meta["batch"], meta["cin"], meta["size"], meta["size"]).to(dev)
+    with torch.no_grad():
+        out = m(x)
+    e = scaled_err(out, z["log_probs"])
+    print(f"tc_fast (1xTF32) log-prob err {e:.2e}")
+    assert e < TOL[L.MATH_TC_FAST]
 
 
 def test_no_slot_classifier_path(dev):
