@@ -166,7 +166,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_commit(&tfull[acc]);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ===== epilogue: thread = one output row, 32 TMEM lanes per warp =====
         const int q = warp - 4;
         const int row = q * 32 + lane;
