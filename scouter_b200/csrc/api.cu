@@ -43,6 +43,7 @@ struct scouter_plan {
     size_t arena_bytes = 0;
     int launches = 0;
     std::vector<UmmaConvPlan> umma;  // per op; .valid says whether the tcgen05 kernel takes it
+    std::vector<std::vector<float>> host_w, host_b;  // per op: host copies of small stem filter banks
 };
 
 extern "C" int scouter_abi_version(void) { return SCOUTER_ABI_VERSION; }
@@ -78,6 +79,25 @@ extern "C" int scouter_plan_create(const scouter_op_t* ops, int n_ops, int n_buf
     p->ops.assign(ops, ops + n_ops);
     p->bufs.resize(n_buffers);
     p->math = math;
+    p->host_w.resize(n_ops);
+    p->host_b.resize(n_ops);
+    for (int i = 0; i < n_ops; ++i) {
+        const scouter_op_t& o = ops[i];
+        // stem filter banks (<= 864 floats) are kept on the host too: they are passed by value in the kernel parameters
+        if (o.kind == SCOUTER_OP_STEM_CONV && o.kh == 3 && o.kw == 3 && (size_t)o.cout * 9 * o.cin <= 1024) {
+            p->host_w[i].resize((size_t)o.cout * 9 * o.cin);
+            cudaError_t e = cudaMemcpy(p->host_w[i].data(), o.w, p->host_w[i].size() * sizeof(float), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && o.b) {
+                p->host_b[i].resize(o.cout);
+                e = cudaMemcpy(p->host_b[i].data(), o.b, o.cout * sizeof(float), cudaMemcpyDeviceToHost);
+            }
+            if (e != cudaSuccess) {  // e.g. no device (CPU-only shape inference): fall back to the generic stem kernel
+                (void)cudaGetLastError();
+                p->host_w[i].clear();
+                p->host_b[i].clear();
+            }
+        }
+    }
     *out = p;
     return 0;
 }
@@ -228,7 +248,9 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
             case SCOUTER_OP_STEM_CONV: {
                 SC_CHECK_ARG(o.kh == o.kw && o.groups == 1, SCOUTER_E_UNSUPPORTED, "stem conv: square, ungrouped kernels only");
                 StemArgs a{ptr(o.src), o.w, o.b, ptr(o.dst), sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.stride, o.pad,
-                           (o.flags & SCOUTER_F_RELU) ? 1 : 0, rnd};
+                           (o.flags & SCOUTER_F_RELU) ? 1 : 0, rnd,
+                           plan->host_w[i].empty() ? nullptr : plan->host_w[i].data(),
+                           plan->host_b[i].empty() ? nullptr : plan->host_b[i].data()};
                 rc = launch_stem_conv(a, s);
                 break;
             }

@@ -85,6 +85,8 @@ struct StemArgs {
     float* out;        // NHWC
     int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad, relu;
     int round_out;
+    const float* w_host;  // host copies of w / bias (plan-owned) for the constant-bank stem kernel, or null
+    const float* b_host;
 };
 int launch_stem_conv(const StemArgs& a, cudaStream_t s);
 

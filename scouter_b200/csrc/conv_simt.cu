@@ -4,6 +4,8 @@
 //
 // Reference ops replaced (eval mode): nn.Conv2d + BatchNorm2d + ReLU chains of timm/models/resnet.py:401-420,
 // resnest.py:111-143, split_attn.py:54-80, the pools at resnet.py:300,420 and resnest.py:101.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace scouter {
@@ -204,6 +206,78 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(StemArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tiled 3x3 stride-2 pad-1 stem (the deep stem's conv1.0 and the MNIST stem): the filter bank travels as a
+// kernel parameter, i.e. in the constant bank, so every FFMA takes its weight as an immediate constant operand;
+// the CTA stages a (CIN, 17, 65) input patch in shared memory and each thread produces one output pixel x COUT.
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+struct StemConst {
+    float w[9 * CIN * COUT];  // [tap = (r*3+s)*CIN + c][cout]
+    float b[COUT];
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) stem3x3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                        int Ho, int Wo, int relu, int round_out,
+                                                        const __grid_constant__ StemConst<CIN, COUT> cw) {
+    constexpr int TH = 8, TW = 32, PH = 2 * TH + 1, PW = 2 * TW + 1, LDP = PW + 2;
+    __shared__ float patch[CIN][PH][LDP];
+    const int b = blockIdx.z;
+    const int h0 = blockIdx.y * TH, w0 = blockIdx.x * TW;
+    const int hi0 = 2 * h0 - 1, wi0 = 2 * w0 - 1;
+    for (int i = threadIdx.x; i < CIN * PH * PW; i += 256) {
+        int c = i / (PH * PW), r = (i / PW) % PH, x = i % PW;
+        int hi = hi0 + r, wi = wi0 + x;
+        float v = 0.f;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(in + (((long long)b * CIN + c) * H + hi) * W + wi);
+        patch[c][r][x] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / TW, tx = threadIdx.x % TW;
+    const int ho = h0 + ty, wo = w0 + tx;
+    if (ho >= Ho || wo >= Wo) return;
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float v = patch[c][2 * ty + r][2 * tx + s];
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, cw.w[((r * 3 + s) * CIN + c) * COUT + co], acc[co]);
+            }
+    float* op = out + (((long long)b * Ho + ho) * Wo + wo) * COUT;
+#pragma unroll
+    for (int co = 0; co < COUT; co += 4) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = acc[co + j] + cw.b[co + j];
+            if (relu) v[j] = fmaxf(v[j], 0.f);
+            if (round_out) v[j] = to_tf32(v[j]);
+        }
+        *reinterpret_cast<float4*>(op + co) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+template <int CIN, int COUT>
+int launch_stem_tiled(const StemArgs& a, cudaStream_t s) {
+    static_assert(sizeof(StemConst<CIN, COUT>) <= 3800, "filter bank must fit the 4 KB kernel-parameter space");
+    StemConst<CIN, COUT> cw;
+    // host copy is laid out (Cout, 3, 3, Cin): transpose to tap-major
+    for (int co = 0; co < COUT; ++co)
+        for (int t = 0; t < 9 * CIN; ++t) cw.w[t * COUT + co] = a.w_host[co * 9 * CIN + t];
+    for (int co = 0; co < COUT; ++co) cw.b[co] = a.b_host ? a.b_host[co] : 0.f;
+    dim3 grid(cdiv(a.Wo, 32), cdiv(a.Ho, 8), a.B);
+    stem3x3s2_kernel<CIN, COUT><<<grid, 256, 0, s>>>(a.in, a.out, a.H, a.W, a.Ho, a.Wo, a.relu, a.round_out, cw);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pools (NHWC, one thread = one output pixel x 4 channels).
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
@@ -305,42 +379,69 @@ __global__ void __launch_bounds__(256) gap_kernel(const float* __restrict__ in, 
     }
 }
 
-// One CTA per image: h = relu(W1 gap + b1)  (bn1 folded), a = W2 h + b2, softmax over the radix pair.
+// h = relu(W1 gap + b1) (bn1 folded), a = W2 h + b2, softmax over the radix pair.  A CTA serves FC_IMG images at
+// once (every weight it reads is used FC_IMG times) and one slice of the 2C outputs; fc1 is recomputed per slice.
+constexpr int FC_IMG = 8;
 __global__ void __launch_bounds__(256) splat_fc_kernel(const float* __restrict__ gap, const float* __restrict__ w1,
                                                        const float* __restrict__ b1, const float* __restrict__ w2,
-                                                       const float* __restrict__ b2, float* __restrict__ attn, int C,
-                                                       int mid) {
+                                                       const float* __restrict__ b2, float* __restrict__ attn, int B, int C,
+                                                       int mid, int cper) {
     extern __shared__ float sm[];
-    float* sg = sm;       // [C]
-    float* sh = sm + C;   // [mid]
-    const int b = blockIdx.x;
+    float* sg = sm;                 // [FC_IMG][C]
+    float* sh = sm + FC_IMG * C;    // [FC_IMG][mid]
+    const int b0 = blockIdx.x * FC_IMG;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) sg[i] = gap[(long long)b * C + i];
-    __syncthreads();
-    for (int a = warp; a < mid; a += nw) {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w1 + (long long)a * C + c), sg[c], s);
-        s = warp_sum(s);
-        if (lane == 0) sh[a] = fmaxf(s + __ldg(b1 + a), 0.f);
+    for (int i = threadIdx.x; i < FC_IMG * C; i += blockDim.x) {
+        int im = i / C;
+        sg[i] = (b0 + im < B) ? gap[(long long)(b0 + im) * C + (i - im * C)] : 0.f;
     }
     __syncthreads();
-    for (int c = warp; c < C; c += nw) {
-        float s0 = 0.f, s1 = 0.f;
-        for (int a = lane; a < mid; a += 32) {
-            float h = sh[a];
-            s0 = fmaf(__ldg(w2 + (long long)c * mid + a), h, s0);
-            s1 = fmaf(__ldg(w2 + (long long)(C + c) * mid + a), h, s1);
+    for (int a = warp; a < mid; a += nw) {
+        float s[FC_IMG];
+#pragma unroll
+        for (int i = 0; i < FC_IMG; ++i) s[i] = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float w = __ldg(w1 + (long long)a * C + c);
+#pragma unroll
+            for (int i = 0; i < FC_IMG; ++i) s[i] = fmaf(w, sg[i * C + c], s[i]);
         }
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
+#pragma unroll
+        for (int i = 0; i < FC_IMG; ++i) s[i] = warp_sum(s[i]);
         if (lane == 0) {
-            s0 += __ldg(b2 + c);
-            s1 += __ldg(b2 + C + c);
-            float mx = fmaxf(s0, s1);
-            float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
-            float inv = 1.f / (e0 + e1);
-            attn[(long long)b * 2 * C + c] = e0 * inv;
-            attn[(long long)b * 2 * C + C + c] = e1 * inv;
+            const float bb = __ldg(b1 + a);
+#pragma unroll
+            for (int i = 0; i < FC_IMG; ++i) sh[i * mid + a] = fmaxf(s[i] + bb, 0.f);
+        }
+    }
+    __syncthreads();
+    const int c_end = min(C, (int)(blockIdx.y + 1) * cper);
+    for (int c = blockIdx.y * cper + warp; c < c_end; c += nw) {
+        float s0[FC_IMG], s1[FC_IMG];
+#pragma unroll
+        for (int i = 0; i < FC_IMG; ++i) s0[i] = s1[i] = 0.f;
+        for (int a = lane; a < mid; a += 32) {
+            const float wa = __ldg(w2 + (long long)c * mid + a), wb = __ldg(w2 + (long long)(C + c) * mid + a);
+#pragma unroll
+            for (int i = 0; i < FC_IMG; ++i) {
+                const float h = sh[i * mid + a];
+                s0[i] = fmaf(wa, h, s0[i]);
+                s1[i] = fmaf(wb, h, s1[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < FC_IMG; ++i) { s0[i] = warp_sum(s0[i]); s1[i] = warp_sum(s1[i]); }
+        if (lane == 0) {
+            const float ba = __ldg(b2 + c), bb = __ldg(b2 + C + c);
+#pragma unroll
+            for (int i = 0; i < FC_IMG; ++i) {
+                if (b0 + i >= B) break;
+                float x0 = s0[i] + ba, x1 = s1[i] + bb;
+                float mx = fmaxf(x0, x1);
+                float e0 = expf(x0 - mx), e1 = expf(x1 - mx);
+                float inv = 1.f / (e0 + e1);
+                attn[(long long)(b0 + i) * 2 * C + c] = e0 * inv;
+                attn[(long long)(b0 + i) * 2 * C + C + c] = e1 * inv;
+            }
         }
     }
 }
@@ -430,6 +531,10 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
 }
 
 int launch_stem_conv(const StemArgs& a, cudaStream_t s) {
+    if (a.w_host && a.k == 3 && a.stride == 2 && a.pad == 1 && a.B <= 65535) {
+        if (a.Cin == 3 && a.Cout == 32) return launch_stem_tiled<3, 32>(a, s);
+        if (a.Cin == 1 && a.Cout == 64) return launch_stem_tiled<1, 64>(a, s);
+    }
     SC_CHECK_ARG(a.Cin >= 1 && a.Cin <= 4, SCOUTER_E_UNSUPPORTED, "stem conv: Cin = %d (supports 1..4)", a.Cin);
     SC_CHECK_ARG(a.Cout % 4 == 0, SCOUTER_E_UNSUPPORTED, "stem conv: Cout = %d not a multiple of 4", a.Cout);
     size_t smem = (size_t)a.k * a.k * a.Cin * a.Cout * sizeof(float);
@@ -475,8 +580,13 @@ int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s
 
 int launch_splat_fc(const float* gap, const float* w1, const float* b1, const float* w2, const float* b2, float* attn,
                     int B, int C, int mid, cudaStream_t s) {
-    size_t smem = (size_t)(C + mid) * sizeof(float);
-    splat_fc_kernel<<<B, 256, smem, s>>>(gap, w1, b1, w2, b2, attn, C, mid);
+    const int gx = cdiv(B, FC_IMG);
+    int gy = std::max(1, std::min(cdiv(296, gx), cdiv(C, 8)));  // ~2 CTAs per SM worth of slices
+    const int cper = cdiv(C, gy);
+    gy = cdiv(C, cper);
+    size_t smem = (size_t)FC_IMG * (C + mid) * sizeof(float);
+    SC_CHECK_ARG(smem <= 48 * 1024, SCOUTER_E_UNSUPPORTED, "splat fc: C=%d mid=%d needs %zu bytes of shared memory", C, mid, smem);
+    splat_fc_kernel<<<dim3(gx, gy), 256, smem, s>>>(gap, w1, b1, w2, b2, attn, B, C, mid, cper);
     SC_LAUNCH_CHECK();
     return 0;
 }

@@ -42,6 +42,7 @@ struct UmmaArgs {
     int kw, pad, kblocks, cblocks;
     int relu, round_out;
     int a_bytes;
+    int chunk;  // k-blocks per accumulation chunk
 };
 
 template <int BN, bool SPLIT>
@@ -52,7 +53,11 @@ struct Cfg {
     static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | B | A_r | B_r]
     static constexpr int STAGES = (200 * 1024 / STAGE) > 8 ? 8 : (200 * 1024 / STAGE);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int THREADS = SPLIT ? 384 : 256;
+    // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
+    // fp32 sums of the chunked accumulation fit in registers (64 per thread).
+    static constexpr int EPI_GROUPS = (SPLIT && BN == 128) ? 2 : 1;
+    static constexpr int NC = BN / EPI_GROUPS;               // columns per epilogue thread
+    static constexpr int THREADS = SPLIT ? 512 : 256;
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
@@ -64,9 +69,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
     uint64_t* empty = full + C::STAGES;
-    uint64_t* tfull = empty + C::STAGES;
-    uint64_t* tempty = tfull + 2;
-    uint64_t* split_done = tempty + 2;  // [STAGES], SPLIT only: remainders written, stage ready for the issuer
+    uint64_t* cfull = empty + C::STAGES;   // [2] accumulator chunk complete (tcgen05.commit)
+    uint64_t* cempty = cfull + 2;          // [2] accumulator chunk drained by every epilogue thread
+    uint64_t* split_done = cempty + 2;     // [STAGES], SPLIT only: remainders written, stage ready for the issuer
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(split_done + C::STAGES);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -81,8 +86,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&split_done[i], 128);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 128);
+            mbar_init(&cfull[i], 1);
+            mbar_init(&cempty[i], 128 * C::EPI_GROUPS);
         }
         fence_barrier_init();
     }
@@ -93,6 +98,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr;
 
     const int total = p.m_tiles * p.n_tiles * p.groups;
+    // The K loop of a tile is cut into chunks of p.chunk k-blocks; each chunk accumulates in its own TMEM buffer
+    // (the two buffers alternate across chunks AND tiles) and the epilogue threads merge the chunks in fp32
+    // round-to-nearest registers.  The TMEM accumulator truncates on every MMA, so this bounds the truncation
+    // chain to chunk*4*(SPLIT?3:1) steps; with one chunk per tile it degenerates to plain double buffering.
+    const int nchunks = (p.kblocks + p.chunk - 1) / p.chunk;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -133,50 +143,53 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t idesc = idesc_tf32(128, BN);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(SPLIT ? &split_done[stage] : &full[stage], phase);
+            uint32_t cc = 0;  // running chunk counter
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.chunk, ++cc) {
+                    const int buf = cc & 1;
+                    mbar_wait(&cempty[buf], ((cc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * C::STAGE);
-                    const uint64_t da = smem_desc_sw128(sa);
-                    const uint64_t db = smem_desc_sw128(sa + C::A_BYTES);
-                    // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom (+2 in 16-byte units)
-                    if constexpr (SPLIT) {
-                        const uint64_t dar = smem_desc_sw128(sa + C::RAW);
-                        const uint64_t dbr = smem_desc_sw128(sa + C::RAW + C::A_BYTES);
+                    const uint32_t d_tmem = tmem_base + buf * BN;
+                    const int kb1 = min(kb0 + p.chunk, p.kblocks);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(SPLIT ? &split_done[stage] : &full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+                        const uint64_t da = smem_desc_sw128(sa);
+                        const uint64_t db = smem_desc_sw128(sa + C::A_BYTES);
+                        const uint32_t first = kb != kb0;
+                        // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
+                        if constexpr (SPLIT) {
+                            const uint64_t dar = smem_desc_sw128(sa + C::RAW);
+                            const uint64_t dbr = smem_desc_sw128(sa + C::RAW + C::A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_tf32(d_tmem, da + 2 * k, dbr + 2 * k, idesc, (kb | k) != 0);  // A_t * W_r
-                            umma_tf32(d_tmem, dar + 2 * k, db + 2 * k, idesc, 1);              // A_r * W_t
-                            umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);               // A_t * W_t
+                            for (int k = 0; k < 4; ++k) {
+                                umma_tf32(d_tmem, da + 2 * k, dbr + 2 * k, idesc, first | k);  // A_t * W_r
+                                umma_tf32(d_tmem, dar + 2 * k, db + 2 * k, idesc, 1);          // A_r * W_t
+                                umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);           // A_t * W_t
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, first | k);
                         }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&cfull[buf]);
                 }
-                umma_commit(&tfull[acc]);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===== epilogue: thread = one output row, 32 TMEM lanes per warp =====
-        const int q = warp - 4;
+    } else if ((warp >= 4 && warp < 8) || (C::EPI_GROUPS == 2 && warp >= 12)) {
+        // ===== epilogue: thread = one output row (32 TMEM lanes per warp) x NC columns =====
+        const int q = warp & 3;
+        const int grp = warp >= 12 ? 1 : 0;
         const int row = q * 32 + lane;
-        int it = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int col0 = grp * C::NC;
+        uint32_t cc = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int nt = t % p.n_tiles;
             const int mt = (t / p.n_tiles) % p.m_tiles;
             const int g = t / (p.n_tiles * p.m_tiles);
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
             bool valid;
             long long orow;
             if (p.mode) {
@@ -192,64 +205,95 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 orow = (long long)mt * 128 + row;
                 valid = orow < p.M;
             }
-            const int ch0 = g * p.cout_g + nt * BN;
+            const int ch0 = g * p.cout_g + nt * BN + col0;
             float* op = p.out + orow * p.Cout + ch0;
             const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
-                tmem_ld_wait();
-                if (valid) {
+
+            auto finish = [&](const uint32_t (&r)[32], int c) {   // bias / residual / ReLU / store of 32 columns
+                if (!valid) return;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                        if (p.bias) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 32 + 4 * j));
-                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                        }
-                        if (rp) {
-                            const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + c * 32 + 4 * j));
-                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                        }
-                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        if (p.round_out) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
-                        *reinterpret_cast<float4*>(op + c * 32 + 4 * j) = v;
+                for (int j = 0; j < 8; ++j) {
+                    float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    if (p.bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 32 + 4 * j));
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     }
+                    if (rp) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + c * 32 + 4 * j));
+                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                    }
+                    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (p.round_out) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                    *reinterpret_cast<float4*>(op + c * 32 + 4 * j) = v;
                 }
+            };
+
+            if constexpr (SPLIT) {
+                float acc[C::NC];
+#pragma unroll
+                for (int j = 0; j < C::NC; ++j) acc[j] = 0.f;
+                for (int ch = 0; ch < nchunks; ++ch, ++cc) {
+                    const int buf = cc & 1;
+                    mbar_wait(&cfull[buf], (cc >> 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < C::NC / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + col0 + c * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&cempty[buf]);
+                }
+#pragma unroll
+                for (int c = 0; c < C::NC / 32; ++c) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[c * 32 + j]);
+                    finish(r, c);
+                }
+            } else {
+                const int buf = cc & 1;
+                mbar_wait(&cfull[buf], (cc >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
+                    tmem_ld_wait();
+                    finish(r, c);
+                }
+                tc_fence_before();
+                mbar_arrive(&cempty[buf]);
+                ++cc;
             }
-            tc_fence_before();
-            mbar_arrive(&tempty[acc]);
         }
-    }
-    if constexpr (SPLIT) {
-        if (warp >= 8) {
-            // ===== operand splitters: x_r = x - trunc19(x) for the A and B tiles, same (swizzled) offsets =====
-            const int tid = threadIdx.x - 256;  // 0..127
-            constexpr int VEC = C::RAW / 16;    // float4 per stage (A then B, contiguous)
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    const float4* src = reinterpret_cast<const float4*>(smem + stage * C::STAGE);
-                    float4* dst = reinterpret_cast<float4*>(smem + stage * C::STAGE + C::RAW);
+    } else if (SPLIT && warp >= 8 && warp < 12) {
+        // ===== operand splitters: x_r = x - trunc19(x) for the A and B tiles, same (swizzled) offsets =====
+        const int tid = threadIdx.x - 256;  // 0..127
+        constexpr int VEC = C::RAW / 16;    // float4 per stage (A then B, contiguous)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                mbar_wait(&full[stage], phase);
+                const float4* src = reinterpret_cast<const float4*>(smem + stage * C::STAGE);
+                float4* dst = reinterpret_cast<float4*>(smem + stage * C::STAGE + C::RAW);
 #pragma unroll 4
-                    for (int i = tid; i < VEC; i += 128) {
-                        float4 v = src[i];
-                        v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                        v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                        v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                        v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                        dst[i] = v;
-                    }
-                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                    mbar_arrive(&split_done[stage]);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                for (int i = tid; i < VEC; i += 128) {
+                    float4 v = src[i];
+                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    dst[i] = v;
                 }
+                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&split_done[stage]);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     }
@@ -334,6 +378,8 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     u.cblocks = cin_g / 32;
     u.kblocks = a.kh * a.kw * u.cblocks;
     u.relu = a.relu; u.round_out = a.round_out;
+    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();
+    u.chunk = a.split ? chunk_kb : u.kblocks;
     u.n_tiles = cout_g / BN;
 
     const bool reuse = plan.valid && plan.in == a.in && plan.w == a.w && plan.B == a.B && plan.H == a.H && plan.W == a.W &&

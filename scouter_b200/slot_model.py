@@ -77,6 +77,7 @@ class SlotModel(nn.Module):
         self.use_cuda_graph = False
         self.keep_attn = False        # retain the final attention maps in .last_attn (first-class output)
         self.last_attn = None
+        self.last_logits = None
         self._states = OrderedDict()
         self._prog = None
         self._sig = None
@@ -212,6 +213,7 @@ class SlotModel(nn.Module):
             else:
                 self._launch(st, x, target)
             output = st.log_probs.clone()
+            self.last_logits = st.logits          # pre-softmax class scores of this call (overwritten by the next)
             if st.attn is not None:
                 self.last_attn = st.attn
                 self.slot.last_attn = st.attn
