@@ -188,7 +188,8 @@ typedef struct scouter_op {
     int32_t mid;              /* SPLAT_FC: attn_chs (width of fc1) */
     int32_t reserved;
     /* Folded parameters, device pointers, fp32:
-     *   CONV / STEM_CONV: w = (cout, kh, kw, cin/groups) "OHWI", b = (cout)
+     *   CONV / STEM_CONV: w = (cout, kh, kw, cin/groups) "OHWI", b = (cout); for SCOUTER_MATH_TC an optional
+     *     w2 = W - trunc19(W) (same layout, stored directly after w) lets the kernels skip the on-the-fly weight split
      *   SPLAT_FC: w = fc1 (mid, C) with bn1 folded, b = (mid); w2 = fc2 (2C, mid), b2 = (2C) */
     const float* w;
     const float* b;
@@ -219,7 +220,7 @@ int scouter_plan_launch_count(const scouter_plan_t* plan);
 
 /* One SCOUTER_OP_CONV outside a plan (unit tests of the kernels; same dispatch as scouter_plan_run):
  * in (B,H,W,cin) NHWC, res (B,Ho,Wo,cout) or NULL, out (B,Ho,Wo,cout).  scouter_conv_path reports which
- * kernel family the dispatch picks: 1 = tcgen05/TMA, 0 = CUDA-core fp32. */
+ * kernel family the dispatch picks: 2 = tcgen05 halo 3x3, 1 = tcgen05 flat / tap-reload, 0 = CUDA-core fp32. */
 int scouter_conv_forward(const scouter_op_t* op, const float* in, const float* res, float* out, int batch, int h, int w,
                          int math, scouter_stream_t stream);
 int scouter_conv_path(const scouter_op_t* op, int batch, int h, int w, int math);

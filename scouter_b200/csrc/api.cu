@@ -257,8 +257,8 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
             case SCOUTER_OP_CONV: {
                 ConvArgs a{ptr(o.src), o.w, o.b, (o.flags & SCOUTER_F_RESIDUAL) ? ptr(o.src2) : nullptr, ptr(o.dst),
                            sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.kw, o.stride, o.pad, o.groups,
-                           (o.flags & SCOUTER_F_RELU) ? 1 : 0, (rnd && db.H * db.W > 1) ? 1 : 0, split};
-                if (plan->math != SCOUTER_MATH_FP32 && umma_conv_supported(a)) rc = launch_conv_umma(a, plan->umma[i], s);
+                           (o.flags & SCOUTER_F_RELU) ? 1 : 0, (rnd && db.H * db.W > 1) ? 1 : 0, split, split ? o.w2 : nullptr};
+                if (plan->math != SCOUTER_MATH_FP32 && tc_conv_supported(a)) rc = launch_conv_tc(a, plan->umma[i], s);
                 else rc = launch_conv_simt(a, s);
                 break;
             }
@@ -333,7 +333,7 @@ extern "C" int scouter_head_forward(const scouter_xslot_desc_t* desc, const void
     // conv1x1 + bias + ReLU (slot_model.py:108-109)
     // The projection always runs error-compensated on the tensor cores (it is HBM-bound: the extra MMAs are free).
     ConvArgs c{feat, io->conv_w, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, XD,
-               1, 1, 1, 0, 1, 1, 0, 1};
+               1, 1, 1, 0, 1, 1, 0, 1, nullptr};
     int rc;
     if (io->math != SCOUTER_MATH_FP32 && umma_conv_supported(c)) {
         UmmaConvPlan tmp;
@@ -392,14 +392,16 @@ static int conv_args_from_op(const scouter_op_t* o, const float* in, const float
     SC_CHECK_ARG(Ho > 0 && Wo > 0, SCOUTER_E_INVALID, "conv_forward: empty output");
     *a = ConvArgs{in, o->w, o->b, (o->flags & SCOUTER_F_RESIDUAL) ? res : nullptr, out, B, H, W, o->cin, Ho, Wo, o->cout,
                   o->kh, o->kw, o->stride, o->pad, o->groups, (o->flags & SCOUTER_F_RELU) ? 1 : 0,
-                  math == SCOUTER_MATH_TC_FAST ? 1 : 0, math == SCOUTER_MATH_TC ? 1 : 0};
+                  math == SCOUTER_MATH_TC_FAST ? 1 : 0, math == SCOUTER_MATH_TC ? 1 : 0,
+                  math == SCOUTER_MATH_TC ? o->w2 : nullptr};
     return 0;
 }
 
 extern "C" int scouter_conv_path(const scouter_op_t* op, int batch, int h, int w, int math) {
     ConvArgs a;
     if (int e = conv_args_from_op(op, nullptr, nullptr, nullptr, batch, h, w, math, &a)) return e;
-    return (math != SCOUTER_MATH_FP32 && umma_conv_supported(a)) ? 1 : 0;
+    if (math == SCOUTER_MATH_FP32) return 0;
+    return halo_conv_supported(a) ? 2 : (umma_conv_supported(a) ? 1 : 0);
 }
 
 extern "C" int scouter_conv_forward(const scouter_op_t* op, const float* in, const float* res, float* out, int batch, int h, int w,
@@ -407,9 +409,9 @@ extern "C" int scouter_conv_forward(const scouter_op_t* op, const float* in, con
     ConvArgs a;
     if (int e = conv_args_from_op(op, in, res, out, batch, h, w, math, &a)) return e;
     SC_CHECK_ARG(in && out && op->w, SCOUTER_E_INVALID, "conv_forward: NULL pointer");
-    if (math != SCOUTER_MATH_FP32 && umma_conv_supported(a)) {
+    if (math != SCOUTER_MATH_FP32 && tc_conv_supported(a)) {
         UmmaConvPlan tmp;
-        return launch_conv_umma(a, tmp, (cudaStream_t)stream);
+        return launch_conv_tc(a, tmp, (cudaStream_t)stream);
     }
     return launch_conv_simt(a, (cudaStream_t)stream);
 }

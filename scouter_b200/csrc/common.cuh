@@ -74,7 +74,8 @@ struct ConvArgs {
     float* out;         // NHWC (B,Ho,Wo,Cout)
     int B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, groups, relu;
     int round_out;  // round the stored activations to tf32 (SCOUTER_MATH_TC: the next conv's MMA reads them as tf32)
-    int split;      // tcgen05 only: error-compensated 3xTF32 (operands split on the fly into trunc19 + remainder)
+    int split;      // tcgen05 only: error-compensated 3xTF32 (operands split into trunc19 + remainder)
+    const float* w_rem;  // optional pre-split remainder weights W - trunc19(W), laid out like w and directly after it
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 

@@ -12,6 +12,8 @@ namespace scouter {
 // Per-op cached launch state: the two TMA descriptors and the spatial tile they were built for.
 struct UmmaConvPlan {
     bool valid = false;
+    bool halo = false;
+    bool presplit = false;
     CUtensorMap tmA, tmB;
     const float* in = nullptr;
     const float* w = nullptr;
@@ -21,5 +23,13 @@ struct UmmaConvPlan {
 
 bool umma_conv_supported(const ConvArgs& a);
 int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s);
+// 3x3 from one halo tile per channel block (umma_halo.cu); needs a.split and a.w_rem
+bool halo_conv_supported(const ConvArgs& a);
+int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s);
+// dispatch: halo kernel when it applies, else the tap-reload / flat kernel
+inline bool tc_conv_supported(const ConvArgs& a) { return halo_conv_supported(a) || umma_conv_supported(a); }
+inline int launch_conv_tc(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
+    return halo_conv_supported(a) ? launch_conv_halo(a, plan, s) : launch_conv_umma(a, plan, s);
+}
 
 }  // namespace scouter

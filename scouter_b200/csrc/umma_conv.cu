@@ -43,6 +43,7 @@ struct UmmaArgs {
     int relu, round_out;
     int a_bytes;
     int chunk;  // k-blocks per accumulation chunk
+    int rem_rows;  // SPLIT: > 0 = weights are pre-split, remainder rows start at this row of the weight map
 };
 
 template <int BN, bool SPLIT>
@@ -123,7 +124,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::STAGE;
                     uint8_t* sb = sa + C::A_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + C::B_BYTES));
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + C::B_BYTES + (SPLIT && p.rem_rows ? C::B_BYTES : 0)));
                     const int tap = kb / p.cblocks;
                     const int c0 = p.cin_g * g + (kb - tap * p.cblocks) * 32;
                     if (p.mode) {
@@ -133,6 +134,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_load_2d(sa, &tmA, &full[stage], c0, mt * 128);
                     }
                     tma_load_2d(sb, &tmB, &full[stage], kb * 32, g * p.cout_g + nt * BN);
+                    if (SPLIT && p.rem_rows)  // pre-split weights: the remainder tile comes from the host-made copy
+                        tma_load_2d(sa + C::RAW + C::A_BYTES, &tmB, &full[stage], kb * 32, p.rem_rows + g * p.cout_g + nt * BN);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -274,7 +277,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (SPLIT && warp >= 8 && warp < 12) {
         // ===== operand splitters: x_r = x - trunc19(x) for the A and B tiles, same (swizzled) offsets =====
         const int tid = threadIdx.x - 256;  // 0..127
-        constexpr int VEC = C::RAW / 16;    // float4 per stage (A then B, contiguous)
+        const int VEC = (p.rem_rows ? C::A_BYTES : C::RAW) / 16;  // float4 per stage: A (then B unless pre-split)
         int stage = 0;
         uint32_t phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -380,12 +383,18 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     u.relu = a.relu; u.round_out = a.round_out;
     static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();
     u.chunk = a.split ? chunk_kb : u.kblocks;
+    const bool presplit = a.split && a.w_rem != nullptr;
+    u.rem_rows = presplit ? a.Cout : 0;
     u.n_tiles = cout_g / BN;
 
     const bool reuse = plan.valid && plan.in == a.in && plan.w == a.w && plan.B == a.B && plan.H == a.H && plan.W == a.W &&
-                       plan.Cin == a.Cin && plan.Cout == a.Cout && plan.kh == a.kh && plan.groups == a.groups && plan.BN == BN;
+                       plan.Cin == a.Cin && plan.Cout == a.Cout && plan.kh == a.kh && plan.groups == a.groups && plan.BN == BN &&
+                       !plan.halo && plan.presplit == presplit;
     if (!reuse) {
         CUresult r;
+        if (presplit)
+            SC_CHECK_ARG(a.w_rem == a.w + (size_t)a.Cout * a.kh * a.kw * cin_g, SCOUTER_E_INVALID,
+                         "conv_umma: the remainder weights must directly follow the weights in memory");
         if (u.mode) {
             choose_tile(a.B, a.H, a.W, plan.Wb, plan.Hb, plan.Nb);
             cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
@@ -405,14 +414,14 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
         }
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
         const cuuint64_t Kt = (cuuint64_t)a.kh * a.kw * cin_g;
-        cuuint64_t dimsB[2] = {Kt, (cuuint64_t)a.Cout};
+        cuuint64_t dimsB[2] = {Kt, (cuuint64_t)a.Cout * (presplit ? 2 : 1)};
         cuuint64_t stridesB[1] = {Kt * 4};
         cuuint32_t boxB[2] = {32, (cuuint32_t)BN};
         cuuint32_t esB[2] = {1, 1};
         r = enc(&plan.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.w, dimsB, stridesB, boxB, esB, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
-        plan.valid = true;
+        plan.valid = true; plan.halo = false; plan.presplit = presplit;
         plan.in = a.in; plan.w = a.w; plan.B = a.B; plan.H = a.H; plan.W = a.W; plan.Cin = a.Cin; plan.Cout = a.Cout;
         plan.kh = a.kh; plan.groups = a.groups; plan.BN = BN;
     }

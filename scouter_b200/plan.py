@@ -54,6 +54,12 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def trunc19_remainder(t: torch.Tensor) -> torch.Tensor:
+    """x - trunc19(x): what is left after kind::tf32 reads the top 19 bits of an fp32 word (exact in fp32)."""
+    hi = (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    return t - hi
+
+
 class Program:
     """Accumulates ops; keeps every packed tensor alive."""
 
@@ -84,10 +90,16 @@ class Program:
         w, b = fold_conv_bn(conv, bn)
         if self.math == L.MATH_TC_FAST and not stem:
             w = round_tf32(w)        # 1-pass kind::tf32 reads the top 19 bits: make that a rounding, not a truncation
+        w2 = None
+        if self.math == L.MATH_TC and not stem:
+            # pre-split for the 3xTF32 kernels: [W ; W - trunc19(W)] in one allocation (the kernels address the
+            # remainder rows through the same TMA map)
+            both = torch.cat([w, trunc19_remainder(w)], dim=0).contiguous()
+            w, w2 = both[: w.shape[0]], both[w.shape[0]:]
         flags = (L.F_RELU if relu else 0) | (L.F_RESIDUAL if residual >= 0 else 0)
         return self.emit(L.OP_STEM_CONV if stem else L.OP_CONV, src, self.buf(), src2=residual,
                          cin=conv.in_channels, cout=conv.out_channels, k=conv.kernel_size[0], stride=conv.stride[0],
-                         pad=conv.padding[0], groups=conv.groups, flags=flags, w=w, b=b)
+                         pad=conv.padding[0], groups=conv.groups, flags=flags, w=w, b=b, w2=w2)
 
 
 def _lower_resnest_block(p: Program, blk, x: int) -> int:

@@ -39,18 +39,24 @@ CASES = [
 ]
 
 
-def run_conv(dev, x, w, b, res, k, groups, relu, math):
+def run_conv(dev, x, w, b, res, k, groups, relu, math, presplit=False):
     """x NCHW cpu, w (Cout,Cin/g,k,k) cpu -> out NCHW cpu via the library."""
+    from scouter_b200.plan import trunc19_remainder
     Bn, Cin, H, W = x.shape
     Cout = w.shape[0]
     xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
     wd = w.permute(0, 2, 3, 1).contiguous().to(dev)
+    w2 = 0
+    if presplit:                                      # [W ; W - trunc19(W)] in one allocation, like plan.py
+        both = torch.cat([wd, trunc19_remainder(wd)], dim=0).contiguous()
+        wd = both[:Cout]
+        w2 = both[Cout:].data_ptr()
     bd = b.to(dev)
     rd = res.permute(0, 2, 3, 1).contiguous().to(dev) if res is not None else None
     out = torch.full((Bn, H, W, Cout), float("nan"), device=dev)
     op = L.Op(kind=L.OP_CONV, src=0, src2=-1, dst=1, cin=Cin, cout=Cout, kh=k, kw=k, stride=1, pad=k // 2, groups=groups,
               flags=(L.F_RELU if relu else 0) | (L.F_RESIDUAL if res is not None else 0), mid=0, reserved=0,
-              w=wd.data_ptr(), b=bd.data_ptr(), w2=0, b2=0)
+              w=wd.data_ptr(), b=bd.data_ptr(), w2=w2, b2=0)
     path = L.lib().scouter_conv_path(C.byref(op), Bn, H, W, math)
     L.check(L.lib().scouter_conv_forward(C.byref(op), xd.data_ptr(), L.ptr(rd), out.data_ptr(), Bn, H, W, math, 0))
     torch.cuda.synchronize()
@@ -78,6 +84,14 @@ def test_conv_vs_torch_cpu(case, math):
     assert path == (0 if math == L.MATH_FP32 else 1), "the tcgen05 kernel must be the one that runs in the TC modes"
     assert torch.isfinite(out).all()
     err = float((out.double() - ref).abs().max() / ref.abs().max())
+    if math == L.MATH_TC:
+        # the plan's configuration: host-pre-split weights; 3x3 convs then take the halo kernel (path 2) unless the
+        # map is too small to fill its 128 virtual rows
+        out2, path2 = run_conv(dev, x, w, b, res, k, groups, relu, math, presplit=True)
+        assert path2 in (1, 2) and (k == 1) == (path2 == 1) or min(H, W) <= 9
+        err2 = float((out2.double() - ref).abs().max() / ref.abs().max())
+        print(f"presplit path {path2}: err {err2:.2e} (on-the-fly split {err:.2e})")
+        assert torch.isfinite(out2).all() and err2 < 5e-5, err2
     if math == L.MATH_TC_FAST:
         # the epilogue of this mode rounds its output to tf32 for the next layer
         assert err < 2.0 ** -11 * 1.5, err
