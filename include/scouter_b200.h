@@ -167,8 +167,9 @@ enum scouter_op_kind {
     SCOUTER_OP_MAXPOOL = 3,    /* k/stride/pad max-pool (resnet.py:420) */
     SCOUTER_OP_AVGPOOL = 4,    /* avg-pool; flags select ceil_mode / count_include_pad (resnest.py:101, resnet.py:300) */
     SCOUTER_OP_SPLAT_GAP = 5,  /* (B,H,W,2C) -> (B,C): mean_hw of the radix sum (split_attn.py:62-68) */
-    SCOUTER_OP_SPLAT_FC = 6,   /* fc1(+bn1)+ReLU -> fc2 -> softmax over radix -> (B,2C) (split_attn.py:69-74, :14-28) */
-    SCOUTER_OP_SPLAT_APPLY = 7,/* sum_r x_r * a_r [+ fused avd AvgPool(3,2,1)] (split_attn.py:76-79, resnest.py:101) */
+    /* 6 is retired: fc1(+bn1)+ReLU and fc2 (split_attn.py:69-73) are ordinary SCOUTER_OP_CONVs on (B,1,1,C) */
+    SCOUTER_OP_SPLAT_APPLY = 7,/* r-softmax of the fc2 output over the radix pair (split_attn.py:14-28,74), then
+                                  sum_r x_r * a_r [+ fused avd AvgPool(3,2,1)] (split_attn.py:76-79, resnest.py:101) */
     SCOUTER_OP_GAP = 8,        /* global average pool (B,H,W,C) -> (B,1,1,C)  (no-slot classifier path) */
     SCOUTER_OP_TO_NCHW = 9     /* NHWC -> NCHW copy for callers that want the reference's flattened layout */
 };
@@ -181,16 +182,16 @@ enum scouter_op_kind {
 
 typedef struct scouter_op {
     int32_t kind;
-    int32_t src, src2, dst;   /* buffer ids; src2 = residual (CONV) / attention vector (SPLAT_APPLY) / -1 */
+    int32_t src, src2, dst;   /* buffer ids; src2 = residual (CONV) / fc2 output (B,2C) (SPLAT_APPLY) / -1 */
     int32_t cin, cout;
     int32_t kh, kw, stride, pad, groups;
     int32_t flags;
-    int32_t mid;              /* SPLAT_FC: attn_chs (width of fc1) */
+    int32_t mid;              /* unused (0) */
     int32_t reserved;
     /* Folded parameters, device pointers, fp32:
      *   CONV / STEM_CONV: w = (cout, kh, kw, cin/groups) "OHWI", b = (cout); for SCOUTER_MATH_TC an optional
      *     w2 = W - trunc19(W) (same layout, stored directly after w) lets the kernels skip the on-the-fly weight split
-     *   SPLAT_FC: w = fc1 (mid, C) with bn1 folded, b = (mid); w2 = fc2 (2C, mid), b2 = (2C) */
+     */
     const float* w;
     const float* b;
     const float* w2;

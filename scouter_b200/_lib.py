@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscouter_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_simt.cu", "xslot.cu", "umma_conv.cu", "umma_halo.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "umma_conv.cu", "umma_halo.cu"]
 
 OK = 0
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
@@ -20,7 +20,7 @@ MATH_FP32, MATH_TC, MATH_TC_FAST = 0, 1, 2
 MAX_TO_K_LAYERS = 8
 
 OP_STEM_CONV, OP_CONV, OP_MAXPOOL, OP_AVGPOOL = 1, 2, 3, 4
-OP_SPLAT_GAP, OP_SPLAT_FC, OP_SPLAT_APPLY, OP_GAP, OP_TO_NCHW = 5, 6, 7, 8, 9
+OP_SPLAT_GAP, OP_SPLAT_APPLY, OP_GAP, OP_TO_NCHW = 5, 7, 8, 9
 F_RELU, F_RESIDUAL, F_CEIL_MODE, F_COUNT_INCLUDE_PAD, F_AVD_POOL = 1, 2, 4, 8, 16
 
 _fp = C.c_void_p  # device pointers travel as integers

@@ -41,6 +41,7 @@ struct scouter_plan {
     int math = SCOUTER_MATH_FP32;
     bool bound = false;
     size_t arena_bytes = 0;
+    size_t scratch_off = 0;  // shared scratch at the end of the arena (split-attention GAP partial sums)
     int launches = 0;
     std::vector<UmmaConvPlan> umma;  // per op; .valid says whether the tcgen05 kernel takes it
     std::vector<std::vector<float>> host_w, host_b;  // per op: host copies of small stem filter banks
@@ -65,14 +66,12 @@ extern "C" int scouter_plan_create(const scouter_op_t* ops, int n_ops, int n_buf
     SC_CHECK_ARG(math >= SCOUTER_MATH_FP32 && math <= SCOUTER_MATH_TC_FAST, SCOUTER_E_INVALID, "plan_create: math=%d", math);
     for (int i = 0; i < n_ops; ++i) {
         const scouter_op_t& o = ops[i];
-        SC_CHECK_ARG(o.kind >= SCOUTER_OP_STEM_CONV && o.kind <= SCOUTER_OP_TO_NCHW, SCOUTER_E_INVALID,
+        SC_CHECK_ARG(o.kind >= SCOUTER_OP_STEM_CONV && o.kind <= SCOUTER_OP_TO_NCHW && o.kind != 6, SCOUTER_E_INVALID,
                      "plan_create: op %d has unknown kind %d", i, o.kind);
         SC_CHECK_ARG(o.src >= 0 && o.src < n_buffers && o.dst > 0 && o.dst < n_buffers && o.src2 < n_buffers,
                      SCOUTER_E_INVALID, "plan_create: op %d references a buffer outside [0,%d)", i, n_buffers);
         if (o.kind == SCOUTER_OP_STEM_CONV || o.kind == SCOUTER_OP_CONV)
             SC_CHECK_ARG(o.w != nullptr, SCOUTER_E_INVALID, "plan_create: op %d (conv) has no weights", i);
-        if (o.kind == SCOUTER_OP_SPLAT_FC)
-            SC_CHECK_ARG(o.w && o.b && o.w2 && o.b2 && o.mid > 0, SCOUTER_E_INVALID, "plan_create: op %d (splat fc) incomplete", i);
     }
     scouter_plan* p = new (std::nothrow) scouter_plan();
     SC_CHECK_ARG(p, SCOUTER_E_INVALID, "plan_create: out of host memory");
@@ -148,10 +147,6 @@ extern "C" int scouter_plan_bind(scouter_plan_t* plan, int batch, int cin, int h
                 SC_CHECK_ARG(s.C == 2 * o.cout, SCOUTER_E_INVALID, "plan_bind: op %d (splat gap) wants %d channels, got %d", i, 2 * o.cout, s.C);
                 d.H = d.W = 1; d.C = o.cout;
                 break;
-            case SCOUTER_OP_SPLAT_FC:
-                SC_CHECK_ARG(s.C == o.cin && o.cout == 2 * o.cin, SCOUTER_E_INVALID, "plan_bind: op %d (splat fc) channel mismatch", i);
-                d.H = d.W = 1; d.C = o.cout;
-                break;
             case SCOUTER_OP_SPLAT_APPLY:
                 SC_CHECK_ARG(s.C == 2 * o.cout && o.src2 >= 0, SCOUTER_E_INVALID, "plan_bind: op %d (splat apply) channel mismatch", i);
                 if (o.flags & SCOUTER_F_AVD_POOL) { d.H = pool_out(s.H, 3, 2, 1, false); d.W = pool_out(s.W, 3, 2, 1, false); }
@@ -203,8 +198,20 @@ extern "C" int scouter_plan_bind(scouter_plan_t* plan, int batch, int cin, int h
                        return l.buf != dst && b.last_use >= 0 && b.last_use <= i;
                    }), live.end());
     }
-    plan->arena_bytes = high;
-    plan->launches = n_ops;
+    size_t scratch = 0;
+    int launches = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const scouter_op_t& o = plan->ops[i];
+        ++launches;
+        if (o.kind == SCOUTER_OP_SPLAT_GAP) {
+            const Buf& sb = plan->bufs[o.src];
+            scratch = std::max(scratch, (size_t)sb.B * splat_gap_splits(sb.B, sb.H * sb.W) * 2 * o.cout * sizeof(float));
+            ++launches;  // partial + finish
+        }
+    }
+    plan->scratch_off = high;
+    plan->arena_bytes = high + align_up(scratch, 1024);
+    plan->launches = launches;
     plan->umma.assign(n_ops, UmmaConvPlan());
     plan->bound = true;
     return 0;
@@ -270,10 +277,7 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
                                     (o.flags & SCOUTER_F_COUNT_INCLUDE_PAD) ? 1 : 0, rnd, s);
                 break;
             case SCOUTER_OP_SPLAT_GAP:
-                rc = launch_splat_gap(ptr(o.src), ptr(o.dst), sb.B, sb.H * sb.W, o.cout, s);
-                break;
-            case SCOUTER_OP_SPLAT_FC:
-                rc = launch_splat_fc(ptr(o.src), o.w, o.b, o.w2, o.b2, ptr(o.dst), sb.B, o.cin, o.mid, s);
+                rc = launch_splat_gap(ptr(o.src), (float*)(base + plan->scratch_off), ptr(o.dst), sb.B, sb.H * sb.W, o.cout, s);
                 break;
             case SCOUTER_OP_SPLAT_APPLY:
                 rc = launch_splat_apply(ptr(o.src), ptr(o.src2), ptr(o.dst), sb.B, sb.H, sb.W, o.cout, db.H, db.W,

@@ -1,0 +1,239 @@
+// Memory-bound helpers of the backbone: pools, split-attention reductions and re-weighting, global average pool.
+// All are NHWC, float4 per thread, indexed through a 3-D grid (x = column*channel-quad, y = row, z = image) so that no
+// 64-bit division sits on the address path, and written to keep several independent 16-byte loads in flight per
+// thread (HBM needs ~90 KB outstanding per SM to reach peak).
+//
+// Reference ops: nn.MaxPool2d(3,2,1) resnet.py:420; AvgPool2d(2,2,ceil_mode,count_include_pad=False) resnet.py:300;
+// AvgPool2d(3,2,1) resnest.py:101; the radix-sum / GAP / r-softmax / re-weighting of split_attn.py:62-79.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace scouter {
+namespace {
+
+#define SC_PIXEL_INDEX()                                            \
+    const int cq = C >> 2;                                          \
+    const int i_ = blockIdx.x * blockDim.x + threadIdx.x;           \
+    if (i_ >= Wo * cq) return;                                      \
+    const int wo = i_ / cq, q = i_ - wo * cq;                       \
+    const int ho = blockIdx.y, b = blockIdx.z
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void add4(float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+__device__ __forceinline__ float4 round4(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
+
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int C,
+                                                      int Ho, int Wo, int k, int stride, int pad) {
+    SC_PIXEL_INDEX();
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const float* base = in + (size_t)b * H * W * C + q * 4;
+    for (int r = 0; r < k; ++r) {
+        const int hi = ho * stride - pad + r;
+        if (hi < 0 || hi >= H) continue;
+        for (int s = 0; s < k; ++s) {
+            const int wi = wo * stride - pad + s;
+            if (wi < 0 || wi >= W) continue;
+            const float4 v = ld4(base + ((size_t)hi * W + wi) * C);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = m;
+}
+
+// PyTorch avg_pool2d semantics: the window is first clipped to the padded extent (that size is the divisor when
+// count_include_pad), then to the real extent (that size is the divisor otherwise).
+__global__ void __launch_bounds__(256) avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int C,
+                                                      int Ho, int Wo, int k, int stride, int pad, int count_include_pad,
+                                                      int round_out) {
+    SC_PIXEL_INDEX();
+    int hs = ho * stride - pad, ws = wo * stride - pad;
+    int he = min(hs + k, H + pad), we = min(ws + k, W + pad);
+    const int pool = (he - hs) * (we - ws);
+    hs = max(hs, 0); ws = max(ws, 0);
+    he = min(he, H); we = min(we, W);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = in + (size_t)b * H * W * C + q * 4;
+    for (int hi = hs; hi < he; ++hi)
+        for (int wi = ws; wi < we; ++wi) add4(a, ld4(base + ((size_t)hi * W + wi) * C));
+    const float div = (float)(count_include_pad ? pool : (he - hs) * (we - ws));
+    a.x /= div; a.y /= div; a.z /= div; a.w /= div;
+    if (round_out) a = round4(a);
+    *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = a;
+}
+
+// ---- split attention --------------------------------------------------------------------------------------------
+// Stage 1: per (image, pixel slice) partial sums of all 2C channels: thread = one float4 channel group x one pixel
+// lane, four independent accumulators.  Stage 2 adds the slices in a fixed order and the two radix halves.
+__global__ void __launch_bounds__(256) splat_gap_partial_kernel(const float* __restrict__ in, float* __restrict__ part, int HW,
+                                                                int C2 /* = 2C */, int nsplit) {
+    __shared__ float4 red[256];
+    const int G = C2 >> 2;                    // float4 groups per pixel (<= 256)
+    const int P = 256 / G;                    // pixel lanes
+    const int g = threadIdx.x % G, pl = threadIdx.x / G;
+    const int b = blockIdx.y, sp = blockIdx.x;
+    const int per = (HW + nsplit - 1) / nsplit;
+    const int hw0 = sp * per, hw1 = min(HW, hw0 + per);
+    const float* base = in + (size_t)b * HW * C2 + g * 4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    int hw = hw0 + pl;
+    if (pl < P) {
+        for (; hw + 3 * P < hw1; hw += 4 * P) {
+            const float4 v0 = ld4(base + (size_t)hw * C2), v1 = ld4(base + (size_t)(hw + P) * C2);
+            const float4 v2 = ld4(base + (size_t)(hw + 2 * P) * C2), v3 = ld4(base + (size_t)(hw + 3 * P) * C2);
+            add4(a0, v0); add4(a1, v1); add4(a2, v2); add4(a3, v3);
+        }
+        for (; hw < hw1; hw += P) add4(a0, ld4(base + (size_t)hw * C2));
+    }
+    add4(a0, a1); add4(a2, a3); add4(a0, a2);
+    red[threadIdx.x] = a0;
+    __syncthreads();
+    if (pl == 0) {
+        float4 t = red[g];
+        for (int i = 1; i < P; ++i) add4(t, red[i * G + g]);
+        *reinterpret_cast<float4*>(part + ((size_t)b * nsplit + sp) * C2 + g * 4) = t;
+    }
+}
+
+__global__ void splat_gap_finish_kernel(const float* __restrict__ part, float* __restrict__ gap, int B, int C, int nsplit, float inv_hw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i - b * C;
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) {
+        const float* p = part + ((size_t)b * nsplit + sp) * 2 * C;
+        s += p[c] + p[C + c];                 // radix sum (split_attn.py:64-65)
+    }
+    gap[i] = s * inv_hw;
+}
+
+// Plain global average pool (B,HW,C) -> (B,C); one CTA = 32 channels x 8 pixel lanes.
+__global__ void __launch_bounds__(256) gap_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x % 32, hy = threadIdx.x / 32;
+    const int b = blockIdx.y, c = blockIdx.x * 32 + cx;
+    const float* base = in + (size_t)b * HW * C;
+    float s = 0.f;
+    if (c < C)
+        for (int hw = hy; hw < HW; hw += 8) s += __ldg(base + (size_t)hw * C + c);
+    red[hy][cx] = s;
+    __syncthreads();
+    if (hy == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][cx];
+        out[(size_t)b * C + c] = t / (float)HW;
+    }
+}
+
+// out[b,ho,wo,c] = pool3x3s2p1?( x[b,h,w,c]*a0[b,c] + x[b,h,w,C+c]*a1[b,c] ), (a0,a1) = softmax over the radix pair of
+// the fc2 output `logit` (B, 2C) (split_attn.py:14-28,74-79).  The pool divisor follows avg_pool2d with
+// count_include_pad=True (resnest.py:101): 9 wherever the padded window is full.
+__global__ void __launch_bounds__(256) splat_apply_kernel(const float* __restrict__ in, const float* __restrict__ logit,
+                                                          float* __restrict__ out, int H, int W, int C, int Ho, int Wo, int avd,
+                                                          int round_out) {
+    SC_PIXEL_INDEX();
+    const float4 l0 = ld4(logit + (size_t)b * 2 * C + q * 4), l1 = ld4(logit + (size_t)b * 2 * C + C + q * 4);
+    float4 a0, a1;
+    {
+        const float x0[4] = {l0.x, l0.y, l0.z, l0.w}, x1[4] = {l1.x, l1.y, l1.z, l1.w};
+        float r0[4], r1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float mx = fmaxf(x0[j], x1[j]);
+            const float e0 = expf(x0[j] - mx), e1 = expf(x1[j] - mx);
+            const float inv = 1.f / (e0 + e1);
+            r0[j] = e0 * inv;
+            r1[j] = e1 * inv;
+        }
+        a0 = make_float4(r0[0], r0[1], r0[2], r0[3]);
+        a1 = make_float4(r1[0], r1[1], r1[2], r1[3]);
+    }
+    const float* base = in + (size_t)b * H * W * 2 * C + q * 4;
+    auto at = [&](int hi, int wi) {
+        const float* p = base + ((size_t)hi * W + wi) * 2 * C;
+        const float4 x0 = ld4(p), x1 = ld4(p + C);
+        // the reference multiplies, then sums over the radix axis: x0*a0 + x1*a1 (two roundings + add)
+        return make_float4(x0.x * a0.x + x1.x * a1.x, x0.y * a0.y + x1.y * a1.y, x0.z * a0.z + x1.z * a1.z,
+                           x0.w * a0.w + x1.w * a1.w);
+    };
+    float4 r;
+    if (!avd) {
+        r = at(ho, wo);
+    } else {
+        int hs = ho * 2 - 1, ws = wo * 2 - 1;
+        int he = min(hs + 3, H + 1), we = min(ws + 3, W + 1);
+        const float div = (float)((he - hs) * (we - ws));
+        hs = max(hs, 0); ws = max(ws, 0);
+        he = min(he, H); we = min(we, W);
+        r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int hi = hs; hi < he; ++hi)
+            for (int wi = ws; wi < we; ++wi) add4(r, at(hi, wi));
+        r.x /= div; r.y /= div; r.z /= div; r.w /= div;
+    }
+    if (round_out) r = round4(r);
+    *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = r;
+}
+
+int pixel_grid(int B, int Ho, int Wo, int C, dim3& grid) {
+    SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "C = %d not a multiple of 4", C);
+    SC_CHECK_ARG(B <= 65535 && Ho <= 65535, SCOUTER_E_UNSUPPORTED, "batch %d / height %d exceed the grid limits", B, Ho);
+    grid = dim3(cdiv(Wo * (C / 4), 256), Ho, B);
+    return 0;
+}
+
+}  // namespace
+
+int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
+                   cudaStream_t s) {
+    dim3 grid;
+    if (int e = pixel_grid(B, Ho, Wo, C, grid)) return e;
+    maxpool_kernel<<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, k, stride, pad);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
+                   int count_include_pad, int round_out, cudaStream_t s) {
+    dim3 grid;
+    if (int e = pixel_grid(B, Ho, Wo, C, grid)) return e;
+    avgpool_kernel<<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, k, stride, pad, count_include_pad, round_out);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int splat_gap_splits(int B, int HW) {
+    // enough CTAs for ~8 per SM, but never slices shorter than 32 pixels
+    int n = std::max(1, std::min(cdiv(148 * 8, B), HW / 32));
+    return std::min(n, 64);
+}
+
+int launch_splat_gap(const float* in, float* part, float* gap, int B, int HW, int C, cudaStream_t s) {
+    SC_CHECK_ARG(C % 2 == 0 && (2 * C / 4) <= 256 && 256 % (2 * C / 4) == 0, SCOUTER_E_UNSUPPORTED,
+                 "splat gap: C = %d (2C/4 must divide 256)", C);
+    SC_CHECK_ARG(B <= 65535, SCOUTER_E_UNSUPPORTED, "splat gap: batch %d", B);
+    const int nsplit = splat_gap_splits(B, HW);
+    splat_gap_partial_kernel<<<dim3(nsplit, B), 256, 0, s>>>(in, part, HW, 2 * C, nsplit);
+    SC_LAUNCH_CHECK();
+    splat_gap_finish_kernel<<<cdiv(B * C, 256), 256, 0, s>>>(part, gap, B, C, nsplit, 1.0f / (float)HW);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s) {
+    dim3 grid(cdiv(C, 32), B);
+    gap_kernel<<<grid, 256, 0, s>>>(in, out, HW, C);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_splat_apply(const float* in, const float* logit, float* out, int B, int H, int W, int C, int Ho, int Wo, int avd,
+                       int round_out, cudaStream_t s) {
+    dim3 grid;
+    if (int e = pixel_grid(B, Ho, Wo, C, grid)) return e;
+    splat_apply_kernel<<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, avd, round_out);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace scouter

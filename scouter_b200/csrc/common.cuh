@@ -95,10 +95,9 @@ int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int 
                    int pad, cudaStream_t s);
 int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride,
                    int pad, int count_include_pad, int round_out, cudaStream_t s);
-int launch_splat_gap(const float* in, float* gap, int B, int HW, int C /*per radix*/, cudaStream_t s);
-int launch_splat_fc(const float* gap, const float* w1, const float* b1, const float* w2, const float* b2,
-                    float* attn, int B, int C, int mid, cudaStream_t s);
-int launch_splat_apply(const float* in, const float* attn, float* out, int B, int H, int W, int C, int Ho, int Wo,
+int splat_gap_splits(int B, int HW);  // pixel slices of the split-attention GAP (workspace = B * splits * 2C floats)
+int launch_splat_gap(const float* in, float* part, float* gap, int B, int HW, int C /*per radix*/, cudaStream_t s);
+int launch_splat_apply(const float* in, const float* logit, float* out, int B, int H, int W, int C, int Ho, int Wo,
                        int avd, int round_out, cudaStream_t s);
 int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s);
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int HW, int C, cudaStream_t s);

@@ -277,221 +277,6 @@ int launch_stem_tiled(const StemArgs& a, cudaStream_t s) {
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Pools (NHWC, one thread = one output pixel x 4 channels).
-// ------------------------------------------------------------------------------------------------
-__global__ void maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
-                               int Ho, int Wo, int k, int stride, int pad) {
-    const int cq = C / 4;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)B * Ho * Wo * cq;
-    if (idx >= total) return;
-    int q = (int)(idx % cq);
-    long long pix = idx / cq;
-    int wo = (int)(pix % Wo);
-    long long t2 = pix / Wo;
-    int ho = (int)(t2 % Ho);
-    int b = (int)(t2 / Ho);
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    for (int r = 0; r < k; ++r) {
-        int hi = ho * stride - pad + r;
-        if (hi < 0 || hi >= H) continue;
-        for (int s = 0; s < k; ++s) {
-            int wi = wo * stride - pad + s;
-            if (wi < 0 || wi >= W) continue;
-            float4 v = __ldg(reinterpret_cast<const float4*>(in + (((long long)b * H + hi) * W + wi) * C + q * 4));
-            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-        }
-    }
-    *reinterpret_cast<float4*>(out + pix * C + q * 4) = m;
-}
-
-// PyTorch avg_pool2d semantics: the window is first clipped to the padded extent (that size is the
-// divisor when count_include_pad), then to the real extent (that size is the divisor otherwise).
-__global__ void avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
-                               int Ho, int Wo, int k, int stride, int pad, int count_include_pad, int round_out) {
-    const int cq = C / 4;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)B * Ho * Wo * cq;
-    if (idx >= total) return;
-    int q = (int)(idx % cq);
-    long long pix = idx / cq;
-    int wo = (int)(pix % Wo);
-    long long t2 = pix / Wo;
-    int ho = (int)(t2 % Ho);
-    int b = (int)(t2 / Ho);
-    int hs = ho * stride - pad, ws = wo * stride - pad;
-    int he = min(hs + k, H + pad), we = min(ws + k, W + pad);
-    int pool = (he - hs) * (we - ws);
-    hs = max(hs, 0); ws = max(ws, 0);
-    he = min(he, H); we = min(we, W);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int hi = hs; hi < he; ++hi)
-        for (int wi = ws; wi < we; ++wi) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(in + (((long long)b * H + hi) * W + wi) * C + q * 4));
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        }
-    float div = (float)(count_include_pad ? pool : (he - hs) * (we - ws));
-    a.x /= div; a.y /= div; a.z /= div; a.w /= div;
-    if (round_out) { a.x = to_tf32(a.x); a.y = to_tf32(a.y); a.z = to_tf32(a.z); a.w = to_tf32(a.w); }
-    *reinterpret_cast<float4*>(out + pix * C + q * 4) = a;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Split attention (radix 2, cardinality 1).
-// ------------------------------------------------------------------------------------------------
-// gap[b][c] = mean_hw (x[b,hw,c] + x[b,hw,C+c]).  CTA = 32 channels x 8 hw-lanes, fixed-order reduction.
-__global__ void __launch_bounds__(256) splat_gap_kernel(const float* __restrict__ in, float* __restrict__ gap,
-                                                        int HW, int C) {
-    __shared__ float red[8][33];
-    const int cx = threadIdx.x % 32, hy = threadIdx.x / 32;
-    const int b = blockIdx.y, c = blockIdx.x * 32 + cx;
-    const float* base = in + (long long)b * HW * 2 * C;
-    float s = 0.f;
-    if (c < C)
-        for (int hw = hy; hw < HW; hw += 8) s += __ldg(base + (long long)hw * 2 * C + c) + __ldg(base + (long long)hw * 2 * C + C + c);
-    red[hy][cx] = s;
-    __syncthreads();
-    if (hy == 0 && c < C) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][cx];
-        gap[(long long)b * C + c] = t / (float)HW;
-    }
-}
-
-// Plain global average pool (B,HW,C) -> (B,C) with the same CTA shape.
-__global__ void __launch_bounds__(256) gap_kernel(const float* __restrict__ in, float* __restrict__ out, int HW, int C) {
-    __shared__ float red[8][33];
-    const int cx = threadIdx.x % 32, hy = threadIdx.x / 32;
-    const int b = blockIdx.y, c = blockIdx.x * 32 + cx;
-    const float* base = in + (long long)b * HW * C;
-    float s = 0.f;
-    if (c < C)
-        for (int hw = hy; hw < HW; hw += 8) s += __ldg(base + (long long)hw * C + c);
-    red[hy][cx] = s;
-    __syncthreads();
-    if (hy == 0 && c < C) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][cx];
-        out[(long long)b * C + c] = t / (float)HW;
-    }
-}
-
-// h = relu(W1 gap + b1) (bn1 folded), a = W2 h + b2, softmax over the radix pair.  A CTA serves FC_IMG images at
-// once (every weight it reads is used FC_IMG times) and one slice of the 2C outputs; fc1 is recomputed per slice.
-constexpr int FC_IMG = 8;
-__global__ void __launch_bounds__(256) splat_fc_kernel(const float* __restrict__ gap, const float* __restrict__ w1,
-                                                       const float* __restrict__ b1, const float* __restrict__ w2,
-                                                       const float* __restrict__ b2, float* __restrict__ attn, int B, int C,
-                                                       int mid, int cper) {
-    extern __shared__ float sm[];
-    float* sg = sm;                 // [FC_IMG][C]
-    float* sh = sm + FC_IMG * C;    // [FC_IMG][mid]
-    const int b0 = blockIdx.x * FC_IMG;
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
-    for (int i = threadIdx.x; i < FC_IMG * C; i += blockDim.x) {
-        int im = i / C;
-        sg[i] = (b0 + im < B) ? gap[(long long)(b0 + im) * C + (i - im * C)] : 0.f;
-    }
-    __syncthreads();
-    for (int a = warp; a < mid; a += nw) {
-        float s[FC_IMG];
-#pragma unroll
-        for (int i = 0; i < FC_IMG; ++i) s[i] = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float w = __ldg(w1 + (long long)a * C + c);
-#pragma unroll
-            for (int i = 0; i < FC_IMG; ++i) s[i] = fmaf(w, sg[i * C + c], s[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < FC_IMG; ++i) s[i] = warp_sum(s[i]);
-        if (lane == 0) {
-            const float bb = __ldg(b1 + a);
-#pragma unroll
-            for (int i = 0; i < FC_IMG; ++i) sh[i * mid + a] = fmaxf(s[i] + bb, 0.f);
-        }
-    }
-    __syncthreads();
-    const int c_end = min(C, (int)(blockIdx.y + 1) * cper);
-    for (int c = blockIdx.y * cper + warp; c < c_end; c += nw) {
-        float s0[FC_IMG], s1[FC_IMG];
-#pragma unroll
-        for (int i = 0; i < FC_IMG; ++i) s0[i] = s1[i] = 0.f;
-        for (int a = lane; a < mid; a += 32) {
-            const float wa = __ldg(w2 + (long long)c * mid + a), wb = __ldg(w2 + (long long)(C + c) * mid + a);
-#pragma unroll
-            for (int i = 0; i < FC_IMG; ++i) {
-                const float h = sh[i * mid + a];
-                s0[i] = fmaf(wa, h, s0[i]);
-                s1[i] = fmaf(wb, h, s1[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < FC_IMG; ++i) { s0[i] = warp_sum(s0[i]); s1[i] = warp_sum(s1[i]); }
-        if (lane == 0) {
-            const float ba = __ldg(b2 + c), bb = __ldg(b2 + C + c);
-#pragma unroll
-            for (int i = 0; i < FC_IMG; ++i) {
-                if (b0 + i >= B) break;
-                float x0 = s0[i] + ba, x1 = s1[i] + bb;
-                float mx = fmaxf(x0, x1);
-                float e0 = expf(x0 - mx), e1 = expf(x1 - mx);
-                float inv = 1.f / (e0 + e1);
-                attn[(long long)(b0 + i) * 2 * C + c] = e0 * inv;
-                attn[(long long)(b0 + i) * 2 * C + C + c] = e1 * inv;
-            }
-        }
-    }
-}
-
-// out[b,ho,wo,c] = pool3x3s2p1?( x[b,h,w,c]*a0[b,c] + x[b,h,w,C+c]*a1[b,c] ); the pool divisor is 9 wherever
-// the padded window is full (count_include_pad=True, resnest.py:101) and follows avg_pool2d otherwise.
-__global__ void splat_apply_kernel(const float* __restrict__ in, const float* __restrict__ attn,
-                                   float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo, int avd,
-                                   int round_out) {
-    const int cq = C / 4;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)B * Ho * Wo * cq;
-    if (idx >= total) return;
-    int q = (int)(idx % cq);
-    long long pix = idx / cq;
-    int wo = (int)(pix % Wo);
-    long long t2 = pix / Wo;
-    int ho = (int)(t2 % Ho);
-    int b = (int)(t2 / Ho);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(attn + (long long)b * 2 * C + q * 4));
-    const float4 a1 = __ldg(reinterpret_cast<const float4*>(attn + (long long)b * 2 * C + C + q * 4));
-    auto at = [&](int hi, int wi) {
-        const float* p = in + (((long long)b * H + hi) * W + wi) * 2 * C + q * 4;
-        float4 x0 = __ldg(reinterpret_cast<const float4*>(p));
-        float4 x1 = __ldg(reinterpret_cast<const float4*>(p + C));
-        // the reference multiplies then sums over the radix axis: x0*a0 + x1*a1 (two roundings + add)
-        return make_float4(x0.x * a0.x + x1.x * a1.x, x0.y * a0.y + x1.y * a1.y, x0.z * a0.z + x1.z * a1.z,
-                           x0.w * a0.w + x1.w * a1.w);
-    };
-    float4 r;
-    if (!avd) {
-        r = at(ho, wo);
-    } else {
-        int hs = ho * 2 - 1, ws = wo * 2 - 1;
-        int he = min(hs + 3, H + 1), we = min(ws + 3, W + 1);
-        float div = (float)((he - hs) * (we - ws));
-        hs = max(hs, 0); ws = max(ws, 0);
-        he = min(he, H); we = min(we, W);
-        r = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int hi = hs; hi < he; ++hi)
-            for (int wi = ws; wi < we; ++wi) {
-                float4 v = at(hi, wi);
-                r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
-            }
-        r.x /= div; r.y /= div; r.z /= div; r.w /= div;
-    }
-    if (round_out) { r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w); }
-    *reinterpret_cast<float4*>(out + pix * C + q * 4) = r;
-}
-
 // Tiled transposes between (B, HW, C) and (B, C, HW).
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Ccols) {
     // in: (B, R, Ccols) -> out: (B, Ccols, R)
@@ -541,61 +326,6 @@ int launch_stem_conv(const StemArgs& a, cudaStream_t s) {
     SC_CHECK_ARG(smem <= 48 * 1024, SCOUTER_E_UNSUPPORTED, "stem conv: filter bank of %zu bytes exceeds 48 KB", smem);
     long long total = (long long)a.B * a.Ho * a.Wo * (a.Cout / 4);
     stem_conv_kernel<<<(unsigned)((total + 255) / 256), 256, smem, s>>>(a);
-    SC_LAUNCH_CHECK();
-    return 0;
-}
-
-int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
-                   cudaStream_t s) {
-    SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "maxpool: C = %d not a multiple of 4", C);
-    long long total = (long long)B * Ho * Wo * (C / 4);
-    maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W, C, Ho, Wo, k, stride, pad);
-    SC_LAUNCH_CHECK();
-    return 0;
-}
-
-int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
-                   int count_include_pad, int round_out, cudaStream_t s) {
-    SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "avgpool: C = %d not a multiple of 4", C);
-    long long total = (long long)B * Ho * Wo * (C / 4);
-    avgpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W, C, Ho, Wo, k, stride, pad,
-                                                                  count_include_pad, round_out);
-    SC_LAUNCH_CHECK();
-    return 0;
-}
-
-int launch_splat_gap(const float* in, float* gap, int B, int HW, int C, cudaStream_t s) {
-    dim3 grid(cdiv(C, 32), B);
-    splat_gap_kernel<<<grid, 256, 0, s>>>(in, gap, HW, C);
-    SC_LAUNCH_CHECK();
-    return 0;
-}
-
-int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s) {
-    dim3 grid(cdiv(C, 32), B);
-    gap_kernel<<<grid, 256, 0, s>>>(in, out, HW, C);
-    SC_LAUNCH_CHECK();
-    return 0;
-}
-
-int launch_splat_fc(const float* gap, const float* w1, const float* b1, const float* w2, const float* b2, float* attn,
-                    int B, int C, int mid, cudaStream_t s) {
-    const int gx = cdiv(B, FC_IMG);
-    int gy = std::max(1, std::min(cdiv(296, gx), cdiv(C, 8)));  // ~2 CTAs per SM worth of slices
-    const int cper = cdiv(C, gy);
-    gy = cdiv(C, cper);
-    size_t smem = (size_t)FC_IMG * (C + mid) * sizeof(float);
-    SC_CHECK_ARG(smem <= 48 * 1024, SCOUTER_E_UNSUPPORTED, "splat fc: C=%d mid=%d needs %zu bytes of shared memory", C, mid, smem);
-    splat_fc_kernel<<<dim3(gx, gy), 256, smem, s>>>(gap, w1, b1, w2, b2, attn, B, C, mid, cper);
-    SC_LAUNCH_CHECK();
-    return 0;
-}
-
-int launch_splat_apply(const float* in, const float* attn, float* out, int B, int H, int W, int C, int Ho, int Wo,
-                       int avd, int round_out, cudaStream_t s) {
-    SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "splat apply: C = %d not a multiple of 4", C);
-    long long total = (long long)B * Ho * Wo * (C / 4);
-    splat_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, attn, out, B, H, W, C, Ho, Wo, avd, round_out);
     SC_LAUNCH_CHECK();
     return 0;
 }

@@ -107,12 +107,9 @@ def _lower_resnest_block(p: Program, blk, x: int) -> int:
     sa = blk.conv2
     c = sa.conv.out_channels // 2
     t2 = p.conv(t, sa.conv, sa.bn0, relu=True)                                   # (B,H,W,2C)
-    gap = p.emit(L.OP_SPLAT_GAP, t2, p.buf(), cout=c)
-    w1, b1 = fold_conv_bn(sa.fc1, sa.bn1)
-    w2, b2 = fold_conv_bn(sa.fc2, None)
-    mid = sa.fc1.out_channels
-    av = p.emit(L.OP_SPLAT_FC, gap, p.buf(), cin=c, cout=2 * c, mid=mid,
-                w=w1.reshape(mid, c).contiguous(), b=b1, w2=w2.reshape(2 * c, mid).contiguous(), b2=b2)
+    gap = p.emit(L.OP_SPLAT_GAP, t2, p.buf(), cout=c)                            # (B,1,1,C)
+    hid = p.conv(gap, sa.fc1, sa.bn1, relu=True)                                 # fc1 + bn1 + ReLU  (B,1,1,mid)
+    av = p.conv(hid, sa.fc2, None, relu=False)                                   # fc2 logits        (B,1,1,2C)
     t3 = p.emit(L.OP_SPLAT_APPLY, t2, p.buf(), src2=av, cout=c, flags=L.F_AVD_POOL if blk.avd_last is not None else 0)
     res = x
     if blk.downsample is not None:
