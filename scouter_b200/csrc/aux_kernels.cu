@@ -12,54 +12,80 @@
 namespace scouter {
 namespace {
 
-#define SC_PIXEL_INDEX()                                            \
+// Each thread owns ROWS consecutive output rows (same column / channel quad): the loads of all rows are issued before
+// any is consumed, which is what keeps enough bytes in flight.
+#define SC_PIXEL_INDEX(ROWS)                                        \
     const int cq = C >> 2;                                          \
     const int i_ = blockIdx.x * blockDim.x + threadIdx.x;           \
     if (i_ >= Wo * cq) return;                                      \
     const int wo = i_ / cq, q = i_ - wo * cq;                       \
-    const int ho = blockIdx.y, b = blockIdx.z
+    const int ho0 = blockIdx.y * (ROWS), b = blockIdx.z
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void add4(float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
 __device__ __forceinline__ float4 round4(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
 
+template <int ROWS>
 __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int C,
                                                       int Ho, int Wo, int k, int stride, int pad) {
-    SC_PIXEL_INDEX();
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    SC_PIXEL_INDEX(ROWS);
     const float* base = in + (size_t)b * H * W * C + q * 4;
-    for (int r = 0; r < k; ++r) {
-        const int hi = ho * stride - pad + r;
-        if (hi < 0 || hi >= H) continue;
+    float4 m[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) m[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < k; ++r)
         for (int s = 0; s < k; ++s) {
             const int wi = wo * stride - pad + s;
             if (wi < 0 || wi >= W) continue;
-            const float4 v = ld4(base + ((size_t)hi * W + wi) * C);
-            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                const int hi = (ho0 + j) * stride - pad + r;
+                if (hi < 0 || hi >= H) continue;
+                const float4 v = ld4(base + ((size_t)hi * W + wi) * C);
+                m[j].x = fmaxf(m[j].x, v.x); m[j].y = fmaxf(m[j].y, v.y); m[j].z = fmaxf(m[j].z, v.z); m[j].w = fmaxf(m[j].w, v.w);
+            }
         }
-    }
-    *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = m;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j)
+        if (ho0 + j < Ho) *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho0 + j) * Wo + wo) * C + q * 4) = m[j];
 }
 
 // PyTorch avg_pool2d semantics: the window is first clipped to the padded extent (that size is the divisor when
 // count_include_pad), then to the real extent (that size is the divisor otherwise).
+template <int ROWS>
 __global__ void __launch_bounds__(256) avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int C,
                                                       int Ho, int Wo, int k, int stride, int pad, int count_include_pad,
                                                       int round_out) {
-    SC_PIXEL_INDEX();
-    int hs = ho * stride - pad, ws = wo * stride - pad;
-    int he = min(hs + k, H + pad), we = min(ws + k, W + pad);
-    const int pool = (he - hs) * (we - ws);
-    hs = max(hs, 0); ws = max(ws, 0);
-    he = min(he, H); we = min(we, W);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    SC_PIXEL_INDEX(ROWS);
     const float* base = in + (size_t)b * H * W * C + q * 4;
-    for (int hi = hs; hi < he; ++hi)
-        for (int wi = ws; wi < we; ++wi) add4(a, ld4(base + ((size_t)hi * W + wi) * C));
-    const float div = (float)(count_include_pad ? pool : (he - hs) * (we - ws));
-    a.x /= div; a.y /= div; a.z /= div; a.w /= div;
-    if (round_out) a = round4(a);
-    *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = a;
+    int ws = wo * stride - pad;
+    const int we_p = min(ws + k, W + pad);
+    const int wspan_p = we_p - ws;
+    ws = max(ws, 0);
+    const int we = min(we_p, W);
+    float4 a[ROWS];
+    float div[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int hs = (ho0 + j) * stride - pad;
+        int he = min(hs + k, H + pad);
+        const int pool = (he - hs) * wspan_p;
+        hs = max(hs, 0);
+        he = min(he, H);
+        div[j] = (float)(count_include_pad ? pool : (he - hs) * (we - ws));
+        if (ho0 + j < Ho)
+            for (int hi = hs; hi < he; ++hi)
+                for (int wi = ws; wi < we; ++wi) add4(a[j], ld4(base + ((size_t)hi * W + wi) * C));
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        if (ho0 + j >= Ho) continue;
+        float4 v = a[j];
+        v.x /= div[j]; v.y /= div[j]; v.z /= div[j]; v.w /= div[j];
+        if (round_out) v = round4(v);
+        *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho0 + j) * Wo + wo) * C + q * 4) = v;
+    }
 }
 
 // ---- split attention --------------------------------------------------------------------------------------------
@@ -129,19 +155,31 @@ __global__ void __launch_bounds__(256) gap_kernel(const float* __restrict__ in, 
 // out[b,ho,wo,c] = pool3x3s2p1?( x[b,h,w,c]*a0[b,c] + x[b,h,w,C+c]*a1[b,c] ), (a0,a1) = softmax over the radix pair of
 // the fc2 output `logit` (B, 2C) (split_attn.py:14-28,74-79).  The pool divisor follows avg_pool2d with
 // count_include_pad=True (resnest.py:101): 9 wherever the padded window is full.
+template <int ROWS>
 __global__ void __launch_bounds__(256) splat_apply_kernel(const float* __restrict__ in, const float* __restrict__ logit,
                                                           float* __restrict__ out, int H, int W, int C, int Ho, int Wo, int avd,
                                                           int round_out) {
-    SC_PIXEL_INDEX();
+    SC_PIXEL_INDEX(ROWS);
     const float4 l0 = ld4(logit + (size_t)b * 2 * C + q * 4), l1 = ld4(logit + (size_t)b * 2 * C + C + q * 4);
+    const float* base = in + (size_t)b * H * W * 2 * C + q * 4;
+    float4 x0[ROWS], x1[ROWS];
+    if (!avd) {   // issue every row's loads before the softmax arithmetic
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            const int ho = min(ho0 + j, Ho - 1);
+            const float* p = base + ((size_t)ho * W + wo) * 2 * C;
+            x0[j] = ld4(p);
+            x1[j] = ld4(p + C);
+        }
+    }
     float4 a0, a1;
     {
-        const float x0[4] = {l0.x, l0.y, l0.z, l0.w}, x1[4] = {l1.x, l1.y, l1.z, l1.w};
+        const float y0[4] = {l0.x, l0.y, l0.z, l0.w}, y1[4] = {l1.x, l1.y, l1.z, l1.w};
         float r0[4], r1[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float mx = fmaxf(x0[j], x1[j]);
-            const float e0 = expf(x0[j] - mx), e1 = expf(x1[j] - mx);
+            const float mx = fmaxf(y0[j], y1[j]);
+            const float e0 = expf(y0[j] - mx), e1 = expf(y1[j] - mx);
             const float inv = 1.f / (e0 + e1);
             r0[j] = e0 * inv;
             r1[j] = e1 * inv;
@@ -149,36 +187,41 @@ __global__ void __launch_bounds__(256) splat_apply_kernel(const float* __restric
         a0 = make_float4(r0[0], r0[1], r0[2], r0[3]);
         a1 = make_float4(r1[0], r1[1], r1[2], r1[3]);
     }
-    const float* base = in + (size_t)b * H * W * 2 * C + q * 4;
-    auto at = [&](int hi, int wi) {
-        const float* p = base + ((size_t)hi * W + wi) * 2 * C;
-        const float4 x0 = ld4(p), x1 = ld4(p + C);
-        // the reference multiplies, then sums over the radix axis: x0*a0 + x1*a1 (two roundings + add)
-        return make_float4(x0.x * a0.x + x1.x * a1.x, x0.y * a0.y + x1.y * a1.y, x0.z * a0.z + x1.z * a1.z,
-                           x0.w * a0.w + x1.w * a1.w);
+    // the reference multiplies, then sums over the radix axis: x0*a0 + x1*a1 (two roundings + add)
+    auto mix = [&](const float4& u0, const float4& u1) {
+        return make_float4(u0.x * a0.x + u1.x * a1.x, u0.y * a0.y + u1.y * a1.y, u0.z * a0.z + u1.z * a1.z,
+                           u0.w * a0.w + u1.w * a1.w);
     };
-    float4 r;
-    if (!avd) {
-        r = at(ho, wo);
-    } else {
-        int hs = ho * 2 - 1, ws = wo * 2 - 1;
-        int he = min(hs + 3, H + 1), we = min(ws + 3, W + 1);
-        const float div = (float)((he - hs) * (we - ws));
-        hs = max(hs, 0); ws = max(ws, 0);
-        he = min(he, H); we = min(we, W);
-        r = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int hi = hs; hi < he; ++hi)
-            for (int wi = ws; wi < we; ++wi) add4(r, at(hi, wi));
-        r.x /= div; r.y /= div; r.z /= div; r.w /= div;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        const int ho = ho0 + j;
+        if (ho >= Ho) continue;
+        float4 r;
+        if (!avd) {
+            r = mix(x0[j], x1[j]);
+        } else {
+            int hs = ho * 2 - 1, ws = wo * 2 - 1;
+            int he = min(hs + 3, H + 1), we = min(ws + 3, W + 1);
+            const float div = (float)((he - hs) * (we - ws));
+            hs = max(hs, 0); ws = max(ws, 0);
+            he = min(he, H); we = min(we, W);
+            r = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int hi = hs; hi < he; ++hi)
+                for (int wi = ws; wi < we; ++wi) {
+                    const float* p = base + ((size_t)hi * W + wi) * 2 * C;
+                    add4(r, mix(ld4(p), ld4(p + C)));
+                }
+            r.x /= div; r.y /= div; r.z /= div; r.w /= div;
+        }
+        if (round_out) r = round4(r);
+        *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = r;
     }
-    if (round_out) r = round4(r);
-    *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = r;
 }
 
-int pixel_grid(int B, int Ho, int Wo, int C, dim3& grid) {
+int pixel_grid(int B, int Ho, int Wo, int C, int rows, dim3& grid) {
     SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "C = %d not a multiple of 4", C);
     SC_CHECK_ARG(B <= 65535 && Ho <= 65535, SCOUTER_E_UNSUPPORTED, "batch %d / height %d exceed the grid limits", B, Ho);
-    grid = dim3(cdiv(Wo * (C / 4), 256), Ho, B);
+    grid = dim3(cdiv(Wo * (C / 4), 256), cdiv(Ho, rows), B);
     return 0;
 }
 
@@ -187,8 +230,8 @@ int pixel_grid(int B, int Ho, int Wo, int C, dim3& grid) {
 int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
                    cudaStream_t s) {
     dim3 grid;
-    if (int e = pixel_grid(B, Ho, Wo, C, grid)) return e;
-    maxpool_kernel<<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, k, stride, pad);
+    if (int e = pixel_grid(B, Ho, Wo, C, 2, grid)) return e;
+    maxpool_kernel<2><<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, k, stride, pad);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -196,8 +239,8 @@ int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int 
 int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
                    int count_include_pad, int round_out, cudaStream_t s) {
     dim3 grid;
-    if (int e = pixel_grid(B, Ho, Wo, C, grid)) return e;
-    avgpool_kernel<<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, k, stride, pad, count_include_pad, round_out);
+    if (int e = pixel_grid(B, Ho, Wo, C, 4, grid)) return e;
+    avgpool_kernel<4><<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, k, stride, pad, count_include_pad, round_out);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -230,8 +273,13 @@ int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s
 int launch_splat_apply(const float* in, const float* logit, float* out, int B, int H, int W, int C, int Ho, int Wo, int avd,
                        int round_out, cudaStream_t s) {
     dim3 grid;
-    if (int e = pixel_grid(B, Ho, Wo, C, grid)) return e;
-    splat_apply_kernel<<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, avd, round_out);
+    if (avd) {
+        if (int e = pixel_grid(B, Ho, Wo, C, 2, grid)) return e;
+        splat_apply_kernel<2><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, avd, round_out);
+    } else {
+        if (int e = pixel_grid(B, Ho, Wo, C, 4, grid)) return e;
+        splat_apply_kernel<4><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, avd, round_out);
+    }
     SC_LAUNCH_CHECK();
     return 0;
 }
