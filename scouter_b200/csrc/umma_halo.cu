@@ -284,15 +284,23 @@ EncodeTiledFn halo_encode_fn() {
     return fn;
 }
 
-// (Wb, Hb) with Hb*(Wb+2) <= 128 virtual rows, maximising useful rows per 128-row MMA.
+// (Wb, Hb) with Hb*(Wb+2) <= 128 virtual rows: maximise the useful rows per 128-row MMA, and among (near-)equal
+// choices take the tile whose halo patch is smallest relative to its output (square-ish tiles: fewer bytes per
+// output and a small patch buffer).
 double choose_halo_tile(int H, int W, int& Wb, int& Hb) {
-    double best = -1.0;
+    double best = -1.0, best_ratio = 1e30;
     Wb = Hb = 1;
     for (int wb = 1; wb <= W && wb + 2 <= 128; ++wb)
         for (int hb = 1; hb <= H && hb * (wb + 2) <= 128; ++hb) {
-            long long tiles = (long long)cdiv(W, wb) * cdiv(H, hb);
-            double util = (double)H * W / (tiles * 128.0) + 1e-6 * wb;
-            if (util > best) { best = util; Wb = wb; Hb = hb; }
+            const long long tiles = (long long)cdiv(W, wb) * cdiv(H, hb);
+            const double util = (double)H * W / (tiles * 128.0);
+            const double ratio = (double)(hb + 2) * (wb + 2) / ((double)hb * wb);
+            if (util > best + 1e-3 || (util > best - 1e-3 && ratio < best_ratio)) {
+                best = std::max(best, util);
+                best_ratio = ratio;
+                Wb = wb;
+                Hb = hb;
+            }
         }
     return best;
 }
