@@ -21,7 +21,6 @@
 //
 // Reference ops replaced: the nn.Conv2d+BatchNorm2d(+ReLU)(+residual) chains of timm/models/resnest.py:111-143,
 // split_attn.py:43-45,56-60 and resnet.py:403-408 (eval mode, BN folded).
-#include "epilogue.cuh"
 #include "ptx.cuh"
 #include "umma.cuh"
 
@@ -53,15 +52,14 @@ struct Cfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
     static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | B | A_r | B_r]
-    static constexpr int STAGES = (204 * 1024 / STAGE) > 8 ? 8 : (204 * 1024 / STAGE);
+    static constexpr int STAGES = (200 * 1024 / STAGE) > 8 ? 8 : (200 * 1024 / STAGE);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
     // fp32 sums of the chunked accumulation fit in registers (64 per thread).
     static constexpr int EPI_GROUPS = (SPLIT && BN == 128) ? 2 : 1;
     static constexpr int NC = BN / EPI_GROUPS;               // columns per epilogue thread
     static constexpr int THREADS = SPLIT ? 512 : 256;
-    static constexpr int SCRATCH = 8 * EPI_SCRATCH_FLOATS * 4;  // per-epilogue-warp transpose scratch
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 512 /*barriers*/ + SCRATCH;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 template <int BN, bool SPLIT>
@@ -76,7 +74,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* cempty = cfull + 2;          // [2] accumulator chunk drained by every epilogue thread
     uint64_t* split_done = cempty + 2;     // [STAGES], SPLIT only: remainders written, stage ready for the issuer
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(split_done + C::STAGES);
-    float* scratch_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + 512);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (warp == 0 && elect_one()) {
@@ -191,8 +188,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int grp = warp >= 12 ? 1 : 0;
         const int row = q * 32 + lane;
         const int col0 = grp * C::NC;
-        float* scratch = scratch_all + (grp * 4 + q) * EPI_SCRATCH_FLOATS;
-        const EpiOut eo{p.bias, p.res, p.out, p.Cout, p.relu, p.round_out};
         uint32_t cc = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int nt = t % p.n_tiles;
@@ -214,7 +209,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 valid = orow < p.M;
             }
             const int ch0 = g * p.cout_g + nt * BN + col0;
-            const int my_row = valid ? (int)orow : -1;   // M < 2^31 (checked on the host)
+            float* op = p.out + orow * p.Cout + ch0;
+            const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
+
+            auto finish = [&](const uint32_t (&r)[32], int c) {   // bias / residual / ReLU / store of 32 columns
+                if (!valid) return;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    if (p.bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 32 + 4 * j));
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    }
+                    if (rp) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + c * 32 + 4 * j));
+                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                    }
+                    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (p.round_out) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                    *reinterpret_cast<float4*>(op + c * 32 + 4 * j) = v;
+                }
+            };
 
             if constexpr (SPLIT) {
                 float acc[C::NC];
@@ -236,7 +252,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_arrive(&cempty[buf]);
                 }
 #pragma unroll
-                for (int c = 0; c < C::NC / 16; ++c) epi_emit16(eo, scratch, lane, my_row, ch0 + c * 16, &acc[c * 16]);
+                for (int c = 0; c < C::NC / 32; ++c) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[c * 32 + j]);
+                    finish(r, c);
+                }
             } else {
                 const int buf = cc & 1;
                 mbar_wait(&cfull[buf], (cc >> 1) & 1);
@@ -246,16 +267,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
                     tmem_ld_wait();
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (c == BN / 32 - 1) {   // accumulator fully read: release it before the global stores
-                        tc_fence_before();
-                        mbar_arrive(&cempty[buf]);
-                    }
-                    epi_emit16(eo, scratch, lane, my_row, ch0 + c * 32, &v[0]);
-                    epi_emit16(eo, scratch, lane, my_row, ch0 + c * 32 + 16, &v[16]);
+                    finish(r, c);
                 }
+                tc_fence_before();
+                mbar_arrive(&cempty[buf]);
                 ++cc;
             }
         }

@@ -20,7 +20,6 @@
 //
 // Replaces: the grouped 3x3 conv + bn0 + ReLU of timm/models/layers/split_attn.py:43-45,55-60 and the deep-stem
 // 3x3 convs of timm/models/resnet.py:404-408 (eval mode, BN folded).
-#include "epilogue.cuh"
 #include "ptx.cuh"
 #include "umma.cuh"
 
@@ -72,7 +71,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* cfull = bempty + C::MAX_ST;    // [2]
     uint64_t* cempty = cfull + 2;            // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cempty + 2);
-    float* scratch_all = reinterpret_cast<float*>(bt0 + p.bst * C::B_STAGE + 512);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (warp == 0 && elect_one()) {
@@ -206,8 +204,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int row = q * 32 + lane;
         const int col0 = grp * C::NC;
         const int hb = row / p.PW, wb = row - hb * p.PW;
-        float* scratch = scratch_all + (grp * 4 + q) * EPI_SCRATCH_FLOATS;
-        const EpiOut eo{p.bias, p.res, p.out, p.Cout, p.relu, 0};
         uint32_t cc = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             int nt, g, w0, h0, b;
@@ -234,9 +230,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(&cempty[buf]);
             }
-            const int my_row = valid ? (int)orow : -1;
+            if (valid) {
+                float* op = p.out + orow * p.Cout + ch0;
+                const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
 #pragma unroll
-            for (int c = 0; c < C::NC / 16; ++c) epi_emit16(eo, scratch, lane, my_row, ch0 + c * 16, &acc[c * 16]);
+                for (int j = 0; j < C::NC / 4; ++j) {
+                    float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                    if (p.bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + 4 * j));
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    }
+                    if (rp) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
+                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                    }
+                    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    *reinterpret_cast<float4*>(op + 4 * j) = v;
+                }
+            }
         }
     } else if (warp >= 8 && warp < 12) {
         // ===== splitters: remainder patch = patch - trunc19(patch), once per patch =====
@@ -358,8 +369,8 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();
     u.chunk = chunk_kb;
     const int b_stage = 2 * BN * 128;
-    const int scratch = 8 * EPI_SCRATCH_FLOATS * 4;
-    const int budget = 224 * 1024 - scratch - 1536;
+    const int scratch = 0;
+    const int budget = 224 * 1024 - 1536;
     // narrow tiles (small BN) do little MMA work per patch and are latency/bandwidth bound: deeper patch prefetch
     const int want_pst = BN == 128 ? 2 : (BN == 64 ? 3 : 4);
     u.pst = 2;
