@@ -153,10 +153,10 @@ def main():
     from scouter_b200 import _lib as L
     from scouter_b200.synth import fill_state_dict
 
+    from scouter_b200 import dist as sdist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    sdist.init_from_env("nccl", dev)
     L.check(L.lib().scouter_device_check(local))
 
     m = sb.SlotModel(make_args(**ARGS))

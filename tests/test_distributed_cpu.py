@@ -1,0 +1,70 @@
+"""CPU, world_size 2, gloo: the data-parallel plumbing of the forward path (no collective touches the data path)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from scouter_b200 import dist as sd
+    r, w, l = sd.init_from_env(backend="gloo")
+    assert (r, w, l) == (rank, world, rank)
+    # 1. shards are disjoint, ordered and cover the batch (uneven split included)
+    b, e = sd.shard_range(257, r, w)
+    sizes = [None] * w
+    dist.all_gather_object(sizes, (b, e))
+    assert sizes[0][0] == 0 and sizes[-1][1] == 257 and all(sizes[i][1] == sizes[i + 1][0] for i in range(w - 1))
+    assert max(x[1] - x[0] for x in sizes) - min(x[1] - x[0] for x in sizes) <= 1
+    # 2. each rank "processes" its shard independently (a replica: same weights, own images); results only meet in a gather
+    torch.manual_seed(0)
+    weight = torch.randn(16, 4)
+    images = torch.arange(257 * 16, dtype=torch.float32).reshape(257, 16)
+    mine = images[b:e] @ weight
+    gathered = [None] * w
+    dist.all_gather_object(gathered, mine)
+    assert torch.equal(torch.cat(gathered), images @ weight)
+    # 3. timing reductions: max over ranks, whole-job throughput
+    sd.barrier()
+    ms = 10.0 * (rank + 1)
+    assert sd.max_over_ranks(ms) == 10.0 * world
+    ips = sd.aggregate_images_per_second(e - b, ms)
+    assert abs(ips - 257 / (10.0 * world / 1e3)) < 1e-6
+    out[rank] = True
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gloo_sharding_and_reductions():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(100)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_shard_range_properties():
+    from scouter_b200.dist import shard_range
+    for total in (0, 1, 7, 256, 1000):
+        for world in (1, 2, 3, 8):
+            r = [shard_range(total, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
