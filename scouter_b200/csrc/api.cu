@@ -312,7 +312,7 @@ static int validate_head(const scouter_xslot_desc_t* desc, const scouter_head_io
 extern "C" size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io) {
     if (validate_head(desc, io)) return 0;
     size_t n = (size_t)io->h * io->w;
-    size_t bytes = align_up((size_t)io->batch * n * XD * sizeof(float), 1024);
+    size_t bytes = align_up((size_t)4 * io->batch * n * XD * sizeof(float), 1024);   // up to 4 split-K partial slabs
     if (io->layout == SCOUTER_LAYOUT_NCHW) bytes += align_up((size_t)io->batch * n * io->channel * sizeof(float), 1024);
     return bytes;
 }
@@ -329,23 +329,48 @@ extern "C" int scouter_head_forward(const scouter_xslot_desc_t* desc, const void
     float* xbuf = (float*)workspace;
     const float* feat = io->feat;
     if (io->layout == SCOUTER_LAYOUT_NCHW) {
-        float* t = (float*)((char*)workspace + align_up((size_t)io->batch * n * XD * sizeof(float), 1024));
+        float* t = (float*)((char*)workspace + align_up((size_t)4 * io->batch * n * XD * sizeof(float), 1024));
         if (int e = launch_nchw_to_nhwc(io->feat, t, io->batch, io->channel, n, s)) return e;
         feat = t;
     }
-    float* x = io->x_out ? io->x_out : xbuf;
-    // conv1x1 + bias + ReLU (slot_model.py:108-109)
-    // The projection always runs error-compensated on the tensor cores (it is HBM-bound: the extra MMAs are free).
-    ConvArgs c{feat, io->conv_w, io->conv_b, nullptr, x, io->batch, io->h, io->w, io->channel, io->h, io->w, XD,
-               1, 1, 1, 0, 1, 1, 0, 1, nullptr};
+    const int M = io->batch * n;
+    const bool fast = xslot_fast_supported(desc, n);
+    // conv1x1 + bias + ReLU (slot_model.py:108-109).  On the tensor cores the projection always runs error-compensated
+    // (it is HBM-bound: the extra MMAs are free).
+    ConvArgs c{feat, io->conv_w, io->conv_b, nullptr, nullptr, io->batch, io->h, io->w, io->channel, io->h, io->w, XD,
+               1, 1, 1, 0, 1, 1, 0, 1, nullptr, 1};
+    const bool tc = io->math != SCOUTER_MATH_FP32 && umma_conv_supported(c);
+    const int kblocks = io->channel / 32;
+    // split-K so that the long serial K loop (K = ch) spreads over all SMs; the partial sums are finished (fixed order,
+    // + bias, ReLU) by the loop kernel while it loads its tokens
+    const int ksplit = (tc && fast && kblocks % 4 == 0 && kblocks >= 16) ? 4 : 1;
+    XSlotFastIO f;
+    f.batch = io->batch; f.n = n; f.pe = io->pe; f.x_out = nullptr;
+    f.logits = io->logits; f.attn = io->attn; f.attn_sum = io->attn_sum;
+    f.x = nullptr; f.xpart = nullptr; f.conv_bias = nullptr; f.split_stride = 0; f.nsplit = 0;
     int rc;
-    if (io->math != SCOUTER_MATH_FP32 && umma_conv_supported(c)) {
+    if (ksplit > 1) {
+        c.out = xbuf;            // ksplit slabs of (M, 64)
+        c.ksplit = ksplit;
+        UmmaConvPlan tmp;
+        if ((rc = launch_conv_umma(c, tmp, s))) return rc;
+        f.xpart = xbuf; f.conv_bias = io->conv_b; f.split_stride = (long long)M * XD; f.nsplit = ksplit;
+        f.x_out = io->x_out;
+        return xslot_fast_launch(desc, packed, f, s);
+    }
+    float* x = io->x_out ? io->x_out : xbuf;
+    c.out = x;
+    if (tc) {
         UmmaConvPlan tmp;
         rc = launch_conv_umma(c, tmp, s);
     } else {
         rc = launch_conv_simt(c, s);
     }
     if (rc) return rc;
+    if (fast) {
+        f.x = x;
+        return xslot_fast_launch(desc, packed, f, s);
+    }
     scouter_xslot_io_t xi;
     memset(&xi, 0, sizeof(xi));
     xi.batch = io->batch; xi.n = n;

@@ -44,6 +44,9 @@ struct UmmaArgs {
     int a_bytes;
     int chunk;  // k-blocks per accumulation chunk
     int rem_rows;  // SPLIT: > 0 = weights are pre-split, remainder rows start at this row of the weight map
+    int ksplit;    // > 1: split-K; unit (tile, sp) covers k-blocks [sp*kblocks, (sp+1)*kblocks) of the full K and writes raw
+                   // partial sums to out + sp*slab (no bias / ReLU); `kblocks` is then the per-split count
+    long long slab;  // floats between partial slabs
 };
 
 template <int BN, bool SPLIT>
@@ -98,7 +101,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int total = p.m_tiles * p.n_tiles * p.groups;
+    const int total = p.m_tiles * p.n_tiles * p.groups * p.ksplit;
     // The K loop of a tile is cut into chunks of p.chunk k-blocks; each chunk accumulates in its own TMEM buffer
     // (the two buffers alternate across chunks AND tiles) and the epilogue threads merge the chunks in fp32
     // round-to-nearest registers.  The TMEM accumulator truncates on every MMA, so this bounds the truncation
@@ -111,9 +114,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int nt = t % p.n_tiles;
-                const int mt = (t / p.n_tiles) % p.m_tiles;
-                const int g = t / (p.n_tiles * p.m_tiles);
+                const int sp = t % p.ksplit;
+                const int tt = t / p.ksplit;
+                const int nt = tt % p.n_tiles;
+                const int mt = (tt / p.n_tiles) % p.m_tiles;
+                const int g = tt / (p.n_tiles * p.m_tiles);
                 int w0 = 0, h0 = 0, b0 = 0;
                 if (p.mode) {
                     w0 = (mt % p.tw) * p.Wb;
@@ -125,17 +130,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint8_t* sa = smem + stage * C::STAGE;
                     uint8_t* sb = sa + C::A_BYTES;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + C::B_BYTES + (SPLIT && p.rem_rows ? C::B_BYTES : 0)));
-                    const int tap = kb / p.cblocks;
-                    const int c0 = p.cin_g * g + (kb - tap * p.cblocks) * 32;
+                    const int kbg = sp * p.kblocks + kb;   // k-block index in the full K
+                    const int tap = kbg / p.cblocks;
+                    const int c0 = p.cin_g * g + (kbg - tap * p.cblocks) * 32;
                     if (p.mode) {
                         const int r = tap / p.kw, s = tap - r * p.kw;
                         tma_load_4d(sa, &tmA, &full[stage], c0, w0 + s - p.pad, h0 + r - p.pad, b0);
                     } else {
                         tma_load_2d(sa, &tmA, &full[stage], c0, mt * 128);
                     }
-                    tma_load_2d(sb, &tmB, &full[stage], kb * 32, g * p.cout_g + nt * BN);
+                    tma_load_2d(sb, &tmB, &full[stage], kbg * 32, g * p.cout_g + nt * BN);
                     if (SPLIT && p.rem_rows)  // pre-split weights: the remainder tile comes from the host-made copy
-                        tma_load_2d(sa + C::RAW + C::A_BYTES, &tmB, &full[stage], kb * 32, p.rem_rows + g * p.cout_g + nt * BN);
+                        tma_load_2d(sa + C::RAW + C::A_BYTES, &tmB, &full[stage], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -190,9 +196,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = grp * C::NC;
         uint32_t cc = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const int nt = t % p.n_tiles;
-            const int mt = (t / p.n_tiles) % p.m_tiles;
-            const int g = t / (p.n_tiles * p.m_tiles);
+            const int sp = t % p.ksplit;
+            const int tt = t / p.ksplit;
+            const int nt = tt % p.n_tiles;
+            const int mt = (tt / p.n_tiles) % p.m_tiles;
+            const int g = tt / (p.n_tiles * p.m_tiles);
             bool valid;
             long long orow;
             if (p.mode) {
@@ -209,7 +217,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 valid = orow < p.M;
             }
             const int ch0 = g * p.cout_g + nt * BN + col0;
-            float* op = p.out + orow * p.Cout + ch0;
+            float* op = p.out + (long long)sp * p.slab + orow * p.Cout + ch0;
             const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
 
             auto finish = [&](const uint32_t (&r)[32], int c) {   // bias / residual / ReLU / store of 32 columns
@@ -441,7 +449,17 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
         SC_CUDA(cudaGetDevice(&dev));
         SC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const long long total = (long long)u.m_tiles * u.n_tiles * u.groups;
+    u.ksplit = 1;
+    u.slab = 0;
+    if (a.ksplit > 1) {
+        SC_CHECK_ARG(u.kblocks % a.ksplit == 0 && !a.res, SCOUTER_E_INVALID, "conv_umma: ksplit=%d does not divide %d k-blocks", a.ksplit, u.kblocks);
+        u.ksplit = a.ksplit;
+        u.kblocks /= a.ksplit;
+        u.slab = (long long)u.M * a.Cout;
+        u.bias = nullptr; u.relu = 0; u.round_out = 0;
+        if (!a.split) u.chunk = u.kblocks;
+    }
+    const long long total = (long long)u.m_tiles * u.n_tiles * u.groups * u.ksplit;
     const int grid = (int)std::min<long long>(total, sms);
     if (a.split) {
         switch (BN) {

@@ -542,6 +542,12 @@ extern "C" int scouter_xslot_forward(const scouter_xslot_desc_t* desc, const voi
     SC_CHECK_ARG(io->batch > 0 && io->n > 0, SCOUTER_E_INVALID, "xslot_forward: batch=%d n=%d", io->batch, io->n);
     SC_CHECK_ARG(io->x && io->logits, SCOUTER_E_INVALID, "xslot_forward: x / logits is NULL");
     SC_CHECK_ARG(io->x_pe || io->pe, SCOUTER_E_INVALID, "xslot_forward: give x_pe or the pe table");
+    if (!io->x_pe && io->x_sd == 1 && io->x_sn == XD && io->x_sb == (int64_t)io->n * XD && xslot_fast_supported(desc, io->n)) {
+        XSlotFastIO f;
+        f.batch = io->batch; f.n = io->n; f.x = io->x; f.xpart = nullptr; f.conv_bias = nullptr; f.split_stride = 0; f.nsplit = 0;
+        f.pe = io->pe; f.x_out = nullptr; f.logits = io->logits; f.attn = io->attn; f.attn_sum = io->attn_sum;
+        return xslot_fast_launch(desc, packed, f, (cudaStream_t)stream);
+    }
     return xslot_loop_launch(desc, packed, io, (cudaStream_t)stream);
 }
 

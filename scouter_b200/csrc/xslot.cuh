@@ -25,4 +25,21 @@ struct XSlotPacked {
 
 int validate_xslot_desc(const scouter_xslot_desc_t* d);
 
+// Fast loop kernel (xslot_fast.cu): contiguous tokens + PE table; optionally finishes a split-K projection.
+struct XSlotFastIO {
+    int batch, n;
+    const float* x;          // (B, n, 64) or null when xpart is given
+    const float* xpart;      // (nsplit, B*n, 64) partial projections (no bias), or null
+    const float* conv_bias;  // (64), with xpart
+    long long split_stride;  // floats between slabs
+    int nsplit;
+    const float* pe;         // (n, 64)
+    float* x_out;            // optional (B, n, 64): the finished projection (tests)
+    float* logits;
+    float* attn;
+    float* attn_sum;
+};
+bool xslot_fast_supported(const scouter_xslot_desc_t* d, int n);
+int xslot_fast_launch(const scouter_xslot_desc_t* d, const void* packed, const XSlotFastIO& io, cudaStream_t s);
+
 }  // namespace scouter

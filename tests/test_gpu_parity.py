@@ -250,3 +250,37 @@ def test_full_size_properties_cfg3(dev):
     assert float((out.exp().sum(1) - 1).abs().max()) < 1e-4
     assert torch.equal(out[perm], out_p)                                   # bitwise: no cross-image coupling
     assert scaled_err(out[:meta["batch"]], z["log_probs"]) < 1e-3          # golden images inside a big batch
+
+
+@pytest.mark.parametrize("name", ["head_s10_n81_l3", "head_s30_n81_l3", "head_s10_n49_l1_neg", "head_s7_n64_b1"])
+def test_xslot_forward_pe_mode_fast_kernel(dev, name):
+    """scouter_xslot_forward with (x, PE table) instead of a materialised x+PE: the throughput kernel (2 images per CTA,
+    weights in shared memory) must reproduce the reference goldens like the general kernel does."""
+    import ctypes as C
+    z, meta = load_golden(name)
+    c = meta["case"]
+    m = sb.SlotAttention(c["C"], c["spc"], 64, loss_status=c["ls"], power=c["power"], to_k_layer=c["L"])
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=3))
+    m = m.to(dev).eval()
+    desc, packed = m.desc_and_pack(dev)
+    _, x = head_inputs(c)
+    fs = int(round(c["n"] ** 0.5))
+    pe = sb.build_position_encoding("sine", 64).table(fs, fs, dev)
+    xd = x.to(dev).contiguous()
+    b, n = c["B"], c["n"]
+    s = c["C"] * c["spc"]
+    logits = torch.empty(b, c["C"], device=dev)
+    attn = torch.empty(b, s, n, device=dev)
+    asum = torch.empty(b, device=dev)
+    io = L.XSlotIO()
+    io.batch, io.n = b, n
+    io.x, io.x_sb, io.x_sn, io.x_sd = xd.data_ptr(), n * 64, 64, 1
+    io.x_pe, io.pe = 0, pe.data_ptr()
+    io.logits, io.attn, io.attn_sum = logits.data_ptr(), attn.data_ptr(), asum.data_ptr()
+    L.check(L.lib().scouter_xslot_forward(C.byref(desc), packed.data_ptr(), C.byref(io), 0, 0, 0))
+    torch.cuda.synchronize()
+    floor = rel_err(z["logits"], z["logits64"])
+    assert scaled_err(logits, z["logits"]) < max(2e-5, 20 * floor)
+    afloor = float(np.abs(z["attn"] - z["attn64"]).max())
+    assert float((attn.cpu() - torch.from_numpy(z["attn"])).abs().max()) < max(2e-5, 20 * afloor)
+    assert torch.allclose(asum.cpu(), torch.from_numpy(z["attn"]).sum((1, 2)), rtol=1e-5, atol=1e-4)
