@@ -14,7 +14,9 @@ struct UmmaConvPlan {
     bool valid = false;
     bool halo = false;
     bool presplit = false;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO;
+    const float* out = nullptr;
+    int ksplit = 0;
     const float* in = nullptr;
     const float* w = nullptr;
     int B = 0, H = 0, W = 0, Cin = 0, Cout = 0, kh = 0, groups = 0, BN = 0;

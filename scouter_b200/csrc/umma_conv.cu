@@ -43,6 +43,7 @@ struct UmmaArgs {
     int relu, round_out;
     int a_bytes;
     int chunk;  // k-blocks per accumulation chunk
+    int tma_store;  // flat mode: epilogue stages 128x16 blocks in shared memory and writes them with TMA stores
     int rem_rows;  // SPLIT: > 0 = weights are pre-split, remainder rows start at this row of the weight map
     int ksplit;    // > 1: split-K; unit (tile, sp) covers k-blocks [sp*kblocks, (sp+1)*kblocks) of the full K and writes raw
                    // partial sums to out + sp*slab (no bias / ReLU); `kblocks` is then the per-split count
@@ -55,19 +56,22 @@ struct Cfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
     static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | B | A_r | B_r]
-    static constexpr int STAGES = (200 * 1024 / STAGE) > 8 ? 8 : (200 * 1024 / STAGE);
+    static constexpr int STAGES = (192 * 1024 / STAGE) > 8 ? 8 : (192 * 1024 / STAGE);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
     // fp32 sums of the chunked accumulation fit in registers (64 per thread).
     static constexpr int EPI_GROUPS = (SPLIT && BN == 128) ? 2 : 1;
     static constexpr int NC = BN / EPI_GROUPS;               // columns per epilogue thread
     static constexpr int THREADS = SPLIT ? 512 : 256;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 512 /*barriers*/;
+    static constexpr int OUT_STAGE = 128 * 64;              // TMA-store staging: 128 rows x 16 fp32, SWIZZLE_64B
+    static constexpr int OUT_BYTES = EPI_GROUPS * 2 * OUT_STAGE;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 1024 /*barriers*/ + OUT_BYTES;
 };
 
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(Cfg<BN, SPLIT>::THREADS, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const UmmaArgs p) {
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const UmmaArgs p) {
     using C = Cfg<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -77,6 +81,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* cempty = cfull + 2;          // [2] accumulator chunk drained by every epilogue thread
     uint64_t* split_done = cempty + 2;     // [STAGES], SPLIT only: remainders written, stage ready for the issuer
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(split_done + C::STAGES);
+    uint8_t* out_stage = smem + C::STAGES * C::STAGE + 1024;   // [EPI_GROUPS][2][OUT_STAGE], 1024-aligned
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (warp == 0 && elect_one()) {
@@ -240,6 +245,48 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             };
 
+            // TMA-store variant (flat mode): 16 columns of every row of the tile go through a swizzled staging buffer
+            // and leave as ONE bulk tensor store -- no LSU wavefronts for the output, rows >= M are clipped by TMA.
+            int sbuf = 0;
+            auto emit_tma16 = [&](const float* v, int c16) {
+                uint8_t* stg = out_stage + (grp * 2 + sbuf) * C::OUT_STAGE;
+                if (row == 0) bulk_wait_read<1>();                 // the store that used this buffer two chunks ago is done
+                named_bar_sync(1 + grp, 128);
+                float x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = v[j];
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c16 * 16 + 4 * j));
+                        x[4 * j] += bv.x; x[4 * j + 1] += bv.y; x[4 * j + 2] += bv.z; x[4 * j + 3] += bv.w;
+                    }
+                }
+                if (rp && valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + c16 * 16 + 4 * j));
+                        x[4 * j] += rv.x; x[4 * j + 1] += rv.y; x[4 * j + 2] += rv.z; x[4 * j + 3] += rv.w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (p.relu) x[j] = fmaxf(x[j], 0.f);
+                    if (p.round_out) x[j] = to_tf32(x[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)   // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+                    *reinterpret_cast<float4*>(stg + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) =
+                        make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                fence_proxy_async();
+                named_bar_sync(1 + grp, 128);
+                if (row == 0) {
+                    tma_store_3d(&tmO, stg, ch0 + c16 * 16, mt * 128, sp);
+                    bulk_commit();
+                }
+                sbuf ^= 1;
+            };
+
             if constexpr (SPLIT) {
                 float acc[C::NC];
 #pragma unroll
@@ -259,12 +306,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_before();
                     mbar_arrive(&cempty[buf]);
                 }
+                if (p.tma_store) {
 #pragma unroll
-                for (int c = 0; c < C::NC / 32; ++c) {
-                    uint32_t r[32];
+                    for (int c = 0; c < C::NC / 16; ++c) emit_tma16(&acc[c * 16], c);
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[c * 32 + j]);
-                    finish(r, c);
+                    for (int c = 0; c < C::NC / 32; ++c) {
+                        uint32_t r[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[c * 32 + j]);
+                        finish(r, c);
+                    }
                 }
             } else {
                 const int buf = cc & 1;
@@ -275,13 +327,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
                     tmem_ld_wait();
-                    finish(r, c);
+                    if (p.tma_store) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        emit_tma16(&v[0], 2 * c);
+                        emit_tma16(&v[16], 2 * c + 1);
+                    } else {
+                        finish(r, c);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&cempty[buf]);
                 ++cc;
             }
         }
+        if (p.tma_store && row == 0) bulk_wait<0>();   // all bulk stores of this group have completed
     } else if (SPLIT && warp >= 8 && warp < 12) {
         // ===== operand splitters: x_r = x - trunc19(x) for the A and B tiles, same (swizzled) offsets =====
         const int tid = threadIdx.x - 256;  // 0..127
@@ -352,11 +413,11 @@ int pick_bn(int cout_g) {
 }
 
 template <int BN, bool SPLIT>
-int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const UmmaArgs& u, int grid, cudaStream_t s) {
+int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tO, const UmmaArgs& u, int grid, cudaStream_t s) {
     using C = Cfg<BN, SPLIT>;
     static_assert(C::STAGES >= 2, "pipeline too shallow");
     SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    conv_umma_kernel<BN, SPLIT><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, u);
+    conv_umma_kernel<BN, SPLIT><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, tO, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -449,6 +510,21 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
         SC_CUDA(cudaGetDevice(&dev));
         SC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    static bool no_tma_store = getenv("SCOUTER_NO_TMA_STORE") != nullptr;
+    u.tma_store = (!u.mode && !no_tma_store && a.Cout % 16 == 0) ? 1 : 0;
+    if (u.tma_store && !(reuse && plan.out == a.out && plan.ksplit == std::max(1, a.ksplit))) {
+        const int ks = std::max(1, a.ksplit);
+        cuuint64_t dimsO[3] = {(cuuint64_t)a.Cout, (cuuint64_t)u.M, (cuuint64_t)ks};
+        cuuint64_t stridesO[2] = {(cuuint64_t)a.Cout * 4, (cuuint64_t)u.M * a.Cout * 4};
+        cuuint32_t boxO[3] = {16, 128, 1};
+        cuuint32_t esO[3] = {1, 1, 1};
+        CUresult r = enc(&plan.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.out, dimsO, stridesO, boxO, esO,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+        plan.out = a.out;
+        plan.ksplit = ks;
+    }
     u.ksplit = 1;
     u.slab = 0;
     if (a.ksplit > 1) {
@@ -463,15 +539,15 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     const int grid = (int)std::min<long long>(total, sms);
     if (a.split) {
         switch (BN) {
-            case 32: return launch_bn<32, true>(plan.tmA, plan.tmB, u, grid, s);
-            case 64: return launch_bn<64, true>(plan.tmA, plan.tmB, u, grid, s);
-            case 128: return launch_bn<128, true>(plan.tmA, plan.tmB, u, grid, s);
+            case 32: return launch_bn<32, true>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
+            case 64: return launch_bn<64, true>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
+            case 128: return launch_bn<128, true>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
         }
     } else {
         switch (BN) {
-            case 32: return launch_bn<32, false>(plan.tmA, plan.tmB, u, grid, s);
-            case 64: return launch_bn<64, false>(plan.tmA, plan.tmB, u, grid, s);
-            case 128: return launch_bn<128, false>(plan.tmA, plan.tmB, u, grid, s);
+            case 32: return launch_bn<32, false>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
+            case 64: return launch_bn<64, false>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
+            case 128: return launch_bn<128, false>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
         }
     }
     return SCOUTER_E_UNSUPPORTED;
