@@ -152,27 +152,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer.  The whole warp walks the loop so the descriptor arithmetic is warp-uniform (uniform
-        // datapath, no R2UR); lane 0 alone polls the barriers and issues. =====
-        const bool leader = lane == 0;
-        constexpr uint32_t idesc = idesc_tf32(128, BN);
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t cc = 0;  // running chunk counter
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.chunk, ++cc) {
-                const int buf = cc & 1;
-                mbar_wait_warp(&cempty[buf], ((cc >> 1) & 1) ^ 1, lane);
-                const uint32_t d_tmem = tmem_base + buf * BN;
-                const int kb1 = min(kb0 + p.chunk, p.kblocks);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait_warp(SPLIT ? &split_done[stage] : &full[stage], phase, lane);
+        if (elect_one()) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = idesc_tf32(128, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t cc = 0;  // running chunk counter
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.chunk, ++cc) {
+                    const int buf = cc & 1;
+                    mbar_wait(&cempty[buf], ((cc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * C::STAGE);
-                    const uint64_t da = smem_desc_sw128(sa);
-                    const uint64_t db = smem_desc_sw128(sa + C::A_BYTES);
-                    const uint32_t first = kb != kb0;
-                    if (leader) {
+                    const uint32_t d_tmem = tmem_base + buf * BN;
+                    const int kb1 = min(kb0 + p.chunk, p.kblocks);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(SPLIT ? &split_done[stage] : &full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+                        const uint64_t da = smem_desc_sw128(sa);
+                        const uint64_t db = smem_desc_sw128(sa + C::A_BYTES);
+                        const uint32_t first = kb != kb0;
                         // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
                         if constexpr (SPLIT) {
                             const uint64_t dar = smem_desc_sw128(sa + C::RAW);
@@ -188,10 +187,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, first | k);
                         }
                         umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
-                        if (kb + 1 == kb1) umma_commit(&cfull[buf]);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&cfull[buf]);
                 }
             }
         }

@@ -150,34 +150,35 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer.  The whole warp walks the loop so the descriptor arithmetic is warp-uniform (uniform
-        // datapath, no R2UR); lane 0 alone polls the barriers and issues. =====
-        const bool leader = lane == 0;
-        constexpr uint32_t idesc = idesc_tf32(128, BN);
-        int ps = 0, bs = 0;
-        uint32_t pphase = 0, bphase = 0, cc = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            int step = 0;
-            for (int cb = 0; cb < p.cblocks; ++cb) {
-                mbar_wait_warp(&pready[ps], pphase, lane);
-                const uint32_t pa = smem_u32(patch0 + ps * 2 * p.patch_alloc);
-                for (int tap = 0; tap < 9; ++tap, ++step) {
-                    const int buf = cc & 1;
-                    const bool chunk_start = step % p.chunk == 0;
-                    if (chunk_start) mbar_wait_warp(&cempty[buf], ((cc >> 1) & 1) ^ 1, lane);
-                    mbar_wait_warp(&bfull[bs], bphase, lane);
+        if (elect_one()) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = idesc_tf32(128, BN);
+            int ps = 0, bs = 0;
+            uint32_t pphase = 0, bphase = 0, cc = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int step = 0;
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    mbar_wait(&pready[ps], pphase);
                     tc_fence_after();
-                    const int r = tap / 3, s = tap - 3 * r;
-                    const uint32_t aoff = (uint32_t)(r * p.PW + s) * 128u;
-                    const uint64_t da = smem_desc_sw128(pa + aoff);
-                    const uint64_t dar = smem_desc_sw128(pa + p.patch_alloc + aoff);
-                    const uint32_t sb = smem_u32(bt0 + bs * C::B_STAGE);
-                    const uint64_t db = smem_desc_sw128(sb);
-                    const uint64_t dbr = smem_desc_sw128(sb + C::B_BYTES);
-                    const uint32_t d_tmem = tmem_base + buf * BN;
-                    const uint32_t first = chunk_start ? 0u : 1u;
-                    const bool chunk_end = (step + 1) % p.chunk == 0 || step + 1 == ksteps;
-                    if (leader) {
+                    const uint32_t pa = smem_u32(patch0 + ps * 2 * p.patch_alloc);
+                    for (int tap = 0; tap < 9; ++tap, ++step) {
+                        const int buf = cc & 1;
+                        const bool chunk_start = step % p.chunk == 0;
+                        if (chunk_start) {
+                            mbar_wait(&cempty[buf], ((cc >> 1) & 1) ^ 1);
+                            tc_fence_after();
+                        }
+                        mbar_wait(&bfull[bs], bphase);
+                        tc_fence_after();
+                        const int r = tap / 3, s = tap - 3 * r;
+                        const uint32_t aoff = (uint32_t)(r * p.PW + s) * 128u;
+                        const uint64_t da = smem_desc_sw128(pa + aoff);
+                        const uint64_t dar = smem_desc_sw128(pa + p.patch_alloc + aoff);
+                        const uint32_t sb = smem_u32(bt0 + bs * C::B_STAGE);
+                        const uint64_t db = smem_desc_sw128(sb);
+                        const uint64_t dbr = smem_desc_sw128(sb + C::B_BYTES);
+                        const uint32_t d_tmem = tmem_base + buf * BN;
+                        const uint32_t first = chunk_start ? 0u : 1u;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             umma_tf32(d_tmem, da + 2 * k, dbr + 2 * k, idesc, first | k);  // A_t * W_r
@@ -185,14 +186,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);           // A_t * W_t
                         }
                         umma_commit(&bempty[bs]);
-                        if (chunk_end) umma_commit(&cfull[buf]);
-                        if (tap == 8) umma_commit(&pempty[ps]);
+                        if (++bs == p.bst) { bs = 0; bphase ^= 1; }
+                        if ((step + 1) % p.chunk == 0 || step + 1 == ksteps) {
+                            umma_commit(&cfull[buf]);
+                            ++cc;
+                        }
                     }
-                    __syncwarp();
-                    if (++bs == p.bst) { bs = 0; bphase ^= 1; }
-                    if (chunk_end) ++cc;
+                    umma_commit(&pempty[ps]);
+                    if (++ps == p.pst) { ps = 0; pphase ^= 1; }
                 }
-                if (++ps == p.pst) { ps = 0; pphase ^= 1; }
             }
         }
     } else if ((warp >= 4 && warp < 8) || (C::EPI_GROUPS == 2 && warp >= 12)) {
