@@ -55,11 +55,9 @@ struct Cfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
-    static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | A_r | W_t | W_r], else [A | W]
-    static constexpr int W_OFF = SPLIT ? 2 * A_BYTES : A_BYTES;
-    static constexpr int ACC_COLS = SPLIT ? 2 * BN : BN;     // SPLIT: [A_t*W_t | A_t*W_r + A_r*W_t]
+    static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | B | A_r | B_r]
     static constexpr int STAGES = (192 * 1024 / STAGE) > 8 ? 8 : (192 * 1024 / STAGE);
-    static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
     // fp32 sums of the chunked accumulation fit in registers (64 per thread).
     static constexpr int EPI_GROUPS = (SPLIT && BN == 128) ? 2 : 1;
@@ -135,7 +133,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::STAGE;
-                    uint8_t* sb = sa + C::W_OFF;
+                    uint8_t* sb = sa + C::A_BYTES;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + C::B_BYTES + (SPLIT && p.rem_rows ? C::B_BYTES : 0)));
                     const int kbg = sp * p.kblocks + kb;   // k-block index in the full K
                     const int tap = kbg / p.cblocks;
@@ -148,7 +146,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     tma_load_2d(sb, &tmB, &full[stage], kbg * 32, g * p.cout_g + nt * BN);
                     if (SPLIT && p.rem_rows)  // pre-split weights: the remainder tile comes from the host-made copy
-                        tma_load_2d(sb + C::B_BYTES, &tmB, &full[stage], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
+                        tma_load_2d(sa + C::RAW + C::A_BYTES, &tmB, &full[stage], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -165,25 +163,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int buf = cc & 1;
                     mbar_wait(&cempty[buf], ((cc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
+                    const uint32_t d_tmem = tmem_base + buf * BN;
                     const int kb1 = min(kb0 + p.chunk, p.kblocks);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(SPLIT ? &split_done[stage] : &full[stage], phase);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + stage * C::STAGE);
                         const uint64_t da = smem_desc_sw128(sa);
-                        const uint64_t db = smem_desc_sw128(sa + C::W_OFF);
+                        const uint64_t db = smem_desc_sw128(sa + C::A_BYTES);
                         const uint32_t first = kb != kb0;
                         // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
                         if constexpr (SPLIT) {
-                            // two MMAs per k-step: A_t x [W_t ; W_r] (N = 2*BN, main | correction) and A_r x W_t into
-                            // the correction block -- one instruction fewer than the three separate products
-                            constexpr uint32_t idesc2 = idesc_tf32(128, 2 * BN);
-                            const uint64_t dar = smem_desc_sw128(sa + C::A_BYTES);
+                            const uint64_t dar = smem_desc_sw128(sa + C::RAW);
+                            const uint64_t dbr = smem_desc_sw128(sa + C::RAW + C::A_BYTES);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc2, first | k);   // [A_t*W_t | A_t*W_r]
-                                umma_tf32(d_tmem + BN, dar + 2 * k, db + 2 * k, idesc, 1);      // += A_r*W_t
+                                umma_tf32(d_tmem, da + 2 * k, dbr + 2 * k, idesc, first | k);  // A_t * W_r
+                                umma_tf32(d_tmem, dar + 2 * k, db + 2 * k, idesc, 1);          // A_r * W_t
+                                umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);           // A_t * W_t
                             }
                         } else {
 #pragma unroll
@@ -301,13 +298,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int c = 0; c < C::NC / 32; ++c) {
                         uint32_t r[32];
-                        uint32_t r2[32];
-                        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * C::ACC_COLS + col0 + c * 32;
-                        tmem_ld_32x32(ta, r);
-                        tmem_ld_32x32(ta + BN, r2);
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + col0 + c * 32, r);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
                     }
                     tc_fence_before();
                     mbar_arrive(&cempty[buf]);
@@ -331,7 +325,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * C::ACC_COLS + c * 32, r);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
                     tmem_ld_wait();
                     if (p.tma_store) {
                         float v[32];
@@ -352,28 +346,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (SPLIT && warp >= 8 && warp < 12) {
         // ===== operand splitters: x_r = x - trunc19(x) for the A and B tiles, same (swizzled) offsets =====
         const int tid = threadIdx.x - 256;  // 0..127
+        const int VEC = (p.rem_rows ? C::A_BYTES : C::RAW) / 16;  // float4 per stage: A (then B unless pre-split)
         int stage = 0;
         uint32_t phase = 0;
-        auto remainder = [](float4 v) {
-            v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            return v;
-        };
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(&full[stage], phase);
-                uint8_t* st = smem + stage * C::STAGE;
-                const float4* srcA = reinterpret_cast<const float4*>(st);
-                float4* dstA = reinterpret_cast<float4*>(st + C::A_BYTES);
+                const float4* src = reinterpret_cast<const float4*>(smem + stage * C::STAGE);
+                float4* dst = reinterpret_cast<float4*>(smem + stage * C::STAGE + C::RAW);
 #pragma unroll 4
-                for (int i = tid; i < C::A_BYTES / 16; i += 128) dstA[i] = remainder(srcA[i]);
-                if (!p.rem_rows) {   // weights not pre-split on the host
-                    const float4* srcB = reinterpret_cast<const float4*>(st + C::W_OFF);
-                    float4* dstB = reinterpret_cast<float4*>(st + C::W_OFF + C::B_BYTES);
-#pragma unroll 4
-                    for (int i = tid; i < C::B_BYTES / 16; i += 128) dstB[i] = remainder(srcB[i]);
+                for (int i = tid; i < VEC; i += 128) {
+                    float4 v = src[i];
+                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    dst[i] = v;
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&split_done[stage]);

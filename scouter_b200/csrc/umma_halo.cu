@@ -47,8 +47,7 @@ template <int BN>
 struct HCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int B_STAGE = 2 * B_BYTES;  // [W_t | W_r]
-    static constexpr int ACC_COLS = 2 * BN;      // per chunk buffer: [A_t*W_t | A_t*W_r + A_r*W_t]
-    static constexpr int TMEM_COLS = 2 * ACC_COLS;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr int EPI_GROUPS = BN == 128 ? 2 : 1;
     static constexpr int NC = BN / EPI_GROUPS;
     static constexpr int THREADS = 512;
@@ -154,7 +153,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (elect_one()) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc = idesc_tf32(128, BN);
-            constexpr uint32_t idesc2 = idesc_tf32(128, 2 * BN);
             int ps = 0, bs = 0;
             uint32_t pphase = 0, bphase = 0, cc = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -177,16 +175,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint64_t da = smem_desc_sw128(pa + aoff);
                         const uint64_t dar = smem_desc_sw128(pa + p.patch_alloc + aoff);
                         const uint32_t sb = smem_u32(bt0 + bs * C::B_STAGE);
-                        const uint64_t db = smem_desc_sw128(sb);       // [W_t ; W_r]: 2*BN rows, W_t first
-                        const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
+                        const uint64_t db = smem_desc_sw128(sb);
+                        const uint64_t dbr = smem_desc_sw128(sb + C::B_BYTES);
+                        const uint32_t d_tmem = tmem_base + buf * BN;
                         const uint32_t first = chunk_start ? 0u : 1u;
-                        // Two MMAs per 8-wide k-step instead of three: A_t against the concatenated [W_t ; W_r]
-                        // (N = 2*BN: main product and first correction land in adjacent column blocks), then A_r
-                        // against W_t into the correction block.  The issuing thread is the bottleneck for narrow N.
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc2, first | k);       // [A_t*W_t | A_t*W_r]
-                            umma_tf32(d_tmem + BN, dar + 2 * k, db + 2 * k, idesc, 1);          // += A_r*W_t
+                            umma_tf32(d_tmem, da + 2 * k, dbr + 2 * k, idesc, first | k);  // A_t * W_r
+                            umma_tf32(d_tmem, dar + 2 * k, db + 2 * k, idesc, 1);          // A_r * W_t
+                            umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);           // A_t * W_t
                         }
                         umma_commit(&bempty[bs]);
                         if (++bs == p.bst) { bs = 0; bphase ^= 1; }
@@ -225,13 +222,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int c = 0; c < C::NC / 32; ++c) {
                     uint32_t r[32];
-                    uint32_t r2[32];
-                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * C::ACC_COLS + col0 + c * 32;
-                    tmem_ld_32x32(ta, r);
-                    tmem_ld_32x32(ta + BN, r2);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + col0 + c * 32, r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
                 }
                 tc_fence_before();
                 mbar_arrive(&cempty[buf]);
