@@ -288,9 +288,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             };
 
             if constexpr (SPLIT) {
+                // The running fp32 sum starts from the residual: its loads are issued here, before the first chunk is
+                // waited for, so their DRAM latency hides behind the tile's MMAs (and costs no extra registers).
                 float acc[C::NC];
+                if (rp && valid) {
 #pragma unroll
-                for (int j = 0; j < C::NC; ++j) acc[j] = 0.f;
+                    for (int j = 0; j < C::NC / 4; ++j) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
+                        acc[4 * j] = rv.x; acc[4 * j + 1] = rv.y; acc[4 * j + 2] = rv.z; acc[4 * j + 3] = rv.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C::NC; ++j) acc[j] = 0.f;
+                }
+                rp = nullptr;   // already folded in
                 for (int ch = 0; ch < nchunks; ++ch, ++cc) {
                     const int buf = cc & 1;
                     mbar_wait(&cfull[buf], (cc >> 1) & 1);
