@@ -202,11 +202,32 @@ def main():
         clocks = sampler.stop(t0, t1) if sampler else None
         value = world * a.batch * a.steps / (ms / 1e3)
 
-        # ---- end to end through the C-ABI host entry -------------------------------------------------
+        # ---- end to end from host memory ----------------------------------------------------------------
+        # (a) one synchronous C call per step (scouter_forward_host: H2D, forward, D2H, sync);
+        # (b) the streaming API: same per-step copies, but batch i+1 uploads while batch i computes
         for _ in range(2):
             m.forward_host(x_host, dev)
-        ms_e2e = timed(lambda: m.forward_host(x_host, dev), a.steps)
+        ms_e2e_sync = timed(lambda: m.forward_host(x_host, dev), a.steps)
+        for _ in m.forward_host_stream([x_host] * 3, dev):
+            pass
+
+        def stream_steps():
+            n = 0
+            for out in m.forward_host_stream([x_host] * a.steps, dev):
+                n += 1
+            assert n == a.steps
+
+        barrier()
+        t_w0 = time.perf_counter()
+        stream_steps()
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t_w0) * 1e3
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t)
         e2e_value = world * a.batch * a.steps / (ms_e2e / 1e3)
+        e2e_sync_value = world * a.batch * a.steps / (ms_e2e_sync / 1e3)
 
         # ---- per-kernel: the fused head and the backbone program, CUDA events on the launch stream ---
         import ctypes as C
@@ -244,7 +265,11 @@ def main():
                    "(154 MB batch + GBs of activations) larger than the 126 MB L2, no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / a.steps,
-                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": a.batch * 10 * 4 + 12},
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": a.batch * 10 * 4,
+                "api": "SlotModel.forward_host_stream (pinned host batches in, pinned log-probs out; the H2D of batch i+1 "
+                       "overlaps the compute of batch i; wall-clock over all steps incl. first upload and last read-back)",
+                "synchronous_call_value": e2e_sync_value,
+                "synchronous_call": "scouter_forward_host: H2D + forward + D2H + sync in one C call per step"},
         "gpu_launches": launches * a.steps,
         "roofline": {"kernel": "xSlot head: scouter_head_forward (conv1x1+ReLU+PE+to_k+3x{QK^T,normalise,sigmoid,attn.V,GRU}+logits)",
                      "bound": "hbm", "achieved": head_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": head_gbs / pk["hbm"],

@@ -284,3 +284,17 @@ def test_xslot_forward_pe_mode_fast_kernel(dev, name):
     afloor = float(np.abs(z["attn"] - z["attn64"]).max())
     assert float((attn.cpu() - torch.from_numpy(z["attn"])).abs().max()) < max(2e-5, 20 * afloor)
     assert torch.allclose(asum.cpu(), torch.from_numpy(z["attn"]).sum((1, 2)), rtol=1e-5, atol=1e-4)
+
+
+def test_forward_host_stream_matches_eager(dev):
+    """The streaming host API (overlapped H2D) returns, in order, exactly what the eager forward returns."""
+    z, meta = load_golden("cfg2_resnest26d_pos_224")
+    m = build(meta, dev, L.MATH_TC)
+    m.keep_attn = False
+    xs = [synth_images(meta["batch"], meta["cin"], meta["size"], meta["size"], seed=100 + i).pin_memory() for i in range(5)]
+    with torch.no_grad():
+        eager = [m(x.to(dev)).cpu() for x in xs]
+        streamed = list(m.forward_host_stream(xs, dev))
+    assert len(streamed) == len(xs)
+    for a, b in zip(eager, streamed):
+        assert torch.equal(a, b)
