@@ -190,7 +190,8 @@ typedef struct scouter_op {
     int32_t reserved;
     /* Folded parameters, device pointers, fp32:
      *   CONV / STEM_CONV: w = (cout, kh, kw, cin/groups) "OHWI", b = (cout); for SCOUTER_MATH_TC an optional
-     *     w2 = W - trunc19(W) (same layout, stored directly after w) lets the kernels skip the on-the-fly weight split
+     *     w2 = bf16 [W ; W - trunc19(W)] ((2*cout, kh, kw, cin/groups) bfloat16) lets the kernels skip the on-the-fly
+     *     weight split
      */
     const float* w;
     const float* b;

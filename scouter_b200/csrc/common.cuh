@@ -75,7 +75,7 @@ struct ConvArgs {
     int B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, groups, relu;
     int round_out;  // round the stored activations to tf32 (SCOUTER_MATH_TC: the next conv's MMA reads them as tf32)
     int split;      // tcgen05 only: error-compensated 3xTF32 (operands split into trunc19 + remainder)
-    const float* w_rem;  // optional pre-split remainder weights W - trunc19(W), laid out like w and directly after it
+    const void* w_rem;   // optional host-pre-split correction weights: bf16 [W ; W - trunc19(W)], (2*Cout, kh, kw, Cin/g)
     int ksplit;          // tcgen05 flat kernel only: > 1 writes `ksplit` raw partial-sum slabs (M*Cout floats apart) to out
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);

@@ -122,6 +122,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 operands (K = 16 per instruction), fp32 accumulate.  Issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Instruction descriptor, kind::f16 with bf16 operands, fp32 accumulator, both operands K-major.
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4)                      // c_format  = F32
+           | (1u << 7) | (1u << 10)       // a_format = b_format = BF16
+           | ((uint32_t)(N >> 3) << 17)   // n_dim
+           | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
 // Instruction descriptor, kind::tf32, fp32 accumulator, both operands K-major (mma_sm100_desc.hpp InstrDescriptor).
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4)                      // c_format  = F32
@@ -140,6 +160,48 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)1 << 46;                    // descriptor version
     d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
     return d;
+}
+
+// Same for 64-byte rows (32 bf16 along K, one SWIZZLE_64B atom): 8-row groups 512 bytes apart, layout 4.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                    // SWIZZLE_64B
+    return d;
+}
+
+// Operand split of one 8-float group for the error-compensated product: x = trunc19(x) + r.  Returns bf16x8 of x
+// (in `xb`) and of r (in `rb`), each packed as 4 x bf16x2 -- the two correction products use 8-bit-mantissa operands,
+// which costs 2^-9 on terms that are themselves 2^-11 of the main product.
+__device__ __forceinline__ void split8_bf16(const float4& a, const float4& b, uint4& xb, uint4& rb) {
+    auto pack = [](float lo, float hi) {
+        uint32_t r;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
+    };
+    auto rem = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+    xb = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(b.x, b.y), pack(b.z, b.w));
+    rb = make_uint4(pack(rem(a.x), rem(a.y)), pack(rem(a.z), rem(a.w)), pack(rem(b.x), rem(b.y)), pack(rem(b.z), rem(b.w)));
+}
+
+// Converts `rows` rows of a SWIZZLE_128B fp32 tile (128-byte rows) into two SWIZZLE_64B bf16 tiles (64-byte rows):
+// bf16(x) and bf16(x - trunc19(x)).  Work item = (row, 8-float group); `tid`/`nthreads` stride over the items.
+__device__ __forceinline__ void split_tile_bf16(const uint8_t* src, uint8_t* dst_x, uint8_t* dst_r, int rows, int tid, int nthreads) {
+    for (int it = tid; it < rows * 4; it += nthreads) {
+        const int row = it >> 2, p = it & 3;
+        const int s = row & 7;
+        const uint8_t* rp = src + row * 128;
+        const float4 a = *reinterpret_cast<const float4*>(rp + (((2 * p) ^ s) << 4));
+        const float4 b = *reinterpret_cast<const float4*>(rp + (((2 * p + 1) ^ s) << 4));
+        uint4 xb, rb;
+        split8_bf16(a, b, xb, rb);
+        const int doff = row * 64 + ((p ^ ((row >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(dst_x + doff) = xb;
+        *reinterpret_cast<uint4*>(dst_r + doff) = rb;
+    }
 }
 
 // 32 lanes x 32 columns of fp32 from TMEM: thread i of the warp gets lane (base_lane + i), columns [col, col+32).

@@ -14,7 +14,7 @@ struct UmmaConvPlan {
     bool valid = false;
     bool halo = false;
     bool presplit = false;
-    CUtensorMap tmA, tmB, tmO;
+    CUtensorMap tmA, tmB, tmB2, tmO;
     const float* out = nullptr;
     int ksplit = 0;
     const float* in = nullptr;

@@ -4,10 +4,13 @@
 //
 // * Two precisions of the same kernel (template SPLIT):
 //     SPLIT=true  (SCOUTER_MATH_TC, default): error-compensated "3xTF32".  kind::tf32 reads the top 19 bits of an
-//       fp32 word, i.e. x_t = trunc19(x) EXACTLY; four splitter warps compute the remainder x_r = x - x_t (exact in
-//       fp32, tf32-representable to 2^-21|x|) for both the activation and the weight tile into sibling smem tiles,
-//       and the issuer accumulates  A_t*W_r + A_r*W_t + A_t*W_t  in the fp32 TMEM accumulator.  Operands stay plain
-//       fp32 in HBM (no extra traffic); the dropped term is <= 2^-20 relative: fp32-class results.
+//       fp32 word, i.e. x_t = trunc19(x) EXACTLY; the remainder x_r = x - x_t is exact in fp32 and ~2^-11 |x|.  The
+//       issuer accumulates, in the fp32 TMEM accumulator,  A_t*W_t (4 tf32 MMAs per 32-channel k-block) plus the two
+//       correction products A*W_r and A_r*W with bf16 operands (2 + 2 kind::f16 MMAs, K = 16 each: half the tensor
+//       time and half the shared-memory operand bytes of tf32; their 2^-9 operand rounding sits on terms that are
+//       2^-11 of the result).  Four splitter warps derive the bf16 tiles from the TMA-written fp32 tile in shared
+//       memory; weights come pre-split from the host.  Operands stay plain fp32 in HBM; measured error 1.5e-6
+//       (fp32 FMA: 5e-7, one-pass tf32: 7e-4).
 //     SPLIT=false (SCOUTER_MATH_TC_FAST): one tf32 MMA; producers round stored activations with cvt.rna and
 //       weights are pre-rounded on the host, so the MMA multiplies exactly the stored values (cuDNN-TF32 class).
 // * No im2col buffer: for a 3x3 conv the K loop walks the 9 taps and each tap is ONE 4-D TMA box load
@@ -55,7 +58,8 @@ struct Cfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
-    static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | B | A_r | B_r]
+    static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | W | bf16 A | bf16 A_r | bf16 W | bf16 W_r]
+    static constexpr int OFF_AB = RAW, OFF_ARB = RAW + A_BYTES / 2, OFF_WB = RAW + A_BYTES, OFF_WRB = RAW + A_BYTES + B_BYTES / 2;
     static constexpr int STAGES = (192 * 1024 / STAGE) > 8 ? 8 : (192 * 1024 / STAGE);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
@@ -71,7 +75,7 @@ struct Cfg {
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(Cfg<BN, SPLIT>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const UmmaArgs p) {
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO, const UmmaArgs p) {
     using C = Cfg<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -145,8 +149,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_load_2d(sa, &tmA, &full[stage], c0, mt * 128);
                     }
                     tma_load_2d(sb, &tmB, &full[stage], kbg * 32, g * p.cout_g + nt * BN);
-                    if (SPLIT && p.rem_rows)  // pre-split weights: the remainder tile comes from the host-made copy
-                        tma_load_2d(sa + C::RAW + C::A_BYTES, &tmB, &full[stage], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
+                    if (SPLIT && p.rem_rows) {  // host-pre-split weights: bf16 W and bf16 W_r tiles
+                        tma_load_2d(sa + C::OFF_WB, &tmB2, &full[stage], kbg * 32, g * p.cout_g + nt * BN);
+                        tma_load_2d(sa + C::OFF_WRB, &tmB2, &full[stage], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -174,14 +180,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint32_t first = kb != kb0;
                         // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
                         if constexpr (SPLIT) {
-                            const uint64_t dar = smem_desc_sw128(sa + C::RAW);
-                            const uint64_t dbr = smem_desc_sw128(sa + C::RAW + C::A_BYTES);
+                            constexpr uint32_t idesc_b = idesc_bf16(128, BN);
+                            const uint64_t dab = smem_desc_sw64(sa + C::OFF_AB), darb = smem_desc_sw64(sa + C::OFF_ARB);
+                            const uint64_t dwb = smem_desc_sw64(sa + C::OFF_WB), dwrb = smem_desc_sw64(sa + C::OFF_WRB);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                umma_tf32(d_tmem, da + 2 * k, dbr + 2 * k, idesc, first | k);  // A_t * W_r
-                                umma_tf32(d_tmem, dar + 2 * k, db + 2 * k, idesc, 1);          // A_r * W_t
-                                umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);           // A_t * W_t
-                            }
+                            for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, dab + 2 * k, dwrb + 2 * k, idesc_b, first | k);  // A * W_r
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, darb + 2 * k, dwb + 2 * k, idesc_b, 1);          // A_r * W
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);               // A_t * W_t
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, first | k);
@@ -355,25 +362,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (p.tma_store && row == 0) bulk_wait<0>();   // all bulk stores of this group have completed
     } else if (SPLIT && warp >= 8 && warp < 12) {
-        // ===== operand splitters: x_r = x - trunc19(x) for the A and B tiles, same (swizzled) offsets =====
+        // ===== operand splitters: bf16(x) and bf16(x - trunc19(x)) tiles of the activation (and, unless pre-split, weight) tile =====
         const int tid = threadIdx.x - 256;  // 0..127
-        const int VEC = (p.rem_rows ? C::A_BYTES : C::RAW) / 16;  // float4 per stage: A (then B unless pre-split)
         int stage = 0;
         uint32_t phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(&full[stage], phase);
-                const float4* src = reinterpret_cast<const float4*>(smem + stage * C::STAGE);
-                float4* dst = reinterpret_cast<float4*>(smem + stage * C::STAGE + C::RAW);
-#pragma unroll 4
-                for (int i = tid; i < VEC; i += 128) {
-                    float4 v = src[i];
-                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    dst[i] = v;
-                }
+                uint8_t* st = smem + stage * C::STAGE;
+                split_tile_bf16(st, st + C::OFF_AB, st + C::OFF_ARB, 128, tid, 128);
+                if (!p.rem_rows) split_tile_bf16(st + C::A_BYTES, st + C::OFF_WB, st + C::OFF_WRB, BN, tid, 128);
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&split_done[stage]);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -424,11 +422,12 @@ int pick_bn(int cout_g) {
 }
 
 template <int BN, bool SPLIT>
-int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tO, const UmmaArgs& u, int grid, cudaStream_t s) {
+int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const CUtensorMap& tO, const UmmaArgs& u, int grid,
+              cudaStream_t s) {
     using C = Cfg<BN, SPLIT>;
     static_assert(C::STAGES >= 2, "pipeline too shallow");
     SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    conv_umma_kernel<BN, SPLIT><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, tO, u);
+    conv_umma_kernel<BN, SPLIT><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, tB2, tO, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -472,9 +471,6 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
                        !plan.halo && plan.presplit == presplit;
     if (!reuse) {
         CUresult r;
-        if (presplit)
-            SC_CHECK_ARG(a.w_rem == a.w + (size_t)a.Cout * a.kh * a.kw * cin_g, SCOUTER_E_INVALID,
-                         "conv_umma: the remainder weights must directly follow the weights in memory");
         if (u.mode) {
             choose_tile(a.B, a.H, a.W, plan.Wb, plan.Hb, plan.Nb);
             cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
@@ -494,13 +490,23 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
         }
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
         const cuuint64_t Kt = (cuuint64_t)a.kh * a.kw * cin_g;
-        cuuint64_t dimsB[2] = {Kt, (cuuint64_t)a.Cout * (presplit ? 2 : 1)};
+        cuuint64_t dimsB[2] = {Kt, (cuuint64_t)a.Cout};
         cuuint64_t stridesB[1] = {Kt * 4};
         cuuint32_t boxB[2] = {32, (cuuint32_t)BN};
         cuuint32_t esB[2] = {1, 1};
         r = enc(&plan.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.w, dimsB, stridesB, boxB, esB, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+        if (presplit) {   // bf16 [W ; W_r]: (2*Cout) rows of Kt bf16
+            cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)2 * a.Cout};
+            cuuint64_t stridesB2[1] = {Kt * 2};
+            r = enc(&plan.tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.w_rem, dimsB2, stridesB2, boxB, esB,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(bf16 W) failed with %d", (int)r);
+        } else {
+            plan.tmB2 = plan.tmB;
+        }
         plan.valid = true; plan.halo = false; plan.presplit = presplit;
         plan.in = a.in; plan.w = a.w; plan.B = a.B; plan.H = a.H; plan.W = a.W; plan.Cin = a.Cin; plan.Cout = a.Cout;
         plan.kh = a.kh; plan.groups = a.groups; plan.BN = BN;
@@ -550,15 +556,15 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     const int grid = (int)std::min<long long>(total, sms);
     if (a.split) {
         switch (BN) {
-            case 32: return launch_bn<32, true>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
-            case 64: return launch_bn<64, true>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
-            case 128: return launch_bn<128, true>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
+            case 32: return launch_bn<32, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
+            case 64: return launch_bn<64, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
+            case 128: return launch_bn<128, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
         }
     } else {
         switch (BN) {
-            case 32: return launch_bn<32, false>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
-            case 64: return launch_bn<64, false>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
-            case 128: return launch_bn<128, false>(plan.tmA, plan.tmB, plan.tmO, u, grid, s);
+            case 32: return launch_bn<32, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
+            case 64: return launch_bn<64, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
+            case 128: return launch_bn<128, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
         }
     }
     return SCOUTER_E_UNSUPPORTED;

@@ -9,11 +9,12 @@
 // The M dimension then walks 128 CONSECUTIVE patch rows, i.e. "virtual" output rows m' = hb*PW + wb' that include
 // the two halo columns of every line (computed and discarded: Wb/PW of the MMA rows are useful).
 //
-// Per (channel block, tap) the weights arrive pre-split (W_t = raw fp32, which kind::tf32 truncates exactly, and
-// W_r = W - trunc19(W) from the host) as two TMA tiles; the activation remainder A_r = A - trunc19(A) is computed
-// by four splitter warps once per patch (not once per tap).  The issuer accumulates A_t*W_r + A_r*W_t + A_t*W_t in
-// TMEM in chunks of `chunk` k-steps; epilogue threads merge the chunks in fp32 registers (the TMEM accumulator
-// truncates on every MMA -- profiles/r01_tmem_accumulator_truncation.txt).
+// Per (channel block, tap) the weights arrive as three TMA tiles: W in fp32 (kind::tf32 reads trunc19(W) exactly) and
+// the host-made bf16 copies of W and of W_r = W - trunc19(W).  Four splitter warps turn each fp32 patch into bf16
+// patches of A and A_r = A - trunc19(A) once per patch (not once per tap).  The issuer accumulates
+// A_t*W_t (4 tf32 MMAs) + A*W_r + A_r*W (2 + 2 bf16 MMAs) in TMEM in chunks of `chunk` k-steps; epilogue threads merge
+// the chunks in fp32 registers (the TMEM accumulator truncates on every MMA --
+// profiles/r01_tmem_accumulator_truncation.txt).
 //
 // Warp roles (512 threads, 1 CTA/SM, persistent): 0 TMA producer | 1 MMA issuer | 2 TMEM alloc | 4-7 and 12-15
 // epilogue (two column halves) | 8-11 splitters.
@@ -46,7 +47,7 @@ struct HaloArgs {
 template <int BN>
 struct HCfg {
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int B_STAGE = 2 * B_BYTES;  // [W_t | W_r]
+    static constexpr int B_STAGE = 2 * B_BYTES;  // [W fp32 | bf16 W | bf16 W_r]
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr int EPI_GROUPS = BN == 128 ? 2 : 1;
     static constexpr int NC = BN / EPI_GROUPS;
@@ -56,7 +57,8 @@ struct HCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(512, 1)
-conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloArgs p) {
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmB2, const HaloArgs p) {
     using C = HCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -142,8 +144,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_arrive_expect_tx(&bfull[bs], (uint32_t)C::B_STAGE);
                         const int kcol = tap * p.cin_g + cb * 32;
                         const int nrow = g * p.cout_g + nt * BN;
-                        tma_load_2d(sb, &tmB, &bfull[bs], kcol, nrow);
-                        tma_load_2d(sb + C::B_BYTES, &tmB, &bfull[bs], kcol, p.Cout + nrow);  // remainder rows follow
+                        tma_load_2d(sb, &tmB, &bfull[bs], kcol, nrow);                                   // W fp32
+                        tma_load_2d(sb + C::B_BYTES, &tmB2, &bfull[bs], kcol, nrow);                      // bf16 W
+                        tma_load_2d(sb + C::B_BYTES + C::B_BYTES / 2, &tmB2, &bfull[bs], kcol, p.Cout + nrow);  // bf16 W_r
                         if (++bs == p.bst) { bs = 0; bphase ^= 1; }
                     }
                 }
@@ -171,20 +174,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_wait(&bfull[bs], bphase);
                         tc_fence_after();
                         const int r = tap / 3, s = tap - 3 * r;
-                        const uint32_t aoff = (uint32_t)(r * p.PW + s) * 128u;
-                        const uint64_t da = smem_desc_sw128(pa + aoff);
-                        const uint64_t dar = smem_desc_sw128(pa + p.patch_alloc + aoff);
+                        const uint32_t arow = (uint32_t)(r * p.PW + s);
+                        const uint64_t da = smem_desc_sw128(pa + arow * 128u);
+                        const uint64_t dab = smem_desc_sw64(pa + p.patch_alloc + arow * 64u);
+                        const uint64_t darb = smem_desc_sw64(pa + p.patch_alloc + p.patch_alloc / 2 + arow * 64u);
                         const uint32_t sb = smem_u32(bt0 + bs * C::B_STAGE);
                         const uint64_t db = smem_desc_sw128(sb);
-                        const uint64_t dbr = smem_desc_sw128(sb + C::B_BYTES);
+                        const uint64_t dwb = smem_desc_sw64(sb + C::B_BYTES);
+                        const uint64_t dwrb = smem_desc_sw64(sb + C::B_BYTES + C::B_BYTES / 2);
                         const uint32_t d_tmem = tmem_base + buf * BN;
                         const uint32_t first = chunk_start ? 0u : 1u;
+                        constexpr uint32_t idesc_b = idesc_bf16(128, BN);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_tf32(d_tmem, da + 2 * k, dbr + 2 * k, idesc, first | k);  // A_t * W_r
-                            umma_tf32(d_tmem, dar + 2 * k, db + 2 * k, idesc, 1);          // A_r * W_t
-                            umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);           // A_t * W_t
-                        }
+                        for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, dab + 2 * k, dwrb + 2 * k, idesc_b, first | k);  // A * W_r
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, darb + 2 * k, dwb + 2 * k, idesc_b, 1);          // A_r * W
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);               // A_t * W_t
                         umma_commit(&bempty[bs]);
                         if (++bs == p.bst) { bs = 0; bphase ^= 1; }
                         if ((step + 1) % p.chunk == 0 || step + 1 == ksteps) {
@@ -250,25 +256,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp >= 8 && warp < 12) {
-        // ===== splitters: remainder patch = patch - trunc19(patch), once per patch =====
+        // ===== splitters: bf16 patches of A and of A - trunc19(A), once per patch =====
         const int tid = threadIdx.x - 256;
-        const int nvec = p.patch_bytes / 16;
+        const int prows = p.patch_bytes / 128;
         int ps = 0;
         uint32_t pphase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             for (int cb = 0; cb < p.cblocks; ++cb) {
                 mbar_wait(&pfull[ps], pphase);
-                const float4* src = reinterpret_cast<const float4*>(patch0 + ps * 2 * p.patch_alloc);
-                float4* dst = reinterpret_cast<float4*>(patch0 + ps * 2 * p.patch_alloc + p.patch_alloc);
-#pragma unroll 4
-                for (int i = tid; i < nvec; i += 128) {
-                    float4 v = src[i];
-                    v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    dst[i] = v;
-                }
+                uint8_t* raw = patch0 + ps * 2 * p.patch_alloc;
+                split_tile_bf16(raw, raw + p.patch_alloc, raw + p.patch_alloc + p.patch_alloc / 2, prows, tid, 128);
                 fence_proxy_async();
                 mbar_arrive(&pready[ps]);
                 if (++ps == p.pst) { ps = 0; pphase ^= 1; }
@@ -323,9 +320,10 @@ int halo_bn(int cout_g) {
 }
 
 template <int BN>
-int launch_halo_bn(const CUtensorMap& tA, const CUtensorMap& tB, const HaloArgs& u, int grid, int smem, cudaStream_t s) {
+int launch_halo_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const HaloArgs& u, int grid, int smem,
+                   cudaStream_t s) {
     SC_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv3x3_halo_kernel<BN><<<grid, 512, smem, s>>>(tA, tB, u);
+    conv3x3_halo_kernel<BN><<<grid, 512, smem, s>>>(tA, tB, tB2, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -391,17 +389,21 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_halo: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
-        // weights: rows [0, Cout) = W, rows [Cout, 2*Cout) = W - trunc19(W); both (9*cin_g) wide
-        SC_CHECK_ARG(a.w_rem == a.w + (size_t)a.Cout * 9 * cin_g, SCOUTER_E_INVALID,
-                     "conv_halo: the remainder weights must directly follow the weights in memory");
         const cuuint64_t Kt = (cuuint64_t)9 * cin_g;
-        cuuint64_t dimsB[2] = {Kt, (cuuint64_t)2 * a.Cout};
+        cuuint64_t dimsB[2] = {Kt, (cuuint64_t)a.Cout};
         cuuint64_t stridesB[1] = {Kt * 4};
         cuuint32_t boxB[2] = {32, (cuuint32_t)BN};
         cuuint32_t esB[2] = {1, 1};
         r = enc(&plan.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.w, dimsB, stridesB, boxB, esB, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_halo: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+        // bf16 [W ; W - trunc19(W)]: (2*Cout) rows of 9*cin_g bf16
+        cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)2 * a.Cout};
+        cuuint64_t stridesB2[1] = {Kt * 2};
+        r = enc(&plan.tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.w_rem, dimsB2, stridesB2, boxB, esB,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_halo: cuTensorMapEncodeTiled(bf16 W) failed with %d", (int)r);
         plan.valid = true; plan.halo = true;
         plan.in = a.in; plan.w = a.w; plan.B = a.B; plan.H = a.H; plan.W = a.W; plan.Cin = a.Cin; plan.Cout = a.Cout;
         plan.kh = 3; plan.groups = a.groups; plan.BN = BN;
@@ -415,9 +417,9 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     const long long total = (long long)u.m_tiles * u.n_tiles * u.groups;
     const int grid = (int)std::min<long long>(total, sms);
     switch (BN) {
-        case 32: return launch_halo_bn<32>(plan.tmA, plan.tmB, u, grid, smem, s);
-        case 64: return launch_halo_bn<64>(plan.tmA, plan.tmB, u, grid, smem, s);
-        case 128: return launch_halo_bn<128>(plan.tmA, plan.tmB, u, grid, smem, s);
+        case 32: return launch_halo_bn<32>(plan.tmA, plan.tmB, plan.tmB2, u, grid, smem, s);
+        case 64: return launch_halo_bn<64>(plan.tmA, plan.tmB, plan.tmB2, u, grid, smem, s);
+        case 128: return launch_halo_bn<128>(plan.tmA, plan.tmB, plan.tmB2, u, grid, smem, s);
     }
     return SCOUTER_E_UNSUPPORTED;
 }

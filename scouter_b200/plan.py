@@ -60,6 +60,11 @@ def trunc19_remainder(t: torch.Tensor) -> torch.Tensor:
     return t - hi
 
 
+def split_weights_bf16(w: torch.Tensor) -> torch.Tensor:
+    """(2*Cout, kh, kw, Cin/g) bf16: rows [0,Cout) = bf16(W), rows [Cout,2Cout) = bf16(W - trunc19(W))."""
+    return torch.cat([w, trunc19_remainder(w)], dim=0).to(torch.bfloat16).contiguous()
+
+
 class Program:
     """Accumulates ops; keeps every packed tensor alive."""
 
@@ -92,10 +97,8 @@ class Program:
             w = round_tf32(w)        # 1-pass kind::tf32 reads the top 19 bits: make that a rounding, not a truncation
         w2 = None
         if self.math == L.MATH_TC and not stem:
-            # pre-split for the 3xTF32 kernels: [W ; W - trunc19(W)] in one allocation (the kernels address the
-            # remainder rows through the same TMA map)
-            both = torch.cat([w, trunc19_remainder(w)], dim=0).contiguous()
-            w, w2 = both[: w.shape[0]], both[w.shape[0]:]
+            # correction operands for the error-compensated kernels: bf16 [W ; W - trunc19(W)]
+            w2 = split_weights_bf16(w)
         flags = (L.F_RELU if relu else 0) | (L.F_RESIDUAL if residual >= 0 else 0)
         return self.emit(L.OP_STEM_CONV if stem else L.OP_CONV, src, self.buf(), src2=residual,
                          cin=conv.in_channels, cout=conv.out_channels, k=conv.kernel_size[0], stride=conv.stride[0],
