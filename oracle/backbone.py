@@ -58,8 +58,9 @@ def _resnest_block(sd, p, x, dtype, avd: bool, has_down: bool, down_pool: bool):
     return torch.relu(out + res)
 
 
-def resnest26d_features(sd: dict, x: torch.Tensor, prefix: str = "backbone.", dtype=torch.float32):
-    """(B,3,H,W) -> (B,2048,h,w).  ``layers=[2,2,2,2]`` (resnest.py:161-173)."""
+def resnest26d_features(sd: dict, x: torch.Tensor, prefix: str = "backbone.", dtype=torch.float32, layers=(2, 2, 2, 2)):
+    """(B,3,H,W) -> (B,2048,h,w).  ``layers=[2,2,2,2]`` (resnest.py:161-173); resnest14d / resnest50d differ only in
+    the block counts ([1,1,1,1] :147-158, [3,4,6,3] :176-189)."""
     p = prefix
     x = x.to(dtype)
     x = torch.relu(_bn(sd, p + "conv1.1", _conv(sd, p + "conv1.0", x, dtype, 2, 1), dtype))
@@ -67,7 +68,7 @@ def resnest26d_features(sd: dict, x: torch.Tensor, prefix: str = "backbone.", dt
     x = torch.relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1.6", x, dtype, 1, 1), dtype))
     x = F.max_pool2d(x, 3, 2, 1)
     for li in range(1, 5):
-        for bi in range(2):
+        for bi in range(layers[li - 1]):
             first = bi == 0
             x = _resnest_block(sd, f"{p}layer{li}.{bi}", x, dtype,
                                avd=first and li > 1, has_down=first, down_pool=first and li > 1)
@@ -83,7 +84,7 @@ def _basic_block(sd, p, x, dtype, stride: int, has_down: bool):
     return torch.relu(out + res)
 
 
-def resnet18_features(sd: dict, x: torch.Tensor, prefix: str = "backbone.", dtype=torch.float32):
+def resnet18_features(sd: dict, x: torch.Tensor, prefix: str = "backbone.", dtype=torch.float32, layers=(2, 2, 2, 2)):
     """(B,Cin,H,W) -> (B,512,h,w).  The stem is whatever ``conv1.weight`` says: the MNIST swap
     (slot_model.py:23-24) is a 3x3 s2 p1 conv, the stock stem a 7x7 s2 p3 conv."""
     p = prefix
@@ -92,17 +93,19 @@ def resnet18_features(sd: dict, x: torch.Tensor, prefix: str = "backbone.", dtyp
     x = torch.relu(_bn(sd, p + "bn1", _conv(sd, p + "conv1", x, dtype, 2, k // 2), dtype))
     x = F.max_pool2d(x, 3, 2, 1)
     for li in range(1, 5):
-        for bi in range(2):
+        for bi in range(layers[li - 1]):
             first = bi == 0 and li > 1
             x = _basic_block(sd, f"{p}layer{li}.{bi}", x, dtype, 2 if first else 1, first)
     return x
 
 
 def backbone_features(model: str, sd: dict, x: torch.Tensor, dtype=torch.float32):
-    if model == "resnest26d":
-        return resnest26d_features(sd, x, dtype=dtype)
-    if model == "resnet18":
-        return resnet18_features(sd, x, dtype=dtype)
+    resnest = {"resnest14d": (1, 1, 1, 1), "resnest26d": (2, 2, 2, 2), "resnest50d": (3, 4, 6, 3)}
+    resnet = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+    if model in resnest:
+        return resnest26d_features(sd, x, dtype=dtype, layers=resnest[model])
+    if model in resnet:
+        return resnet18_features(sd, x, dtype=dtype, layers=resnet[model])
     raise ValueError(f"oracle has no restatement for backbone {model!r}")
 
 

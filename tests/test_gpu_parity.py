@@ -298,3 +298,36 @@ def test_forward_host_stream_matches_eager(dev):
     assert len(streamed) == len(xs)
     for a, b in zip(eager, streamed):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("model,channel,cin", [("resnest50d", 2048, 3), ("resnest14d", 2048, 3), ("resnet34", 512, 3)])
+def test_other_hot_path_backbones_vs_oracle(dev, model, channel, cin):
+    """The other members of the two backbone families the hot path can select (README 'resnest50d' runs):
+    same blocks, different depths; resnet34 also exercises the stock 7x7 stem and strided 3x3 convs."""
+    from oracle import backbone as ob
+    a = dict(model=model, dataset="ImageNet", num_classes=10, slots_per_class=1, power=2, to_k_layer=3, loss_status=1, channel=channel)
+    m = build(dict(args=a), dev, L.MATH_TC)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    x = synth_images(2, cin, 160, 160, seed=21)
+    o = ob.slot_model_forward(model, sd, x, num_classes=10, slots_per_class=1, loss_status=1, power=2, return_attn=True)
+    with torch.no_grad():
+        out = m(x.to(dev))
+    e = scaled_err(out, o["log_probs"])
+    print(f"{model}: log-prob err {e:.2e}")
+    assert e < 1e-3
+
+
+@pytest.mark.parametrize("b", [1, 3, 7])
+def test_small_and_odd_batches(dev, b):
+    """Edge cases of the batch dimension: a single image (test.py's use), odd counts (2-image-per-CTA head kernel tail)."""
+    from oracle import backbone as ob
+    z, meta = load_golden("cfg2_resnest26d_pos_224")
+    m = build(meta, dev, L.MATH_TC)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    x = synth_images(b, 3, 224, 224, seed=40 + b)
+    a = meta["args"]
+    o = ob.slot_model_forward("resnest26d", sd, x, num_classes=10, slots_per_class=1, loss_status=1, power=2)
+    with torch.no_grad():
+        out = m(x.to(dev))
+    assert out.shape == (b, 10)
+    assert scaled_err(out, o["log_probs"]) < 1e-3
