@@ -259,7 +259,7 @@ def main():
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"tc": "3xtf32 (fp32-equivalent, fp32 accumulate)", "tc_fast": "tf32", "fp32": "f32"}[a.math], "data": "synthetic",
+        "dtype": {"tc": "tf32 + 2 bf16 correction products (error-compensated, fp32-class; fp32 accumulate)", "tc_fast": "tf32", "fp32": "f32"}[a.math], "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * a.batch, "parallelism": f"dp{world}",
                    "math": a.math, "timing": "CUDA events, max over ranks; whole forward = one CUDA-graph replay; inputs "
                    "(154 MB batch + GBs of activations) larger than the 126 MB L2, no explicit flush"},
