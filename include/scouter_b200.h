@@ -228,6 +228,16 @@ int scouter_conv_forward(const scouter_op_t* op, const float* in, const float* r
 int scouter_conv_path(const scouter_op_t* op, int batch, int h, int w, int math);
 
 /* ------------------------------------------------------------------------------------------------
+ * f2  input pipeline boundary (engine.py:25, dataset/transform_func.py:52-67 ToTensor, :87-94 Normalize,
+ *     normalisation constants :101-106): uint8 HWC images -> the fp32 NCHW batch the model consumes.
+ *     out[b,c,y,x] = (float)(((double)img[b,y,x,c] / 255 - mean[c]) / std[c])  -- evaluated in fp64 and rounded once,
+ *     exactly like the reference (its ToTensor yields float64; engine.py casts to float32 on the device).
+ *     `mean`/`std` are HOST arrays of `c` doubles (c <= 4).  4x fewer H2D bytes than shipping fp32 images.
+ * ---------------------------------------------------------------------------------------------- */
+int scouter_preprocess_u8(const uint8_t* img_nhwc, int batch, int h, int w, int c, const double* mean_host,
+                          const double* std_host, float* out_nchw, scouter_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * a1  SlotModel.forward from HOST buffers in one call (sloter/slot_model.py:105-127 as driven by
  *     engine.py:25-30: H2D copy of the batch, forward, read-back of the result).
  *     cudaMemcpyAsync(input_host -> input_dev), scouter_plan_run, scouter_head_forward on the plan's

@@ -133,3 +133,12 @@ def vis_maps_u8(attn: torch.Tensor, *, num_classes: int, slots_per_class: int, v
     a = (a - a.min()) / (a.max() - a.min()) * 255.0
     fs = int(n ** 0.5)
     return a.reshape(a.shape[0], fs, fs).to(torch.float32).numpy().astype("uint8")
+
+
+def preprocess_u8(images_u8_hwc, mean, std):
+    """dataset/transform_func.py:63-66 (ToTensor: image/255 in float64, HWC->CHW) + :87-94 (Normalize) + engine.py:25
+    (cast to float32).  ``images_u8_hwc``: (B,H,W,C) uint8 numpy array."""
+    import numpy as np
+    x = images_u8_hwc.astype(np.float64) / 255
+    x = (x - np.asarray(mean, dtype=np.float64)) / np.asarray(std, dtype=np.float64)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2))).to(torch.float32)

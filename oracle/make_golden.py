@@ -176,6 +176,30 @@ def run_pe_case():
     print("[pe_sine] ok")
 
 
+def run_preprocess_case():
+    """f2: the reference's ToTensor + Normalize (dataset/transform_func.py:52-67,87-106) followed by engine.py:25's cast
+    on seeded uint8 images -> tests/golden/preprocess_u8.npz (PIL Resize excluded: images arrive at the final size)."""
+    refshim.install_shims()
+    import types
+    for mod in ("imgaug", "imgaug.augmenters", "matplotlib", "matplotlib.pyplot"):           # harness-side stub: tools/image_aug.py:1 imports the
+        sys.modules.setdefault(mod, types.ModuleType(mod))   # (uninstalled) augmentation library; 'val' never uses it
+    sys.modules["imgaug"].augmenters = sys.modules["imgaug.augmenters"]
+    from dataset import transform_func as tf
+    out = {}
+    for ds, c in (("ImageNet", 3), ("MNIST", 1)):
+        val = tf.make_transform(argparse.Namespace(dataset=ds, img_size=24, aug=False), "val")
+        normalize = val.transforms[-1]                       # Compose([ToTensor(), Normalize(...)])
+        img = np.random.RandomState(11 + c).randint(0, 256, size=(3, 24, 20, c)).astype(np.uint8)
+        img[0, 0, 0], img[0, 0, 1] = 0, 255
+        ref = torch.stack([normalize(im if c > 1 else im[:, :, 0]) for im in img]).to(torch.float32)
+        mean, std = {"ImageNet": ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]),
+                     "MNIST": ([0.1307], [0.3081])}[ds]
+        assert torch.equal(ref, oh.preprocess_u8(img, mean, std)), ds
+        out[ds + "_u8"], out[ds + "_f32"] = img, ref.numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "preprocess_u8.npz"), **out)
+    print("[preprocess_u8] oracle == reference bit-for-bit")
+
+
 def run_keys_case():
     """state_dict key/shape contract of the reference modules -> tests/golden/state_dict_keys.json."""
     out = {}
@@ -202,6 +226,8 @@ def main():
         run_pe_case()
     if not a.only or a.only == "keys":
         run_keys_case()
+    if not a.only or a.only == "preprocess":
+        run_preprocess_case()
     for name, case in HEAD_CASES.items():
         if not a.only or a.only in name:
             run_head_case(name, case, a.check)

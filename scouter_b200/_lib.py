@@ -103,6 +103,7 @@ SIGNATURES = {
     "scouter_plan_buffer_offset": (C.c_size_t, [C.c_void_p, C.c_int]),
     "scouter_plan_run": (C.c_int, [C.c_void_p, _fp, _fp, C.c_size_t, _fp]),
     "scouter_plan_launch_count": (C.c_int, [C.c_void_p]),
+    "scouter_preprocess_u8": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _fp, _fp]),
     "scouter_forward_host": (C.c_int, [C.POINTER(ForwardHostArgs)]),
 }
 
@@ -113,9 +114,9 @@ class ScouterError(RuntimeError):
     pass
 
 
-def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
+def nvcc_command(out_path: str = LIB_PATH, defines: tuple = ()) -> list[str]:
     return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(os.path.dirname(_HERE), "include"),
+            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(os.path.dirname(_HERE), "include"), *defines,
             *[os.path.join(CSRC, s) for s in SOURCES], "-o", out_path]
 
 

@@ -444,3 +444,14 @@ extern "C" int scouter_conv_forward(const scouter_op_t* op, const float* in, con
     }
     return launch_conv_simt(a, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------------
+// f2: input pipeline boundary
+// ------------------------------------------------------------------------------------------------
+extern "C" int scouter_preprocess_u8(const uint8_t* img_nhwc, int batch, int h, int w, int c, const double* mean_host,
+                                     const double* std_host, float* out_nchw, scouter_stream_t stream) {
+    SC_CHECK_ARG(img_nhwc && out_nchw && mean_host && std_host && batch > 0 && h > 0 && w > 0, SCOUTER_E_INVALID,
+                 "preprocess_u8: bad arguments");
+    for (int i = 0; i < c && i < 4; ++i) SC_CHECK_ARG(std_host[i] != 0.0, SCOUTER_E_INVALID, "preprocess_u8: std[%d] is 0", i);
+    return launch_preprocess_u8(img_nhwc, batch, h, w, c, mean_host, std_host, out_nchw, (cudaStream_t)stream);
+}

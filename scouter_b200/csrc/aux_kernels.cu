@@ -218,6 +218,21 @@ __global__ void __launch_bounds__(256) splat_apply_kernel(const float* __restric
     }
 }
 
+// f2: uint8 HWC -> normalised fp32 NCHW, fp64 arithmetic with a single rounding (reference: float64 ToTensor/Normalize,
+// then .to(float32)).  One thread = one pixel (all channels), coalesced planar stores.
+struct NormConst { double mean[4], inv255, std[4]; };
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ img, float* __restrict__ out,
+                                                            long long npix_per_img, int C, NormConst k) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (p >= npix_per_img) return;
+    const uint8_t* src = img + ((long long)b * npix_per_img + p) * C;
+    for (int c = 0; c < C; ++c) {
+        const double v = ((double)src[c] / 255.0 - k.mean[c]) / k.std[c];
+        out[((long long)b * C + c) * npix_per_img + p] = (float)v;
+    }
+}
+
 int pixel_grid(int B, int Ho, int Wo, int C, int rows, dim3& grid) {
     SC_CHECK_ARG(C % 4 == 0, SCOUTER_E_UNSUPPORTED, "C = %d not a multiple of 4", C);
     SC_CHECK_ARG(B <= 65535 && Ho <= 65535, SCOUTER_E_UNSUPPORTED, "batch %d / height %d exceed the grid limits", B, Ho);
@@ -280,6 +295,18 @@ int launch_splat_apply(const float* in, const float* logit, float* out, int B, i
         if (int e = pixel_grid(B, Ho, Wo, C, 4, grid)) return e;
         splat_apply_kernel<4><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, avd, round_out);
     }
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_preprocess_u8(const uint8_t* img, int B, int H, int W, int C, const double* mean, const double* stdv, float* out,
+                         cudaStream_t s) {
+    SC_CHECK_ARG(C >= 1 && C <= 4 && B <= 65535, SCOUTER_E_UNSUPPORTED, "preprocess_u8: channels=%d batch=%d", C, B);
+    NormConst k;
+    for (int c = 0; c < 4; ++c) { k.mean[c] = c < C ? mean[c] : 0.0; k.std[c] = c < C ? stdv[c] : 1.0; }
+    k.inv255 = 1.0 / 255.0;
+    const long long npix = (long long)H * W;
+    preprocess_u8_kernel<<<dim3((unsigned)((npix + 255) / 256), B), 256, 0, s>>>(img, out, npix, C, k);
     SC_LAUNCH_CHECK();
     return 0;
 }

@@ -101,6 +101,8 @@ int launch_splat_gap(const float* in, float* part, float* gap, int B, int HW, in
 int launch_splat_apply(const float* in, const float* logit, float* out, int B, int H, int W, int C, int Ho, int Wo,
                        int avd, int round_out, cudaStream_t s);
 int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s);
+int launch_preprocess_u8(const uint8_t* img, int B, int H, int W, int C, const double* mean, const double* stdv, float* out,
+                         cudaStream_t s);
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int HW, int C, cudaStream_t s);
 int launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cudaStream_t s);
 

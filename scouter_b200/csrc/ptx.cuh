@@ -36,7 +36,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// The hot loops keep 32-bit shared-window addresses of their barriers (one cvta at kernel start, not one per use).
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
@@ -45,21 +46,41 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (and fail the launch), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_a(smem_u32(bar), parity); }
+static __device__ __noinline__ void mbar_timeout(uint32_t parity) {
+    printf("scouter_b200: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+    __trap();
+}
+// Bounded wait: a protocol bug must trap (and fail the launch), never hang the GPU.  The single-thread issue loops
+// run at ~4.5 clk per instruction, so the fast path is one try_wait + branch and the diagnostics live out of line.
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_a(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("scouter_b200: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-            __trap();
-        }
+    while (!mbar_try_wait_a(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) mbar_timeout(parity);
     }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// ---- role-level stall accounting (only in the -DSCOUTER_PROF build made by scripts/prof_roles.py) -------
+#ifdef SCOUTER_PROF
+#define PROF_DECL(n) long long prof_##n = 0
+#define PROF_T(n, stmt) do { const long long _t = clock64(); stmt; prof_##n += clock64() - _t; } while (0)
+#define PROF_BEGIN(n) const long long prof_begin_##n = clock64()
+#define PROF_END(n) prof_##n = clock64() - prof_begin_##n
+#define PROF_STORE(buf, slot, n) (buf)[blockIdx.x * 32 + (slot)] = (unsigned long long)prof_##n
+#else
+#define PROF_DECL(n)
+#define PROF_T(n, stmt) stmt
+#define PROF_BEGIN(n)
+#define PROF_END(n)
+#define PROF_STORE(buf, slot, n)
+#endif
 
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
@@ -106,9 +127,10 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // tcgen05.commit: arrive (count 1) on an mbarrier when all previously issued MMAs of this thread are done.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) { umma_commit_a(smem_u32(bar)); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, tf32 operands, fp32 accumulate.  Issued by ONE thread.
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -173,6 +195,13 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
     return d;
 }
 
+// Descriptors split into a constant high word and a low word {start address >> 4 | LBO}: the issue loops advance the
+// low word with 32-bit adds (stage += bytes/16, k sub-step += 2, halo tap += rows*8) instead of rebuilding 64 bits.
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_make(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
 // Operand split of one 8-float group for the error-compensated product: x = trunc19(x) + r.  Returns bf16x8 of x
 // (in `xb`) and of r (in `rb`), each packed as 4 x bf16x2 -- the two correction products use 8-bit-mantissa operands,
 // which costs 2^-9 on terms that are themselves 2^-11 of the main product.
@@ -187,21 +216,57 @@ __device__ __forceinline__ void split8_bf16(const float4& a, const float4& b, ui
     rb = make_uint4(pack(rem(a.x), rem(a.y)), pack(rem(a.z), rem(a.w)), pack(rem(b.x), rem(b.y)), pack(rem(b.z), rem(b.w)));
 }
 
-// Converts `rows` rows of a SWIZZLE_128B fp32 tile (128-byte rows) into two SWIZZLE_64B bf16 tiles (64-byte rows):
-// bf16(x) and bf16(x - trunc19(x)).  Work item = (row, 8-float group); `tid`/`nthreads` stride over the items.
-__device__ __forceinline__ void split_tile_bf16(const uint8_t* src, uint8_t* dst_x, uint8_t* dst_r, int rows, int tid, int nthreads) {
-    for (int it = tid; it < rows * 4; it += nthreads) {
-        const int row = it >> 2, p = it & 3;
-        const int s = row & 7;
-        const uint8_t* rp = src + row * 128;
-        const float4 a = *reinterpret_cast<const float4*>(rp + (((2 * p) ^ s) << 4));
-        const float4 b = *reinterpret_cast<const float4*>(rp + (((2 * p + 1) ^ s) << 4));
-        uint4 xb, rb;
-        split8_bf16(a, b, xb, rb);
-        const int doff = row * 64 + ((p ^ ((row >> 1) & 3)) << 4);
-        *reinterpret_cast<uint4*>(dst_x + doff) = xb;
-        *reinterpret_cast<uint4*>(dst_r + doff) = rb;
+// Converts rows of a SWIZZLE_128B fp32 tile (128-byte rows) into two SWIZZLE_64B bf16 tiles (64-byte rows): bf16(x) and
+// bf16(x - trunc19(x)).  128 threads; thread `tid` owns the 8-float group p = tid % 4 of rows tid/4 + 32*i, so its
+// swizzled source / destination offsets are the same for every i up to a multiple of 4096 / 2048 bytes (row % 8 and
+// (row / 2) % 4 do not change when the row advances by 32): three offsets per thread, computed once per kernel.
+struct SplitLane {
+    uint32_t src0, src1, dst;
+    int row;
+};
+__device__ __forceinline__ SplitLane split_lane(int tid) {
+    const int row = tid >> 2, p = tid & 3, s = row & 7;
+    SplitLane l;
+    l.src0 = row * 128 + (((2 * p) ^ s) << 4);
+    l.src1 = row * 128 + (((2 * p + 1) ^ s) << 4);
+    l.dst = row * 64 + ((p ^ ((row >> 1) & 3)) << 4);
+    l.row = row;
+    return l;
+}
+// U groups of 32 rows starting at row group `g0`; all loads are issued before the first conversion so that their
+// shared-memory latency overlaps.  Rows >= rows are skipped (halo patches are not a multiple of 32 rows).
+template <int U, bool GUARD>
+__device__ __forceinline__ void split_groups(const uint8_t* src, uint8_t* dst_x, uint8_t* dst_r, const SplitLane& l, int g0, int rows) {
+    float4 a[U], b[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        if (!GUARD || l.row + 32 * (g0 + i) < rows) {
+            a[i] = *reinterpret_cast<const float4*>(src + l.src0 + 4096 * (g0 + i));
+            b[i] = *reinterpret_cast<const float4*>(src + l.src1 + 4096 * (g0 + i));
+        }
     }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        if (!GUARD || l.row + 32 * (g0 + i) < rows) {
+            uint4 xb, rb;
+            split8_bf16(a[i], b[i], xb, rb);
+            *reinterpret_cast<uint4*>(dst_x + l.dst + 2048 * (g0 + i)) = xb;
+            *reinterpret_cast<uint4*>(dst_r + l.dst + 2048 * (g0 + i)) = rb;
+        }
+    }
+}
+// Whole tile of ROWS rows (a multiple of 32).
+template <int ROWS>
+__device__ __forceinline__ void split_tile_bf16(const uint8_t* src, uint8_t* dst_x, uint8_t* dst_r, const SplitLane& l) {
+    static_assert(ROWS % 32 == 0, "split_tile_bf16: whole 32-row groups");
+    split_groups<ROWS / 32, false>(src, dst_x, dst_r, l, 0, ROWS);
+}
+// Any number of rows (halo patches).
+__device__ __forceinline__ void split_rows_bf16(const uint8_t* src, uint8_t* dst_x, uint8_t* dst_r, const SplitLane& l, int rows) {
+    const int groups = (rows + 31) >> 5;
+    int g = 0;
+    for (; g + 4 <= groups; g += 4) split_groups<4, true>(src, dst_x, dst_r, l, g, rows);
+    for (; g < groups; ++g) split_groups<1, true>(src, dst_x, dst_r, l, g, rows);
 }
 
 // 32 lanes x 32 columns of fp32 from TMEM: thread i of the warp gets lane (base_lane + i), columns [col, col+32).

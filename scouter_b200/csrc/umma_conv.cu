@@ -72,6 +72,10 @@ struct Cfg {
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 1024 /*barriers*/ + OUT_BYTES;
 };
 
+#ifdef SCOUTER_PROF
+__device__ unsigned long long g_prof_flat[256 * 32];
+#endif
+
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(Cfg<BN, SPLIT>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -122,6 +126,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
+            PROF_DECL(empty); PROF_DECL(prod); PROF_BEGIN(prod);
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const int sp = t % p.ksplit;
                 const int tt = t / p.ksplit;
@@ -135,7 +140,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     b0 = (mt / (p.tw * p.th)) * p.Nb;
                 }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    PROF_T(empty, mbar_wait(&empty[stage], phase ^ 1));
                     uint8_t* sa = smem + stage * C::STAGE;
                     uint8_t* sb = sa + C::A_BYTES;
                     mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + C::B_BYTES + (SPLIT && p.rem_rows ? C::B_BYTES : 0)));
@@ -156,49 +161,68 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            PROF_END(prod);
+            PROF_STORE(g_prof_flat, 0, prod); PROF_STORE(g_prof_flat, 1, empty);
         }
     } else if (warp == 1) {
         if (elect_one()) {
             // ===== MMA issuer =====
+            // One thread, ~4.5 clk per dependent instruction (profiles/r01_role_stalls_*.txt): descriptors are a constant
+            // high word plus a low word advanced by one 32-bit add per stage, barriers are 32-bit shared addresses.
             constexpr uint32_t idesc = idesc_tf32(128, BN);
-            int stage = 0;
-            uint32_t phase = 0;
+            constexpr uint32_t SSTEP = C::STAGE >> 4;
+            const uint32_t s_lo0 = desc_lo(smem_u32(smem));
+            const uint32_t ready_a = smem_u32(SPLIT ? split_done : full), empty_a = smem_u32(empty), cfull_a = smem_u32(cfull),
+                           cempty_a = smem_u32(cempty);
+            const int kblocks = p.kblocks, chunk = p.chunk;
+            int stage = 0, in_chunk = 0;
+            uint32_t phase = 0, s_lo = s_lo0;
             uint32_t cc = 0;  // running chunk counter
+            PROF_DECL(cempty); PROF_DECL(full); PROF_DECL(iss); PROF_DECL(nkb); PROF_BEGIN(iss);
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.chunk, ++cc) {
-                    const int buf = cc & 1;
-                    mbar_wait(&cempty[buf], ((cc >> 1) & 1) ^ 1);
+#ifdef SCOUTER_PROF
+                prof_nkb += p.kblocks;
+#endif
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const uint32_t buf = cc & 1;
+                    if (in_chunk == 0) PROF_T(cempty, mbar_wait_a(cempty_a + 8 * buf, ((cc >> 1) & 1) ^ 1));
+                    PROF_T(full, mbar_wait_a(ready_a + 8 * stage, phase));
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * BN;
-                    const int kb1 = min(kb0 + p.chunk, p.kblocks);
-                    for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(SPLIT ? &split_done[stage] : &full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * C::STAGE);
-                        const uint64_t da = smem_desc_sw128(sa);
-                        const uint64_t db = smem_desc_sw128(sa + C::A_BYTES);
-                        const uint32_t first = kb != kb0;
-                        // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
-                        if constexpr (SPLIT) {
-                            constexpr uint32_t idesc_b = idesc_bf16(128, BN);
-                            const uint64_t dab = smem_desc_sw64(sa + C::OFF_AB), darb = smem_desc_sw64(sa + C::OFF_ARB);
-                            const uint64_t dwb = smem_desc_sw64(sa + C::OFF_WB), dwrb = smem_desc_sw64(sa + C::OFF_WRB);
+                    const uint32_t acc = in_chunk != 0;
+                    // UMMA_K = 8 tf32 / 16 bf16 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
+                    if constexpr (SPLIT) {
+                        constexpr uint32_t idesc_b = idesc_bf16(128, BN);
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, dab + 2 * k, dwrb + 2 * k, idesc_b, first | k);  // A * W_r
+                        for (uint32_t k = 0; k < 2; ++k)   // A * W_r
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + (C::OFF_AB >> 4) + 2 * k),
+                                      desc_make(DESC_HI_SW64, s_lo + (C::OFF_WRB >> 4) + 2 * k), idesc_b, acc | k);
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, darb + 2 * k, dwb + 2 * k, idesc_b, 1);          // A_r * W
+                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + (C::OFF_ARB >> 4) + 2 * k),
+                                      desc_make(DESC_HI_SW64, s_lo + (C::OFF_WB >> 4) + 2 * k), idesc_b, 1);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);               // A_t * W_t
-                        } else {
+                        for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
+                            umma_tf32(d_tmem, desc_make(DESC_HI_SW128, s_lo + 2 * k),
+                                      desc_make(DESC_HI_SW128, s_lo + (C::A_BYTES >> 4) + 2 * k), idesc, 1);
+                    } else {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, first | k);
-                        }
-                        umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                        for (uint32_t k = 0; k < 4; ++k)
+                            umma_tf32(d_tmem, desc_make(DESC_HI_SW128, s_lo + 2 * k),
+                                      desc_make(DESC_HI_SW128, s_lo + (C::A_BYTES >> 4) + 2 * k), idesc, acc | k);
                     }
-                    umma_commit(&cfull[buf]);
+                    umma_commit_a(empty_a + 8 * stage);  // frees the smem slot when these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; s_lo = s_lo0; } else { s_lo += SSTEP; }
+                    if (++in_chunk == chunk || kb + 1 == kblocks) {
+                        umma_commit_a(cfull_a + 8 * buf);
+                        ++cc;
+                        in_chunk = 0;
+                    }
                 }
             }
+            PROF_END(iss);
+            PROF_STORE(g_prof_flat, 4, iss); PROF_STORE(g_prof_flat, 6, cempty); PROF_STORE(g_prof_flat, 7, full);
+            PROF_STORE(g_prof_flat, 8, nkb);
         }
     } else if ((warp >= 4 && warp < 8) || (C::EPI_GROUPS == 2 && warp >= 12)) {
         // ===== epilogue: thread = one output row (32 TMEM lanes per warp) x NC columns =====
@@ -207,6 +231,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int row = q * 32 + lane;
         const int col0 = grp * C::NC;
         uint32_t cc = 0;
+        PROF_DECL(cfull); PROF_DECL(store); PROF_DECL(merge); PROF_DECL(epi); PROF_BEGIN(epi);
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int sp = t % p.ksplit;
             const int tt = t / p.ksplit;
@@ -311,8 +336,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 rp = nullptr;   // already folded in
                 for (int ch = 0; ch < nchunks; ++ch, ++cc) {
                     const int buf = cc & 1;
-                    mbar_wait(&cfull[buf], (cc >> 1) & 1);
+                    PROF_T(cfull, mbar_wait(&cfull[buf], (cc >> 1) & 1));
                     tc_fence_after();
+#ifdef SCOUTER_PROF
+                    const long long _tm = clock64();
+#endif
 #pragma unroll
                     for (int c = 0; c < C::NC / 32; ++c) {
                         uint32_t r[32];
@@ -323,10 +351,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     tc_fence_before();
                     mbar_arrive(&cempty[buf]);
+#ifdef SCOUTER_PROF
+                    prof_merge += clock64() - _tm;
+#endif
                 }
+#ifdef SCOUTER_PROF
+                const long long _ts = clock64();
+#endif
                 if (p.tma_store) {
 #pragma unroll
                     for (int c = 0; c < C::NC / 16; ++c) emit_tma16(&acc[c * 16], c);
+#ifdef SCOUTER_PROF
+                    prof_store += clock64() - _ts;
+#endif
                 } else {
 #pragma unroll
                     for (int c = 0; c < C::NC / 32; ++c) {
@@ -361,22 +398,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
         if (p.tma_store && row == 0) bulk_wait<0>();   // all bulk stores of this group have completed
+        PROF_END(epi);
+        if (threadIdx.x == 128) {
+            PROF_STORE(g_prof_flat, 10, epi); PROF_STORE(g_prof_flat, 11, cfull); PROF_STORE(g_prof_flat, 12, store);
+            PROF_STORE(g_prof_flat, 13, merge);
+        }
     } else if (SPLIT && warp >= 8 && warp < 12) {
         // ===== operand splitters: bf16(x) and bf16(x - trunc19(x)) tiles of the activation (and, unless pre-split, weight) tile =====
         const int tid = threadIdx.x - 256;  // 0..127
+        const SplitLane sl = split_lane(tid);
         int stage = 0;
         uint32_t phase = 0;
+        PROF_DECL(pfull); PROF_DECL(spl); PROF_BEGIN(spl);
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             for (int kb = 0; kb < p.kblocks; ++kb) {
-                mbar_wait(&full[stage], phase);
+                PROF_T(pfull, mbar_wait(&full[stage], phase));
                 uint8_t* st = smem + stage * C::STAGE;
-                split_tile_bf16(st, st + C::OFF_AB, st + C::OFF_ARB, 128, tid, 128);
-                if (!p.rem_rows) split_tile_bf16(st + C::A_BYTES, st + C::OFF_WB, st + C::OFF_WRB, BN, tid, 128);
+                split_tile_bf16<128>(st, st + C::OFF_AB, st + C::OFF_ARB, sl);
+                if (!p.rem_rows) split_tile_bf16<BN>(st + C::A_BYTES, st + C::OFF_WB, st + C::OFF_WRB, sl);
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&split_done[stage]);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        PROF_END(spl);
+        if (tid == 0) { PROF_STORE(g_prof_flat, 14, spl); PROF_STORE(g_prof_flat, 15, pfull); }
     }
     tc_fence_before();
     __syncthreads();
@@ -571,3 +617,9 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
 }
 
 }  // namespace scouter
+
+#ifdef SCOUTER_PROF
+extern "C" int scouter_prof_read_flat(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, scouter::g_prof_flat, sizeof(unsigned long long) * n);
+}
+#endif

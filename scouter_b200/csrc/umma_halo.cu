@@ -29,6 +29,10 @@ using namespace ptx;
 
 namespace {
 
+#ifdef SCOUTER_PROF
+__device__ unsigned long long g_prof_halo[256 * 32];
+#endif
+
 struct HaloArgs {
     const float* bias;
     const float* res;
@@ -117,10 +121,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ===== TMA producer: patch job j+1 is issued before the nine weight tiles of job j =====
             int ps = 0, bs = 0;
             uint32_t pphase = 0, bphase = 0;
+            PROF_DECL(pempty); PROF_DECL(bempty); PROF_DECL(prod); PROF_BEGIN(prod);
             auto issue_patch = [&](int t, int cb) {
                 int nt, g, w0, h0, b;
                 tile_coords(t, nt, g, w0, h0, b);
-                mbar_wait(&pempty[ps], pphase ^ 1);
+                PROF_T(pempty, mbar_wait(&pempty[ps], pphase ^ 1));
                 mbar_arrive_expect_tx(&pfull[ps], (uint32_t)p.patch_bytes);
                 tma_load_4d(patch0 + ps * 2 * p.patch_alloc, &tmA, &pfull[ps], g * p.cin_g + cb * 32, w0 - 1, h0 - 1, b);
                 if (++ps == p.pst) { ps = 0; pphase ^= 1; }
@@ -139,7 +144,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int cb = 0; cb < p.cblocks; ++cb) {
                     for (int tap = 0; tap < 9; ++tap) {
                         if (tap == 3) issue_next_patch();  // the issuer is inside this job: the oldest patch stage is (about to be) free
-                        mbar_wait(&bempty[bs], bphase ^ 1);
+                        PROF_T(bempty, mbar_wait(&bempty[bs], bphase ^ 1));
                         uint8_t* sb = bt0 + bs * C::B_STAGE;
                         mbar_arrive_expect_tx(&bfull[bs], (uint32_t)C::B_STAGE);
                         const int kcol = tap * p.cin_g + cb * 32;
@@ -151,57 +156,70 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
             }
+            PROF_END(prod);
+            PROF_STORE(g_prof_halo, 0, prod); PROF_STORE(g_prof_halo, 1, pempty); PROF_STORE(g_prof_halo, 2, bempty);
         }
     } else if (warp == 1) {
         if (elect_one()) {
             // ===== MMA issuer =====
-            constexpr uint32_t idesc = idesc_tf32(128, BN);
-            int ps = 0, bs = 0;
+            // One thread, ~4.5 clk per dependent instruction: everything that can be hoisted is.  Descriptors are a
+            // constant high word plus a low word advanced by 32-bit adds; barrier addresses are 32-bit shared-window
+            // addresses; the nine taps are unrolled so that (r, s) and the k sub-steps are immediates.
+            constexpr uint32_t idesc = idesc_tf32(128, BN), idesc_b = idesc_bf16(128, BN);
+            constexpr uint32_t BSTEP = C::B_STAGE >> 4, WB_OFF = C::B_BYTES >> 4, WRB_OFF = (C::B_BYTES + C::B_BYTES / 2) >> 4;
+            const uint32_t pa_lo0 = desc_lo(smem_u32(patch0)), b_lo0 = desc_lo(smem_u32(bt0));
+            const uint32_t pstep = (uint32_t)(2 * p.patch_alloc) >> 4;
+            const uint32_t ab_off = (uint32_t)p.patch_alloc >> 4, arb_off = (uint32_t)(p.patch_alloc + p.patch_alloc / 2) >> 4;
+            const uint32_t pw8 = (uint32_t)p.PW * 8u, pw4 = (uint32_t)p.PW * 4u;   // one patch line in 16-byte units (fp32 / bf16 rows)
+            const uint32_t pready_a = smem_u32(pready), pempty_a = smem_u32(pempty), bfull_a = smem_u32(bfull),
+                           bempty_a = smem_u32(bempty), cfull_a = smem_u32(cfull), cempty_a = smem_u32(cempty);
+            const int last_cb = p.cblocks - 1, chunk = p.chunk, pst = p.pst, bst = p.bst;
+            int ps = 0, bs = 0, in_chunk = 0;
             uint32_t pphase = 0, bphase = 0, cc = 0;
+            uint32_t pa_lo = pa_lo0, b_lo = b_lo0;
+            PROF_DECL(pready); PROF_DECL(cempty); PROF_DECL(bfull); PROF_DECL(iss); PROF_DECL(ntaps); PROF_BEGIN(iss);
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                int step = 0;
-                for (int cb = 0; cb < p.cblocks; ++cb) {
-                    mbar_wait(&pready[ps], pphase);
-                    tc_fence_after();
-                    const uint32_t pa = smem_u32(patch0 + ps * 2 * p.patch_alloc);
-                    for (int tap = 0; tap < 9; ++tap, ++step) {
-                        const int buf = cc & 1;
-                        const bool chunk_start = step % p.chunk == 0;
-                        if (chunk_start) {
-                            mbar_wait(&cempty[buf], ((cc >> 1) & 1) ^ 1);
-                            tc_fence_after();
-                        }
-                        mbar_wait(&bfull[bs], bphase);
+                for (int cb = 0; cb <= last_cb; ++cb) {
+                    PROF_T(pready, mbar_wait_a(pready_a + 8 * ps, pphase));
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t buf = cc & 1;
+                        if (in_chunk == 0) PROF_T(cempty, mbar_wait_a(cempty_a + 8 * buf, ((cc >> 1) & 1) ^ 1));
+                        PROF_T(bfull, mbar_wait_a(bfull_a + 8 * bs, bphase));
                         tc_fence_after();
-                        const int r = tap / 3, s = tap - 3 * r;
-                        const uint32_t arow = (uint32_t)(r * p.PW + s);
-                        const uint64_t da = smem_desc_sw128(pa + arow * 128u);
-                        const uint64_t dab = smem_desc_sw64(pa + p.patch_alloc + arow * 64u);
-                        const uint64_t darb = smem_desc_sw64(pa + p.patch_alloc + p.patch_alloc / 2 + arow * 64u);
-                        const uint32_t sb = smem_u32(bt0 + bs * C::B_STAGE);
-                        const uint64_t db = smem_desc_sw128(sb);
-                        const uint64_t dwb = smem_desc_sw64(sb + C::B_BYTES);
-                        const uint64_t dwrb = smem_desc_sw64(sb + C::B_BYTES + C::B_BYTES / 2);
+                        const uint32_t r = tap / 3, sx = tap % 3;              // immediates after unrolling
+                        const uint32_t a32 = pa_lo + r * pw8 + sx * 8u;        // fp32 patch, tap row (r*PW + s) * 128 B
+                        const uint32_t a16 = pa_lo + ab_off + r * pw4 + sx * 4u;
+                        const uint32_t ar16 = pa_lo + arb_off + r * pw4 + sx * 4u;
                         const uint32_t d_tmem = tmem_base + buf * BN;
-                        const uint32_t first = chunk_start ? 0u : 1u;
-                        constexpr uint32_t idesc_b = idesc_bf16(128, BN);
+                        const uint32_t acc = in_chunk != 0;
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, dab + 2 * k, dwrb + 2 * k, idesc_b, first | k);  // A * W_r
+                        for (uint32_t k = 0; k < 2; ++k)   // A * W_r
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, a16 + 2 * k), desc_make(DESC_HI_SW64, b_lo + WRB_OFF + 2 * k), idesc_b, acc | k);
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, darb + 2 * k, dwb + 2 * k, idesc_b, 1);          // A_r * W
+                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ar16 + 2 * k), desc_make(DESC_HI_SW64, b_lo + WB_OFF + 2 * k), idesc_b, 1);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, 1);               // A_t * W_t
-                        umma_commit(&bempty[bs]);
-                        if (++bs == p.bst) { bs = 0; bphase ^= 1; }
-                        if ((step + 1) % p.chunk == 0 || step + 1 == ksteps) {
-                            umma_commit(&cfull[buf]);
+                        for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
+                            umma_tf32(d_tmem, desc_make(DESC_HI_SW128, a32 + 2 * k), desc_make(DESC_HI_SW128, b_lo + 2 * k), idesc, 1);
+                        umma_commit_a(bempty_a + 8 * bs);
+                        if (++bs == bst) { bs = 0; bphase ^= 1; b_lo = b_lo0; } else { b_lo += BSTEP; }
+                        if (++in_chunk == chunk || (tap == 8 && cb == last_cb)) {
+                            umma_commit_a(cfull_a + 8 * buf);
                             ++cc;
+                            in_chunk = 0;
                         }
                     }
-                    umma_commit(&pempty[ps]);
-                    if (++ps == p.pst) { ps = 0; pphase ^= 1; }
+                    umma_commit_a(pempty_a + 8 * ps);
+                    if (++ps == pst) { ps = 0; pphase ^= 1; pa_lo = pa_lo0; } else { pa_lo += pstep; }
+#ifdef SCOUTER_PROF
+                    prof_ntaps += 9;
+#endif
                 }
             }
+            PROF_END(iss);
+            PROF_STORE(g_prof_halo, 4, iss); PROF_STORE(g_prof_halo, 5, pready); PROF_STORE(g_prof_halo, 6, cempty);
+            PROF_STORE(g_prof_halo, 7, bfull); PROF_STORE(g_prof_halo, 8, ntaps);
         }
     } else if ((warp >= 4 && warp < 8) || (C::EPI_GROUPS == 2 && warp >= 12)) {
         // ===== epilogue: thread = one virtual output row (hb*PW + wb') x NC columns =====
@@ -211,6 +229,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int col0 = grp * C::NC;
         const int hb = row / p.PW, wb = row - hb * p.PW;
         uint32_t cc = 0;
+        PROF_DECL(cfull); PROF_DECL(store); PROF_DECL(epi); PROF_BEGIN(epi);
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             int nt, g, w0, h0, b;
             tile_coords(t, nt, g, w0, h0, b);
@@ -223,7 +242,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < C::NC; ++j) acc[j] = 0.f;
             for (int ch = 0; ch < nchunks; ++ch, ++cc) {
                 const int buf = cc & 1;
-                mbar_wait(&cfull[buf], (cc >> 1) & 1);
+                PROF_T(cfull, mbar_wait(&cfull[buf], (cc >> 1) & 1));
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < C::NC / 32; ++c) {
@@ -236,6 +255,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(&cempty[buf]);
             }
+#ifdef SCOUTER_PROF
+            const long long _ts = clock64();
+#endif
             if (valid) {
                 float* op = p.out + orow * p.Cout + ch0;
                 const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
@@ -254,23 +276,32 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     *reinterpret_cast<float4*>(op + 4 * j) = v;
                 }
             }
+#ifdef SCOUTER_PROF
+            prof_store += clock64() - _ts;
+#endif
         }
+        PROF_END(epi);
+        if (threadIdx.x == 128) { PROF_STORE(g_prof_halo, 10, epi); PROF_STORE(g_prof_halo, 11, cfull); PROF_STORE(g_prof_halo, 12, store); }
     } else if (warp >= 8 && warp < 12) {
         // ===== splitters: bf16 patches of A and of A - trunc19(A), once per patch =====
         const int tid = threadIdx.x - 256;
         const int prows = p.patch_bytes / 128;
+        const SplitLane sl = split_lane(tid);
         int ps = 0;
         uint32_t pphase = 0;
+        PROF_DECL(pfull); PROF_DECL(spl); PROF_BEGIN(spl);
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             for (int cb = 0; cb < p.cblocks; ++cb) {
-                mbar_wait(&pfull[ps], pphase);
+                PROF_T(pfull, mbar_wait(&pfull[ps], pphase));
                 uint8_t* raw = patch0 + ps * 2 * p.patch_alloc;
-                split_tile_bf16(raw, raw + p.patch_alloc, raw + p.patch_alloc + p.patch_alloc / 2, prows, tid, 128);
+                split_rows_bf16(raw, raw + p.patch_alloc, raw + p.patch_alloc + p.patch_alloc / 2, sl, prows);
                 fence_proxy_async();
                 mbar_arrive(&pready[ps]);
                 if (++ps == p.pst) { ps = 0; pphase ^= 1; }
             }
         }
+        PROF_END(spl);
+        if (tid == 0) { PROF_STORE(g_prof_halo, 14, spl); PROF_STORE(g_prof_halo, 15, pfull); }
     }
     tc_fence_before();
     __syncthreads();
@@ -425,3 +456,10 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
 }
 
 }  // namespace scouter
+
+#ifdef SCOUTER_PROF
+// per-CTA role counters of the last halo launch: 32 slots per CTA (see scripts/prof_roles.py for the slot names)
+extern "C" int scouter_prof_read_halo(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, scouter::g_prof_halo, sizeof(unsigned long long) * n);
+}
+#endif

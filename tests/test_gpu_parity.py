@@ -331,3 +331,39 @@ def test_small_and_odd_batches(dev, b):
         out = m(x.to(dev))
     assert out.shape == (b, 10)
     assert scaled_err(out, o["log_probs"]) < 1e-3
+
+
+@pytest.mark.parametrize("dataset,c", [("ImageNet", 3), ("MNIST", 1)])
+def test_preprocess_u8_bit_exact(dev, dataset, c):
+    """f2: uint8 HWC -> normalised fp32 NCHW on the device is bit-identical to the reference's float64 pipeline + cast."""
+    r = np.random.RandomState(3)
+    img = r.randint(0, 256, size=(5, 37, 41, c)).astype(np.uint8)
+    img[0, 0, 0, :] = 0
+    img[0, 0, 1, :] = 255
+    mean, std = sb.SlotModel.NORMALIZE[dataset]
+    ref = oh.preprocess_u8(img, mean, std)
+    got = sb.SlotModel.preprocess_u8(torch.from_numpy(img).to(dev), dataset).cpu()
+    assert got.shape == ref.shape and torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("dataset", ["ImageNet", "MNIST"])
+def test_preprocess_u8_reference_golden(dev, dataset):
+    z = np.load("tests/golden/preprocess_u8.npz")
+    got = sb.SlotModel.preprocess_u8(torch.from_numpy(z[dataset + "_u8"]).to(dev), dataset).cpu().numpy()
+    assert np.array_equal(got, z[dataset + "_f32"])
+
+
+def test_forward_host_stream_u8_matches_fp32_path(dev):
+    """f2 + a1: streaming uint8 images through the on-device preprocessing gives exactly the forward of the oracle-
+    preprocessed fp32 batch."""
+    z, meta = load_golden("cfg3_resnest26d_neg_224")
+    m = build(meta, dev, L.MATH_TC)
+    m.keep_attn = False
+    r = np.random.RandomState(9)
+    imgs = [torch.from_numpy(r.randint(0, 256, size=(3, 96, 96, 3)).astype(np.uint8)).pin_memory() for _ in range(3)]
+    got = list(m.forward_host_stream(imgs, device=dev, dataset="ImageNet"))
+    mean, std = sb.SlotModel.NORMALIZE["ImageNet"]
+    for g, im in zip(got, imgs):
+        with torch.no_grad():
+            want = m(oh.preprocess_u8(im.numpy(), mean, std).to(dev)).cpu()
+        assert torch.equal(g, want)

@@ -57,3 +57,12 @@ def test_model_oracle_vs_reference_golden(name):
     assert float((o["attn"] - torch.from_numpy(z["attn"])).abs().max()) < 1e-3
     got = np.array([float(o["loss"]), float(o["nll"]), float(o["attn_loss"])])
     assert np.allclose(got, z["losses"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("dataset", ["ImageNet", "MNIST"])
+def test_preprocess_oracle_vs_reference_golden(dataset):
+    """f2: the oracle's ToTensor+Normalize+cast equals what the reference's own transform objects produced, bit for bit."""
+    z = np.load("tests/golden/preprocess_u8.npz")
+    mean, std = sb.SlotModel.NORMALIZE[dataset]
+    got = oh.preprocess_u8(z[dataset + "_u8"], mean, std).numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, z[dataset + "_f32"])
