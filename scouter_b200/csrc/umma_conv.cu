@@ -100,7 +100,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < C::STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
-            mbar_init(&split_done[i], 128);
+            mbar_init(&split_done[i], 4);   // one arrival per splitter warp
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&cfull[i], 1);
@@ -231,7 +231,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int row = q * 32 + lane;
         const int col0 = grp * C::NC;
         uint32_t cc = 0;
-        PROF_DECL(cfull); PROF_DECL(store); PROF_DECL(merge); PROF_DECL(epi); PROF_BEGIN(epi);
+        PROF_DECL(cfull); PROF_DECL(store); PROF_DECL(merge); PROF_DECL(epi); PROF_DECL(e_wait); PROF_DECL(e_bar1); PROF_DECL(e_math);
+        PROF_DECL(e_fence); PROF_DECL(e_bar2); PROF_DECL(e_tma); PROF_BEGIN(epi);
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int sp = t % p.ksplit;
             const int tt = t / p.ksplit;
@@ -256,6 +257,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int ch0 = g * p.cout_g + nt * BN + col0;
             float* op = p.out + (long long)sp * p.slab + orow * p.Cout + ch0;
             const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
+            // SPLIT folds bias and residual into the initial value of the running sums (loads issued before the MMAs of
+            // the tile are waited for); a bias load inside the store phase costs an exposed L2 round trip per 16 columns
+            const float* bias_e = SPLIT ? nullptr : p.bias;
 
             auto finish = [&](const uint32_t (&r)[32], int c) {   // bias / residual / ReLU / store of 32 columns
                 if (!valid) return;
@@ -263,8 +267,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < 8; ++j) {
                     float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                    if (p.bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c * 32 + 4 * j));
+                    if (bias_e) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_e + ch0 + c * 32 + 4 * j));
                         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     }
                     if (rp) {
@@ -282,15 +286,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int sbuf = 0;
             auto emit_tma16 = [&](const float* v, int c16) {
                 uint8_t* stg = out_stage + (grp * 2 + sbuf) * C::OUT_STAGE;
-                if (row == 0) bulk_wait_read<1>();                 // the store that used this buffer two chunks ago is done
-                named_bar_sync(1 + grp, 128);
+                PROF_T(e_wait, if (row == 0) bulk_wait_read<1>());   // the store that used this buffer two chunks ago is done
+                PROF_T(e_bar1, named_bar_sync(1 + grp, 128));
                 float x[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) x[j] = v[j];
-                if (p.bias) {
+#ifdef SCOUTER_PROF
+                const long long _tb = clock64();
+#endif
+                if (bias_e) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c16 * 16 + 4 * j));
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_e + ch0 + c16 * 16 + 4 * j));
                         x[4 * j] += bv.x; x[4 * j + 1] += bv.y; x[4 * j + 2] += bv.z; x[4 * j + 3] += bv.w;
                     }
                 }
@@ -310,11 +317,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < 4; ++j)   // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
                     *reinterpret_cast<float4*>(stg + row * 64 + ((j ^ ((row >> 1) & 3)) << 4)) =
                         make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-                fence_proxy_async();
-                named_bar_sync(1 + grp, 128);
+#ifdef SCOUTER_PROF
+                prof_e_math += clock64() - _tb;
+#endif
+                PROF_T(e_fence, fence_proxy_async());
+                PROF_T(e_bar2, named_bar_sync(1 + grp, 128));
                 if (row == 0) {
-                    tma_store_3d(&tmO, stg, ch0 + c16 * 16, mt * 128, sp);
-                    bulk_commit();
+                    PROF_T(e_tma, tma_store_3d(&tmO, stg, ch0 + c16 * 16, mt * 128, sp); bulk_commit());
                 }
                 sbuf ^= 1;
             };
@@ -323,15 +332,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 // The running fp32 sum starts from the residual: its loads are issued here, before the first chunk is
                 // waited for, so their DRAM latency hides behind the tile's MMAs (and costs no extra registers).
                 float acc[C::NC];
-                if (rp && valid) {
+                const bool with_bias = p.bias && p.ksplit == 1;   // split-K slabs are raw partial sums
 #pragma unroll
-                    for (int j = 0; j < C::NC / 4; ++j) {
+                for (int j = 0; j < C::NC / 4; ++j) {
+                    float4 v = with_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rp && valid) {
                         const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
-                        acc[4 * j] = rv.x; acc[4 * j + 1] = rv.y; acc[4 * j + 2] = rv.z; acc[4 * j + 3] = rv.w;
+                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < C::NC; ++j) acc[j] = 0.f;
+                    acc[4 * j] = v.x; acc[4 * j + 1] = v.y; acc[4 * j + 2] = v.z; acc[4 * j + 3] = v.w;
                 }
                 rp = nullptr;   // already folded in
                 for (int ch = 0; ch < nchunks; ++ch, ++cc) {
@@ -401,7 +410,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         PROF_END(epi);
         if (threadIdx.x == 128) {
             PROF_STORE(g_prof_flat, 10, epi); PROF_STORE(g_prof_flat, 11, cfull); PROF_STORE(g_prof_flat, 12, store);
-            PROF_STORE(g_prof_flat, 13, merge);
+            PROF_STORE(g_prof_flat, 13, merge); PROF_STORE(g_prof_flat, 16, e_wait); PROF_STORE(g_prof_flat, 17, e_bar1);
+            PROF_STORE(g_prof_flat, 18, e_math); PROF_STORE(g_prof_flat, 19, e_fence); PROF_STORE(g_prof_flat, 20, e_bar2); PROF_STORE(g_prof_flat, 21, e_tma);
         }
     } else if (SPLIT && warp >= 8 && warp < 12) {
         // ===== operand splitters: bf16(x) and bf16(x - trunc19(x)) tiles of the activation (and, unless pre-split, weight) tile =====
@@ -417,7 +427,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 split_tile_bf16<128>(st, st + C::OFF_AB, st + C::OFF_ARB, sl);
                 if (!p.rem_rows) split_tile_bf16<BN>(st + C::A_BYTES, st + C::OFF_WB, st + C::OFF_WRB, sl);
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                mbar_arrive(&split_done[stage]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split_done[stage]);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }

@@ -46,6 +46,7 @@ struct HaloArgs {
     int patch_alloc;   // bytes reserved per patch buffer (raw or remainder), multiple of 1024
     int pst, bst;      // ring depths
     int chunk;         // k-steps (cb,tap pairs) per accumulation chunk
+    int tma_store;     // epilogue leaves through swizzled staging + 4-D TMA stores (box {16 ch, Wb, Hb, 1})
 };
 
 template <int BN>
@@ -57,18 +58,21 @@ struct HCfg {
     static constexpr int NC = BN / EPI_GROUPS;
     static constexpr int THREADS = 512;
     static constexpr int MAX_ST = 8;
+    static constexpr int OUT_STAGE = 128 * 64;   // staging of 16 columns x <=128 compact tile rows, SWIZZLE_64B
+    static constexpr int OUT_BYTES = EPI_GROUPS * 2 * OUT_STAGE;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(512, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmB2, const HaloArgs p) {
+                    const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO, const HaloArgs p) {
     using C = HCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* patch0 = smem;                                      // pst x [raw | rem]
     uint8_t* bt0 = smem + p.pst * 2 * p.patch_alloc;            // bst x [W_t | W_r]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bt0 + p.bst * C::B_STAGE);
+    uint8_t* out_stage = bt0 + p.bst * C::B_STAGE;               // [EPI_GROUPS][2][OUT_STAGE], 1024-aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + C::OUT_BYTES);
     uint64_t* pfull = bars;                  // [MAX_ST] patch landed (TMA)
     uint64_t* pready = pfull + C::MAX_ST;    // [MAX_ST] remainder written (128 splitter threads)
     uint64_t* pempty = pready + C::MAX_ST;   // [MAX_ST] all MMAs that read the patch retired
@@ -86,7 +90,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < C::MAX_ST; ++i) {
             mbar_init(&pfull[i], 1);
-            mbar_init(&pready[i], 128);
+            mbar_init(&pready[i], 4);   // one arrival per splitter warp
             mbar_init(&pempty[i], 1);
             mbar_init(&bfull[i], 1);
             mbar_init(&bempty[i], 1);
@@ -237,9 +241,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const bool valid = hb < p.Hb && wb < p.Wb && h < p.H && w < p.W;
             const long long orow = ((long long)b * p.H + h) * p.W + w;
             const int ch0 = g * p.cout_g + nt * BN + col0;
+            // The running fp32 sums start from bias (+ residual): those loads are issued here, before the first chunk
+            // is waited for, so their latency hides behind the tile's MMAs instead of sitting in the store phase.
             float acc[C::NC];
+            const float* rp = (p.res && valid) ? p.res + orow * p.Cout + ch0 : nullptr;
 #pragma unroll
-            for (int j = 0; j < C::NC; ++j) acc[j] = 0.f;
+            for (int j = 0; j < C::NC / 4; ++j) {
+                float4 v = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rp) {
+                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
+                    v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                }
+                acc[4 * j] = v.x; acc[4 * j + 1] = v.y; acc[4 * j + 2] = v.z; acc[4 * j + 3] = v.w;
+            }
             for (int ch = 0; ch < nchunks; ++ch, ++cc) {
                 const int buf = cc & 1;
                 PROF_T(cfull, mbar_wait(&cfull[buf], (cc >> 1) & 1));
@@ -258,28 +272,45 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #ifdef SCOUTER_PROF
             const long long _ts = clock64();
 #endif
-            if (valid) {
-                float* op = p.out + orow * p.Cout + ch0;
-                const float* rp = p.res ? p.res + orow * p.Cout + ch0 : nullptr;
+            if (p.relu) {
 #pragma unroll
-                for (int j = 0; j < C::NC / 4; ++j) {
-                    float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-                    if (p.bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + 4 * j));
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                for (int j = 0; j < C::NC; ++j) acc[j] = fmaxf(acc[j], 0.f);
+            }
+            if (p.tma_store) {
+                // 16 columns of every tile pixel go through a swizzled staging buffer (rows = compact pixel index
+                // hb*Wb + wb, the order of the TMA box) and leave as one 4-D bulk tensor store; pixels outside the
+                // image are clipped by TMA.
+                const bool inbox = hb < p.Hb && wb < p.Wb;
+                const int cr = hb * p.Wb + wb;
+#pragma unroll
+                for (int c16 = 0; c16 < C::NC / 16; ++c16) {
+                    uint8_t* stg = out_stage + (grp * 2 + (c16 & 1)) * C::OUT_STAGE;
+                    if (row == 0) bulk_wait_read<1>();
+                    named_bar_sync(1 + grp, 128);
+                    if (inbox) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)   // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+                            *reinterpret_cast<float4*>(stg + cr * 64 + ((j ^ ((cr >> 1) & 3)) << 4)) =
+                                make_float4(acc[c16 * 16 + 4 * j], acc[c16 * 16 + 4 * j + 1], acc[c16 * 16 + 4 * j + 2], acc[c16 * 16 + 4 * j + 3]);
                     }
-                    if (rp) {
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
-                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                    fence_proxy_async();
+                    named_bar_sync(1 + grp, 128);
+                    if (row == 0) {
+                        tma_store_4d(&tmO, stg, ch0 + c16 * 16, w0, h0, b);
+                        bulk_commit();
                     }
-                    if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                    *reinterpret_cast<float4*>(op + 4 * j) = v;
                 }
+            } else if (valid) {
+                float* op = p.out + orow * p.Cout + ch0;
+#pragma unroll
+                for (int j = 0; j < C::NC / 4; ++j)
+                    *reinterpret_cast<float4*>(op + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
             }
 #ifdef SCOUTER_PROF
             prof_store += clock64() - _ts;
 #endif
         }
+        if (p.tma_store && row == 0) bulk_wait<0>();   // all bulk stores of this group have completed
         PROF_END(epi);
         if (threadIdx.x == 128) { PROF_STORE(g_prof_halo, 10, epi); PROF_STORE(g_prof_halo, 11, cfull); PROF_STORE(g_prof_halo, 12, store); }
     } else if (warp >= 8 && warp < 12) {
@@ -296,7 +327,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint8_t* raw = patch0 + ps * 2 * p.patch_alloc;
                 split_rows_bf16(raw, raw + p.patch_alloc, raw + p.patch_alloc + p.patch_alloc / 2, sl, prows);
                 fence_proxy_async();
-                mbar_arrive(&pready[ps]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pready[ps]);
                 if (++ps == p.pst) { ps = 0; pphase ^= 1; }
             }
         }
@@ -351,10 +383,10 @@ int halo_bn(int cout_g) {
 }
 
 template <int BN>
-int launch_halo_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const HaloArgs& u, int grid, int smem,
-                   cudaStream_t s) {
+int launch_halo_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const CUtensorMap& tO, const HaloArgs& u,
+                   int grid, int smem, cudaStream_t s) {
     SC_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv3x3_halo_kernel<BN><<<grid, 512, smem, s>>>(tA, tB, tB2, u);
+    conv3x3_halo_kernel<BN><<<grid, 512, smem, s>>>(tA, tB, tB2, tO, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -398,8 +430,10 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();
     u.chunk = chunk_kb;
     const int b_stage = 2 * BN * 128;
-    const int scratch = 0;
-    const int budget = 224 * 1024 - 1536;
+    static bool no_tma_store = getenv("SCOUTER_NO_TMA_STORE") != nullptr;
+    u.tma_store = no_tma_store ? 0 : 1;
+    const int scratch = (BN == 128 ? 2 : 1) * 2 * 128 * 64;   // HCfg<BN>::OUT_BYTES
+    const int budget = 226 * 1024 - 1536 - scratch;
     // narrow tiles (small BN) do little MMA work per patch and are latency/bandwidth bound: deeper patch prefetch
     const int want_pst = BN == 128 ? 2 : (BN == 64 ? 3 : 4);
     u.pst = 2;
@@ -410,7 +444,7 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     const int smem = u.pst * 2 * u.patch_alloc + u.bst * b_stage + 1024 + 512 + scratch;
 
     const bool reuse = plan.valid && plan.halo && plan.in == a.in && plan.w == a.w && plan.B == a.B && plan.H == a.H &&
-                       plan.W == a.W && plan.Cin == a.Cin && plan.Cout == a.Cout && plan.groups == a.groups && plan.BN == BN;
+                       plan.W == a.W && plan.Cin == a.Cin && plan.Cout == a.Cout && plan.groups == a.groups && plan.BN == BN && plan.out == a.out;
     if (!reuse) {
         cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
         cuuint64_t strides[3] = {(cuuint64_t)a.Cin * 4, (cuuint64_t)a.W * a.Cin * 4, (cuuint64_t)a.H * a.W * a.Cin * 4};
@@ -435,6 +469,14 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_halo: cuTensorMapEncodeTiled(bf16 W) failed with %d", (int)r);
+        // output (Cout, W, H, B) fp32, box {16, Wb, Hb, 1}: one epilogue staging buffer = 16 channels of every tile pixel
+        cuuint64_t dimsO[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+        cuuint64_t stridesO[3] = {(cuuint64_t)a.Cout * 4, (cuuint64_t)a.W * a.Cout * 4, (cuuint64_t)a.H * a.W * a.Cout * 4};
+        cuuint32_t boxO[4] = {16, (cuuint32_t)u.Wb, (cuuint32_t)u.Hb, 1};
+        r = enc(&plan.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.out, dimsO, stridesO, boxO, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_halo: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+        plan.out = a.out;
         plan.valid = true; plan.halo = true;
         plan.in = a.in; plan.w = a.w; plan.B = a.B; plan.H = a.H; plan.W = a.W; plan.Cin = a.Cin; plan.Cout = a.Cout;
         plan.kh = 3; plan.groups = a.groups; plan.BN = BN;
@@ -448,9 +490,9 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     const long long total = (long long)u.m_tiles * u.n_tiles * u.groups;
     const int grid = (int)std::min<long long>(total, sms);
     switch (BN) {
-        case 32: return launch_halo_bn<32>(plan.tmA, plan.tmB, plan.tmB2, u, grid, smem, s);
-        case 64: return launch_halo_bn<64>(plan.tmA, plan.tmB, plan.tmB2, u, grid, smem, s);
-        case 128: return launch_halo_bn<128>(plan.tmA, plan.tmB, plan.tmB2, u, grid, smem, s);
+        case 32: return launch_halo_bn<32>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, smem, s);
+        case 64: return launch_halo_bn<64>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, smem, s);
+        case 128: return launch_halo_bn<128>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, smem, s);
     }
     return SCOUTER_E_UNSUPPORTED;
 }

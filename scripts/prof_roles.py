@@ -38,7 +38,8 @@ lib = L.lib()
 dev = torch.device("cuda", 0)
 SLOTS = {0: "prod.total", 1: "prod.wait_patch_empty|empty", 2: "prod.wait_b_empty", 4: "issuer.total", 5: "issuer.wait_pready",
          6: "issuer.wait_cempty", 7: "issuer.wait_bfull|full", 8: "issuer.ksteps", 10: "epi.total", 11: "epi.wait_cfull",
-         12: "epi.store", 13: "epi.merge", 14: "split.total", 15: "split.wait_full"}
+         12: "epi.store", 13: "epi.merge", 14: "split.total", 15: "split.wait_full", 16: "emit.bulk_wait_read", 17: "emit.bar1", 18: "emit.bias+math+sts",
+         19: "emit.fence_proxy", 20: "emit.bar2", 21: "emit.tma_issue"}
 
 # (name, H, W, Cin, Cout, k, groups, residual)
 CASES = [
