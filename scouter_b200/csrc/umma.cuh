@@ -14,8 +14,9 @@ struct UmmaConvPlan {
     bool valid = false;
     bool halo = false;
     bool presplit = false;
-    CUtensorMap tmA, tmB, tmB2, tmO;
+    CUtensorMap tmA, tmB, tmB2, tmO, tmR;
     const float* out = nullptr;
+    const float* res = nullptr;
     int ksplit = 0;
     const float* in = nullptr;
     const float* w = nullptr;

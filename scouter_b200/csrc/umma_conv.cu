@@ -53,14 +53,14 @@ struct UmmaArgs {
     long long slab;  // floats between partial slabs
 };
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool RES = false>
 struct Cfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
     static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | W | bf16 A | bf16 A_r | bf16 W | bf16 W_r]
     static constexpr int OFF_AB = RAW, OFF_ARB = RAW + A_BYTES / 2, OFF_WB = RAW + A_BYTES, OFF_WRB = RAW + A_BYTES + B_BYTES / 2;
-    static constexpr int STAGES = (192 * 1024 / STAGE) > 8 ? 8 : (192 * 1024 / STAGE);
+
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
     // fp32 sums of the chunked accumulation fit in registers (64 per thread).
@@ -68,7 +68,10 @@ struct Cfg {
     static constexpr int NC = BN / EPI_GROUPS;               // columns per epilogue thread
     static constexpr int THREADS = SPLIT ? 512 : 256;
     static constexpr int OUT_STAGE = 128 * 64;              // TMA-store staging: 128 rows x 16 fp32, SWIZZLE_64B
-    static constexpr int OUT_BYTES = EPI_GROUPS * 2 * OUT_STAGE;
+    // RES: the whole 128 x BN residual tile is TMA-loaded into BN/16 slabs; the epilogue adds it in place and the
+    // same slabs are the source of the TMA stores (no staging double buffer, no row-per-thread residual loads).
+    static constexpr int OUT_BYTES = RES ? (BN / 16) * OUT_STAGE : EPI_GROUPS * 2 * OUT_STAGE;
+    static constexpr int STAGES = ((224 * 1024 - OUT_BYTES) / STAGE) > 8 ? 8 : ((224 * 1024 - OUT_BYTES) / STAGE);
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 1024 /*barriers*/ + OUT_BYTES;
 };
 
@@ -76,11 +79,13 @@ struct Cfg {
 __device__ unsigned long long g_prof_flat[256 * 32];
 #endif
 
-template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(Cfg<BN, SPLIT>::THREADS, 1)
+template <int BN, bool SPLIT, bool RES>
+__global__ void __launch_bounds__(Cfg<BN, SPLIT, RES>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO, const UmmaArgs p) {
-    using C = Cfg<BN, SPLIT>;
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO,
+                 const __grid_constant__ CUtensorMap tmR, const UmmaArgs p) {
+    using C = Cfg<BN, SPLIT, RES>;
+    static_assert(!RES || SPLIT, "the in-place residual epilogue exists for the SPLIT kernel only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
@@ -88,7 +93,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* cfull = empty + C::STAGES;   // [2] accumulator chunk complete (tcgen05.commit)
     uint64_t* cempty = cfull + 2;          // [2] accumulator chunk drained by every epilogue thread
     uint64_t* split_done = cempty + 2;     // [STAGES], SPLIT only: remainders written, stage ready for the issuer
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(split_done + C::STAGES);
+    uint64_t* rfull = split_done + C::STAGES;   // RES: residual tile landed (TMA)
+    uint64_t* rempty = rfull + 1;               // RES: every store of the tile has read its slab (one arrival per epilogue group)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rempty + 1);
     uint8_t* out_stage = smem + C::STAGES * C::STAGE + 1024;   // [EPI_GROUPS][2][OUT_STAGE], 1024-aligned
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -106,6 +113,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&cfull[i], 1);
             mbar_init(&cempty[i], 128 * C::EPI_GROUPS);
         }
+        mbar_init(rfull, 1);
+        mbar_init(rempty, C::EPI_GROUPS);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -127,6 +136,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             PROF_DECL(empty); PROF_DECL(prod); PROF_BEGIN(prod);
+            uint32_t rphase = 0;   // RES: parity of the residual buffer cycle
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const int sp = t % p.ksplit;
                 const int tt = t / p.ksplit;
@@ -139,7 +149,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     h0 = ((mt / p.tw) % p.th) * p.Hb;
                     b0 = (mt / (p.tw * p.th)) * p.Nb;
                 }
+                // RES: the residual tile goes out as soon as the previous tile's stores have drained the slabs -- polled
+                // between k-blocks so that a busy epilogue never holds back the operand loads of this tile.
+                bool res_pending = RES;
+                auto issue_residual = [&]() {
+                    mbar_arrive_expect_tx(rfull, (uint32_t)(128 * BN * 4));
+#pragma unroll
+                    for (int j = 0; j < BN / 16; ++j)
+                        tma_load_2d(out_stage + j * C::OUT_STAGE, &tmR, rfull, g * p.cout_g + nt * BN + j * 16, mt * 128);
+                    res_pending = false;
+                    rphase ^= 1;
+                };
                 for (int kb = 0; kb < p.kblocks; ++kb) {
+                    if (RES && res_pending && mbar_try_wait(rempty, rphase ^ 1)) issue_residual();
                     PROF_T(empty, mbar_wait(&empty[stage], phase ^ 1));
                     uint8_t* sa = smem + stage * C::STAGE;
                     uint8_t* sb = sa + C::A_BYTES;
@@ -159,6 +181,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_load_2d(sa + C::OFF_WRB, &tmB2, &full[stage], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (RES && res_pending) {
+                    mbar_wait(rempty, rphase ^ 1);
+                    issue_residual();
                 }
             }
             PROF_END(prod);
@@ -231,6 +257,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int row = q * 32 + lane;
         const int col0 = grp * C::NC;
         uint32_t cc = 0;
+        uint32_t rphase = 0;
         PROF_DECL(cfull); PROF_DECL(store); PROF_DECL(merge); PROF_DECL(epi); PROF_DECL(e_wait); PROF_DECL(e_bar1); PROF_DECL(e_math);
         PROF_DECL(e_fence); PROF_DECL(e_bar2); PROF_DECL(e_tma); PROF_BEGIN(epi);
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -336,7 +363,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < C::NC / 4; ++j) {
                     float4 v = with_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rp && valid) {
+                    if (!RES && rp && valid) {
                         const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + 4 * j));
                         v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
                     }
@@ -367,7 +394,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #ifdef SCOUTER_PROF
                 const long long _ts = clock64();
 #endif
-                if (p.tma_store) {
+                if constexpr (RES) {
+                    // residual slabs: add in place (own row, swizzled 16-byte chunks), ReLU, store from the same slab
+                    PROF_T(e_wait, mbar_wait(rfull, rphase));
+                    rphase ^= 1;
+#pragma unroll
+                    for (int c = 0; c < C::NC / 16; ++c) {
+                        uint8_t* stg = out_stage + (col0 / 16 + c) * C::OUT_STAGE + row * 64;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float4* cell = reinterpret_cast<float4*>(stg + ((j ^ ((row >> 1) & 3)) << 4));
+                            float4 v = *cell;
+                            v.x += acc[c * 16 + 4 * j]; v.y += acc[c * 16 + 4 * j + 1]; v.z += acc[c * 16 + 4 * j + 2]; v.w += acc[c * 16 + 4 * j + 3];
+                            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            if (p.round_out) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                            *cell = v;
+                        }
+                        fence_proxy_async();
+                        named_bar_sync(1 + grp, 128);
+                        if (row == 0) {
+                            tma_store_3d(&tmO, out_stage + (col0 / 16 + c) * C::OUT_STAGE, ch0 + c * 16, mt * 128, 0);
+                            bulk_commit();
+                        }
+                    }
+                    if (row == 0) {
+                        bulk_wait_read<0>();      // the slabs may now be refilled with the next tile's residual
+                        mbar_arrive(rempty);
+                    }
+#ifdef SCOUTER_PROF
+                    prof_store += clock64() - _ts;
+#endif
+                } else if (p.tma_store) {
 #pragma unroll
                     for (int c = 0; c < C::NC / 16; ++c) emit_tma16(&acc[c * 16], c);
 #ifdef SCOUTER_PROF
@@ -406,7 +463,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ++cc;
             }
         }
-        if (p.tma_store && row == 0) bulk_wait<0>();   // all bulk stores of this group have completed
+        if ((RES || p.tma_store) && row == 0) bulk_wait<0>();   // all bulk stores of this group have completed
         PROF_END(epi);
         if (threadIdx.x == 128) {
             PROF_STORE(g_prof_flat, 10, epi); PROF_STORE(g_prof_flat, 11, cfull); PROF_STORE(g_prof_flat, 12, store);
@@ -478,13 +535,14 @@ int pick_bn(int cout_g) {
     return 0;
 }
 
-template <int BN, bool SPLIT>
-int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const CUtensorMap& tO, const UmmaArgs& u, int grid,
-              cudaStream_t s) {
-    using C = Cfg<BN, SPLIT>;
+template <int BN, bool SPLIT, bool RES = false>
+int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const CUtensorMap& tO, const CUtensorMap& tR,
+              const UmmaArgs& u, int grid, cudaStream_t s) {
+    using C = Cfg<BN, SPLIT, RES>;
     static_assert(C::STAGES >= 2, "pipeline too shallow");
-    SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    conv_umma_kernel<BN, SPLIT><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, tB2, tO, u);
+    static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
+    SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, SPLIT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    conv_umma_kernel<BN, SPLIT, RES><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, tB2, tO, tR, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -611,17 +669,37 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     }
     const long long total = (long long)u.m_tiles * u.n_tiles * u.groups * u.ksplit;
     const int grid = (int)std::min<long long>(total, sms);
-    if (a.split) {
+    // residual convs (the block-final 1x1 conv3 + shortcut) take the in-place residual epilogue
+    static bool no_res_tma = getenv("SCOUTER_NO_RES_TMA") != nullptr;
+    const bool res_tma = a.split && a.res && u.tma_store && u.ksplit == 1 && !no_res_tma;
+    if (res_tma) {
+        if (!(reuse && plan.res == a.res)) {
+            cuuint64_t dimsR[2] = {(cuuint64_t)a.Cout, (cuuint64_t)u.M};
+            cuuint64_t stridesR[1] = {(cuuint64_t)a.Cout * 4};
+            cuuint32_t boxR[2] = {16, 128};
+            cuuint32_t esR[2] = {1, 1};
+            CUresult r = enc(&plan.tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.res, dimsR, stridesR, boxR, esR,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(residual) failed with %d", (int)r);
+            plan.res = a.res;
+        }
         switch (BN) {
-            case 32: return launch_bn<32, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
-            case 64: return launch_bn<64, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
-            case 128: return launch_bn<128, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
+            case 32: return launch_bn<32, true, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmR, u, grid, s);
+            case 64: return launch_bn<64, true, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmR, u, grid, s);
+            case 128: return launch_bn<128, true, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmR, u, grid, s);
+        }
+    } else if (a.split) {
+        switch (BN) {
+            case 32: return launch_bn<32, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
+            case 64: return launch_bn<64, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
+            case 128: return launch_bn<128, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
         }
     } else {
         switch (BN) {
-            case 32: return launch_bn<32, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
-            case 64: return launch_bn<64, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
-            case 128: return launch_bn<128, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, s);
+            case 32: return launch_bn<32, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
+            case 64: return launch_bn<64, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
+            case 128: return launch_bn<128, false>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
         }
     }
     return SCOUTER_E_UNSUPPORTED;

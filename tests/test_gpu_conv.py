@@ -36,6 +36,8 @@ CASES = [
     (1, 17, 17, 1024, 256, 1, 1, False, True),
     (1, 5, 3, 32, 32, 3, 1, False, False),         # tiny map, smaller than one box
     (300, 1, 1, 64, 64, 1, 1, False, False),       # M = 300: partial last flat tile
+    (1, 17, 17, 64, 128, 1, 1, True, True),        # residual epilogue with a partial last tile (M = 289)
+    (2, 14, 14, 256, 320, 1, 1, True, False),      # residual, BN = 64, several k-blocks per chunk
 ]
 
 
