@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SCOUTER_ABI_VERSION 1
+#define SCOUTER_ABI_VERSION 2
 
 #define SCOUTER_OK 0
 #define SCOUTER_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, ...) */
@@ -144,6 +144,8 @@ typedef struct scouter_head_io {
     float* attn;             /* (B, S, n) or NULL */
     float* attn_sum;         /* (B) or NULL */
     float* x_out;            /* (B, n, d) projected features, or NULL (debug / tests) */
+    const void* conv_w_split;/* optional (2d, ch) bfloat16: rows [0,d) = bf16(W), rows [d,2d) = bf16(W - trunc19(W)), the
+                                correction operands of the error-compensated product; NULL = derived per call */
 } scouter_head_io_t;
 
 size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io);

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscouter_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "umma_conv.cu", "umma_halo.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "head_fused.cu", "umma_conv.cu", "umma_halo.cu"]
 
 OK = 0
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
@@ -51,7 +51,7 @@ class HeadIO(C.Structure):
         ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("channel", C.c_int32),
         ("layout", C.c_int32), ("math", C.c_int32),
         ("feat", _fp), ("conv_w", _fp), ("conv_b", _fp), ("pe", _fp),
-        ("logits", _fp), ("attn", _fp), ("attn_sum", _fp), ("x_out", _fp),
+        ("logits", _fp), ("attn", _fp), ("attn_sum", _fp), ("x_out", _fp), ("conv_w_split", _fp),
     ]
 
 

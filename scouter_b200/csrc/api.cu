@@ -309,12 +309,17 @@ static int validate_head(const scouter_xslot_desc_t* desc, const scouter_head_io
     return 0;
 }
 
-extern "C" size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io) {
-    if (validate_head(desc, io)) return 0;
+// workspace = [4 split-K partial slabs][NHWC copy of NCHW features][bf16 split of conv1x1.weight (fused kernel)]
+static size_t head_ws_base(const scouter_head_io_t* io) {
     size_t n = (size_t)io->h * io->w;
-    size_t bytes = align_up((size_t)4 * io->batch * n * XD * sizeof(float), 1024);   // up to 4 split-K partial slabs
+    size_t bytes = align_up((size_t)4 * io->batch * n * XD * sizeof(float), 1024);
     if (io->layout == SCOUTER_LAYOUT_NCHW) bytes += align_up((size_t)io->batch * n * io->channel * sizeof(float), 1024);
     return bytes;
+}
+
+extern "C" size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io) {
+    if (validate_head(desc, io)) return 0;
+    return head_ws_base(io) + head_fused_workspace_bytes(io->channel);
 }
 
 extern "C" int scouter_head_forward(const scouter_xslot_desc_t* desc, const void* packed, const scouter_head_io_t* io,
@@ -333,6 +338,9 @@ extern "C" int scouter_head_forward(const scouter_xslot_desc_t* desc, const void
         if (int e = launch_nchw_to_nhwc(io->feat, t, io->batch, io->channel, n, s)) return e;
         feat = t;
     }
+    // one kernel for the whole head when a unit of images fits a 128-row UMMA tile (head_fused.cu)
+    if (io->math != SCOUTER_MATH_FP32 && head_fused_supported(desc, io->batch, n, io->channel))
+        return head_fused_launch(desc, packed, io, feat, (char*)workspace + head_ws_base(io), s);
     const int M = io->batch * n;
     const bool fast = xslot_fast_supported(desc, n);
     // conv1x1 + bias + ReLU (slot_model.py:108-109).  On the tensor cores the projection always runs error-compensated

@@ -1,0 +1,690 @@
+// The xSlot head as ONE kernel (SURVEY 8(d) "fused head"): conv1x1 + bias + ReLU (sloter/slot_model.py:108-109), + PE
+// (:110-111) and SlotAttention.forward (sloter/utils/slot_attention.py:44-96) without the projected tokens ever
+// leaving the SM.
+//
+//   unit  = G consecutive images whose R = G*n token rows fit one 128-row UMMA tile (n = 49 -> 2 images, 81 -> 1);
+//           one CTA per unit, 512 threads, CTAs paired into clusters of two.
+//   phase A (HBM-bound): the unit's (R x ch) fp32 feature slab streams through a deep TMA ring (NA stages of 32
+//           channels).  Error-compensated tensor-core product as in umma_conv.cu (tf32 main product A_t*W_t + two bf16
+//           correction products A*W_r, A_r*W; chunked TMEM accumulation merged in fp32 registers) -- but with the A
+//           operands in TENSOR MEMORY: this GEMM is thin (N = 64), so in SS mode the MMAs' own operand reads (6 KB per
+//           instruction, 48 KB per k-block) plus the split tiles saturate the 128 B/clk shared-memory pipe at 2.5x the
+//           HBM time (measured: 1170 clk per k-block).  Here the splitter threads (thread = token row) read their row of
+//           the TMA tile once, derive bf16(x) and bf16(x - trunc19(x)) in registers and tcgen05.st all three forms into
+//           a TMEM operand buffer; the MMAs then read only the small weight tile from shared memory.
+//           conv1x1.weight (fp32 + pre-split bf16 [W ; W_r]) streams through a 3-slot ring, multicast to both CTAs of
+//           the cluster (each loads half).
+//           warp 0 = feature producer, warp 3 = weight producer, warps 1 and 2 = MMA issuers on alternate k-blocks (four
+//           TMEM accumulators: the single-thread issue cost is the floor of such a thin GEMM), warps 4-7 = accumulator
+//           owners (thread = token row), warps 8-15 = two groups of splitters on alternate k-blocks.
+//           ONE multicast tcgen05.commit per k-block releases the weight slot and the operand buffer in both CTAs.
+//           The to_k weights are prefetched with cp.async meanwhile.
+//   hand-over: the accumulator owners add the bias, apply ReLU and write X and X + PE straight into shared memory.
+//   phase B (FP32 FMA, all 16 warps): to_k MLP, 3 x {QK^T, sum-normalise, sigmoid, attn.X / d, GRU}, logits -- the
+//           arithmetic of xslot_fast.cu (fp32 with IEEE division, fixed-order reductions: bit-reproducible).
+//
+// Algorithmic HBM bytes = B*n*ch*4 (features) + weights + outputs; nothing is written back in between.
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+#include "ptx.cuh"
+#include "umma.cuh"
+#include "xslot.cuh"
+
+namespace scouter {
+using namespace ptx;
+
+namespace {
+
+constexpr int HT = 512, HW_ = HT / 32;
+constexpr int LDX = XD + 4;
+constexpr int W_FLOATS = 2 * XD * XG + 2 * XG;   // GRU block: WihT[64][192], WhhT[64][192], b_ih[192], b_hh[192]
+constexpr int TOK_FLOATS = XD * XD + XD;         // one to_k layer: WT[64][64], b[64]
+
+// phase-A shared memory: [NA feature stages | NW weight slots]; tensor memory: [4 accumulators | NO operand buffers]
+constexpr int W_F32 = XD * 128;                  // 64 rows x 32 tf32
+constexpr int W_SLOT = 2 * W_F32;                // [W fp32 | bf16 W | bf16 W_r]
+constexpr int MAX_NW = 8;                        // weight slots (a.nw of them)
+constexpr int NO = 4;                            // TMEM operand buffers of 64 columns: [fp32 A (32) | bf16 A (16) | bf16 A_r (16)]
+constexpr int ND = 8;                            // "k-block retired" barriers (>= MAX_NW, NO); power of two (index = kb & 7)
+constexpr int OP_COL0 = 4 * XD;                  // operand buffers start after the four 64-column accumulators
+constexpr int MAX_NA = 8;
+constexpr int CHUNK = 4;                         // k-blocks per TMEM accumulation chunk (per issuer; see umma_conv.cu)
+
+struct FusedArgs {
+    const float* conv_b;
+    const float* packed;
+    const float* pe;
+    float* x_out;
+    float* logits;
+    float* attn;
+    float* attn_sum;
+    int B, n, G, S, C, spc, L, iters, loss_status;
+    int kblocks;
+    // shared-memory map (bytes from the 1024-aligned base); the phase-B regions alias the phase-A rings
+    int na, nw, a_stage, off_w;
+    int issue_batch;   // feature stages issued back to back (longer contiguous runs per feature row at the DRAM)
+    int blocked;       // features are channel-block major: (ch/32, B*n, 32)
+    int off_tokw, off_gru, off_small, off_bar;
+};
+
+__host__ __device__ inline int kb_floats(int img, int n, int S) {
+    const int a = img * n * LDX, b = img * S * 2 * XG + img * n * ((S + 3) & ~3);
+    return ((a > b ? a : b) + 3) & ~3;
+}
+
+__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+#ifdef SCOUTER_PROF
+__device__ unsigned long long g_prof_head[256 * 32];
+__device__ unsigned long long g_trace_head[128 * 8];   // CTA 0: [k-block][event] clock64 timestamps
+#define TRACE(kb, ev) do { if (blockIdx.x == 0 && (kb) < 128) g_trace_head[(kb) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(kb, ev)
+#endif
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HT, 1)
+head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmB2, const FusedArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int n = a.n, S = a.S, G = a.G;
+    const int R = G * n;            // token rows of this unit
+    const int SR = G * S;           // slot rows
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const int b0 = blockIdx.x * G;
+    const int nimg = min(G, a.B - b0);   // <= 0 for the padding CTA of an odd unit count (it streams zeros, writes nothing)
+    const int NA = a.na, NW = a.nw;
+    const uint32_t rank = cluster_ctarank();
+    const XSlotPacked pk{S, a.L};
+
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + a.off_bar);   // [MAX_NA] feature stage landed
+    uint64_t* emptyA = fullA + MAX_NA;      // [MAX_NA] stage read into registers by its splitter group (4 warps)
+    uint64_t* done = emptyA + MAX_NA;       // [ND] MMAs of the k-block retired in BOTH CTAs (2 multicast commits)
+    uint64_t* fullW = done + ND;            // [NW] weight slot landed (own half + the peer's multicast half)
+    uint64_t* opfull = fullW + MAX_NW;      // [NO] operands of the k-block are in TMEM
+    uint64_t* cfull = opfull + NO;          // [2 issuers][2] accumulator chunk complete
+    uint64_t* cempty = cfull + 4;           // [2][2] chunk drained by the 128 accumulator owners
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cempty + 4);
+
+    // phase-B views
+    const int SP = (S + 3) & ~3;
+    float* Xs = reinterpret_cast<float*>(smem);   // [R][LDX]
+    float* Ka = Xs + R * LDX;                      // [R][LDX]
+    float* Kb = Ka + R * LDX;                      // MLP ping-pong; afterwards gates / attention scratch
+    float* Wtok = reinterpret_cast<float*>(smem + a.off_tokw);   // to_k layers (beyond the rings: prefetched in phase A)
+    float* Wsm = reinterpret_cast<float*>(smem + a.off_gru);     // GRU block (aliases rings / to_k weights; loaded after the MLP)
+    float* slots = reinterpret_cast<float*>(smem + a.off_small); // [SR][64]
+    float* upd = slots + SR * XD;
+    float* rsum = upd + SR * XD;
+    float* usum = rsum + SR;
+    float* misc = usum + SR;
+    float* gates = Kb;
+    float* attnT = Kb + SR * 2 * XG;
+    float* kin = (a.L & 1) ? Kb : Ka;              // after L ping-pong layers the keys end up in Ka
+    float* kout = (a.L & 1) ? Ka : Kb;
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        prefetch_tmap(&tmB2);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < MAX_NA; ++i) {
+            mbar_init(&fullA[i], 1);
+            mbar_init(&emptyA[i], 4);
+        }
+        for (int i = 0; i < ND; ++i) mbar_init(&done[i], 2);
+        for (int i = 0; i < MAX_NW; ++i) mbar_init(&fullW[i], 1);
+        for (int i = 0; i < NO; ++i) mbar_init(&opfull[i], 4);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&cfull[i], 1);
+            mbar_init(&cempty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_arrive();     // the peer multicasts into this CTA's weight slots and arrives on its barriers
+    cluster_wait();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    PROF_DECL(phaseA); PROF_DECL(mlp); PROF_DECL(loop); PROF_BEGIN(phaseA);
+
+    const int kblocks = a.kblocks;
+    uint8_t* const w_ring = smem + a.off_w;
+
+    // =========================================== phase A ===========================================================
+    if (warp == 0) {
+        if (elect_one()) {
+            // ----- feature producer: runs NA k-blocks ahead of the MMAs -----
+            int stage = 0;
+            uint32_t phase = 0;
+            const int row0 = blockIdx.x * R;
+            PROF_DECL(pa_wait);
+            const int nb = a.issue_batch;
+            for (int kb0 = 0; kb0 < kblocks; kb0 += nb) {
+                const int kb1 = min(kb0 + nb, kblocks);
+                {                                      // all stages of the batch must be free before the first load goes out
+                    int st = stage;
+                    uint32_t ph = phase;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        if (kb >= NA) PROF_T(pa_wait, mbar_wait(&emptyA[st], ph ^ 1));
+                        if (++st == NA) { st = 0; ph ^= 1; }
+                    }
+                }
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_arrive_expect_tx(&fullA[stage], (uint32_t)(R * 128));
+                    if (a.blocked) tma_load_3d(smem + stage * a.a_stage, &tmA, &fullA[stage], 0, row0, kb);
+                    else tma_load_2d(smem + stage * a.a_stage, &tmA, &fullA[stage], kb * 32, row0);
+                    TRACE(kb, 0);
+                    if (++stage == NA) { stage = 0; phase ^= 1; }
+                }
+            }
+            PROF_STORE(g_prof_head, 3, pa_wait);
+        }
+    } else if (warp == 3) {
+        if (elect_one()) {
+            // ----- weight producer: rank 0 multicasts the fp32 tile, rank 1 the bf16 [W ; W_r] pair -----
+            PROF_DECL(pw_wait);
+            int ws = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                if (kb >= NW) {
+                    const int j = kb - NW;
+                    PROF_T(pw_wait, mbar_wait(&done[j & (ND - 1)], (uint32_t)(j >> 3) & 1u));   // slot drained in both CTAs
+                }
+                mbar_arrive_expect_tx(&fullW[ws], (uint32_t)W_SLOT);
+                if (rank == 0) tma_load_2d_mc(w_ring + ws * W_SLOT, &tmB, &fullW[ws], kb * 32, 0, (uint16_t)3);
+                else tma_load_2d_mc(w_ring + ws * W_SLOT + W_F32, &tmB2, &fullW[ws], kb * 32, 0, (uint16_t)3);
+                TRACE(kb, 1);
+                if (++ws == NW) ws = 0;
+            }
+            PROF_STORE(g_prof_head, 4, pw_wait);
+        }
+    } else if (warp == 1 || warp == 2) {
+        if (elect_one()) {
+            // ----- MMA issuers: issuer w takes k-blocks kb = w (mod 2) into its own pair of TMEM accumulators -----
+            const int w = warp - 1;
+            constexpr uint32_t idesc = idesc_tf32(128, XD);
+            constexpr uint32_t idesc_b = idesc_bf16(128, XD);
+            const uint32_t w_lo0 = desc_lo(smem_u32(w_ring));
+            const uint32_t ready_a = smem_u32(opfull), done_a = smem_u32(done), cfull_a = smem_u32(cfull + 2 * w),
+                           cempty_a = smem_u32(cempty + 2 * w), fullw_a = smem_u32(fullW);
+            int ws = w % NW, ob = w, dn = w, in_chunk = 0;     // kb % NW, kb % NO, kb % ND (kb advances by 2)
+            uint32_t ophase = 0, wphase = 0, cc = 0;
+            PROF_DECL(is_cempty); PROF_DECL(is_op);
+            for (int kb = w; kb < kblocks; kb += 2) {
+                const uint32_t buf = cc & 1;
+                if (in_chunk == 0) PROF_T(is_cempty, mbar_wait_a(cempty_a + 8 * buf, ((cc >> 1) & 1) ^ 1));
+                PROF_T(is_op, mbar_wait_a(ready_a + 8 * ob, ophase));
+                TRACE(kb, 5);
+                mbar_wait_a(fullw_a + 8 * ws, wphase);
+                TRACE(kb, 6);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(2 * w + buf) * XD;
+                const uint32_t acc = in_chunk != 0;
+                const uint32_t a_tm = tmem_base + OP_COL0 + (uint32_t)ob * 64;   // [fp32 A | bf16 A | bf16 A_r]
+                const uint32_t w_lo = w_lo0 + (uint32_t)ws * (W_SLOT >> 4);      // [W fp32 | bf16 W | bf16 W_r]
+#pragma unroll
+                for (uint32_t k = 0; k < 2; ++k)   // A * W_r
+                    umma_bf16_ts(d_tmem, a_tm + 32 + 8 * k, desc_make(DESC_HI_SW64, w_lo + ((W_F32 + W_F32 / 2) >> 4) + 2 * k), idesc_b, acc | k);
+#pragma unroll
+                for (uint32_t k = 0; k < 2; ++k)   // A_r * W
+                    umma_bf16_ts(d_tmem, a_tm + 48 + 8 * k, desc_make(DESC_HI_SW64, w_lo + (W_F32 >> 4) + 2 * k), idesc_b, 1);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
+                    umma_tf32_ts(d_tmem, a_tm + 8 * k, desc_make(DESC_HI_SW128, w_lo + 2 * k), idesc, 1);
+                umma_commit_mc_a(done_a + 8 * dn, (uint16_t)3);   // frees the weight slot and the operand buffer in both CTAs
+                TRACE(kb, 7);
+                dn = (dn + 2) & (ND - 1);
+                ws += 2; if (ws >= NW) { ws -= NW; wphase ^= 1; }
+                ob += 2; if (ob >= NO) { ob -= NO; ophase ^= 1; }
+                if (++in_chunk == CHUNK || kb + 2 >= kblocks) {
+                    umma_commit_a(cfull_a + 8 * buf);
+                    ++cc;
+                    in_chunk = 0;
+                }
+            }
+            if (w == 0) { PROF_STORE(g_prof_head, 5, is_cempty); PROF_STORE(g_prof_head, 6, is_op); }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ----- accumulator owners: thread = token row, 64 running fp32 sums starting from the bias -----
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        for (int i = tid - 128; i < a.L * TOK_FLOATS / 4; i += 128)   // to_k weights -> shared memory, behind the stream
+            cp_async16(Wtok + i * 4, a.packed + pk.tok_wt(0) + i * 4);
+        float acc[XD];
+#pragma unroll
+        for (int j = 0; j < XD / 4; ++j) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.conv_b + 4 * j));
+            acc[4 * j] = v.x; acc[4 * j + 1] = v.y; acc[4 * j + 2] = v.z; acc[4 * j + 3] = v.w;
+        }
+        const int nch0 = ((kblocks + 1) / 2 + CHUNK - 1) / CHUNK, nch1 = (kblocks / 2 + CHUNK - 1) / CHUNK;
+        for (int ch = 0; ch < nch0; ++ch) {
+            const int buf = ch & 1;
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {          // fixed merge order: issuer 0's chunk, then issuer 1's
+                if (w == 1 && ch >= nch1) break;
+                mbar_wait(&cfull[2 * w + buf], (ch >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < XD / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * w + buf) * XD + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                }
+                tc_fence_before();
+                mbar_arrive(&cempty[2 * w + buf]);
+            }
+        }
+        // every MMA has retired (the last commits cover them all): the rings are dead, X and X + PE take their place
+        if (row < R) {
+            const int img = row / n, j = row - img * n;
+            const bool live = img < nimg;
+            float* xo = (a.x_out && live) ? a.x_out + ((size_t)(b0 + img) * n + j) * XD : nullptr;
+#pragma unroll
+            for (int e4 = 0; e4 < XD / 4; ++e4) {
+                float4 xv = make_float4(fmaxf(acc[4 * e4], 0.f), fmaxf(acc[4 * e4 + 1], 0.f), fmaxf(acc[4 * e4 + 2], 0.f),
+                                        fmaxf(acc[4 * e4 + 3], 0.f));
+                if (!live) xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(a.pe + j * XD + e4 * 4));
+                *reinterpret_cast<float4*>(Xs + row * LDX + e4 * 4) = xv;
+                *reinterpret_cast<float4*>(kin + row * LDX + e4 * 4) = make_float4(xv.x + pv.x, xv.y + pv.y, xv.z + pv.z, xv.w + pv.w);
+                if (xo) *reinterpret_cast<float4*>(xo + e4 * 4) = xv;
+            }
+        }
+        cp_async_wait_all();
+    } else if (warp >= 8) {
+        // ----- splitters: two groups of four warps on alternate k-blocks; thread = token row -----
+        const int sg = (warp - 8) >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool valid = row < R;
+        const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + OP_COL0;
+        PROF_DECL(sp_fullA); PROF_DECL(sp_done); PROF_DECL(sp_fullW); PROF_DECL(sp_st);
+        int stage = sg % NA;
+        uint32_t aphase = 0;
+        for (int kb = sg; kb < kblocks; kb += 2) {
+            const int ob = kb & (NO - 1);
+            PROF_T(sp_fullA, mbar_wait(&fullA[stage], aphase));
+            if (tid == 256 || tid == 384) TRACE(kb, 2);
+            uint32_t f[32];
+            {
+                const uint8_t* src = smem + stage * a.a_stage + row * 128;
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid) v = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));   // SWIZZLE_128B: 16-byte chunk ^= row % 8
+                    f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
+                }
+            }
+            uint32_t xb[16], rb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float x0 = __uint_as_float(f[2 * i]), x1 = __uint_as_float(f[2 * i + 1]);
+                const float r0 = x0 - __uint_as_float(f[2 * i] & 0xFFFFE000u), r1 = x1 - __uint_as_float(f[2 * i + 1] & 0xFFFFE000u);
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xb[i]) : "f"(x1), "f"(x0));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rb[i]) : "f"(r1), "f"(r0));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyA[stage]);               // the stage lives in registers now
+            if (kb >= NO) {
+                const int j = kb - NO;
+                PROF_T(sp_done, mbar_wait(&done[j & (ND - 1)], (uint32_t)(j >> 3) & 1u));   // the MMAs that read this operand buffer have retired
+                tc_fence_after();
+            }
+            if (tid == 256 || tid == 384) TRACE(kb, 3);
+            const uint32_t t0 = t_lane + (uint32_t)ob * 64;
+            PROF_T(sp_st, tmem_st_32x32(t0, f); tmem_st_32x16(t0 + 32, xb); tmem_st_32x16(t0 + 48, rb); tmem_st_wait());
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&opfull[ob]);
+            if (tid == 256 || tid == 384) TRACE(kb, 4);
+            stage += 2; if (stage >= NA) { stage -= NA; aphase ^= 1; }
+        }
+        if (tid == 256) { PROF_STORE(g_prof_head, 7, sp_fullA); PROF_STORE(g_prof_head, 8, sp_done); PROF_STORE(g_prof_head, 9, sp_fullW); PROF_STORE(g_prof_head, 10, sp_st); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_arrive();     // no more multicasts / remote arrivals from this CTA; matched by cluster_wait() before exit
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    PROF_END(phaseA); PROF_BEGIN(mlp);
+
+    // =========================================== phase B ===========================================================
+    for (int idx = tid; idx < SR * XD; idx += HT) slots[idx] = __ldg(a.packed + pk.slots() + (idx % (S * XD)));
+
+    // ---- to_k MLP: thread = output feature o (weights of its column in registers), 4 token rows at a time ---------
+    {
+        const int o = tid % XD, rg = tid / XD;   // 8 row groups
+        for (int l = 0; l < a.L; ++l) {
+            const float* WT = Wtok + l * TOK_FLOATS;
+            float wreg[XD];
+#pragma unroll
+            for (int e = 0; e < XD; ++e) wreg[e] = WT[e * XD + o];
+            const float bias = WT[XD * XD + o];
+            const bool relu = l + 1 < a.L;
+            for (int j0 = rg * 4; j0 < R; j0 += (HT / XD) * 4) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* r0 = kin + min(j0 + 0, R - 1) * LDX;
+                const float* r1 = kin + min(j0 + 1, R - 1) * LDX;
+                const float* r2 = kin + min(j0 + 2, R - 1) * LDX;
+                const float* r3 = kin + min(j0 + 3, R - 1) * LDX;
+#pragma unroll
+                for (int e4 = 0; e4 < XD / 4; ++e4) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(r0 + e4 * 4);
+                    const float4 v1 = *reinterpret_cast<const float4*>(r1 + e4 * 4);
+                    const float4 v2 = *reinterpret_cast<const float4*>(r2 + e4 * 4);
+                    const float4 v3 = *reinterpret_cast<const float4*>(r3 + e4 * 4);
+                    acc[0] = fmaf(v0.x, wreg[e4 * 4 + 0], acc[0]); acc[1] = fmaf(v1.x, wreg[e4 * 4 + 0], acc[1]);
+                    acc[2] = fmaf(v2.x, wreg[e4 * 4 + 0], acc[2]); acc[3] = fmaf(v3.x, wreg[e4 * 4 + 0], acc[3]);
+                    acc[0] = fmaf(v0.y, wreg[e4 * 4 + 1], acc[0]); acc[1] = fmaf(v1.y, wreg[e4 * 4 + 1], acc[1]);
+                    acc[2] = fmaf(v2.y, wreg[e4 * 4 + 1], acc[2]); acc[3] = fmaf(v3.y, wreg[e4 * 4 + 1], acc[3]);
+                    acc[0] = fmaf(v0.z, wreg[e4 * 4 + 2], acc[0]); acc[1] = fmaf(v1.z, wreg[e4 * 4 + 2], acc[1]);
+                    acc[2] = fmaf(v2.z, wreg[e4 * 4 + 2], acc[2]); acc[3] = fmaf(v3.z, wreg[e4 * 4 + 2], acc[3]);
+                    acc[0] = fmaf(v0.w, wreg[e4 * 4 + 3], acc[0]); acc[1] = fmaf(v1.w, wreg[e4 * 4 + 3], acc[1]);
+                    acc[2] = fmaf(v2.w, wreg[e4 * 4 + 3], acc[2]); acc[3] = fmaf(v3.w, wreg[e4 * 4 + 3], acc[3]);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (j0 + r < R) {
+                        const float v = acc[r] + bias;
+                        kout[(j0 + r) * LDX + o] = relu ? fmaxf(v, 0.f) : v;
+                    }
+            }
+            __syncthreads();
+            float* t = kin; kin = kout; kout = t;
+        }
+    }
+    PROF_END(mlp); PROF_BEGIN(loop);
+    const float* K = Ka;
+    // the to_k weights (and the ring) are dead: bring in the GRU block while the first attention pass runs
+    if (a.iters > 1)
+        for (int i = tid; i < W_FLOATS / 4; i += HT) cp_async16(Wsm + i * 4, a.packed + pk.gru_wih_t() + i * 4);
+
+    for (int it = 0; it < a.iters; ++it) {
+        const bool last = it == a.iters - 1;
+        for (int idx = tid; idx < SR * n; idx += HT) {      // dots[img][i][j] = scale * <slot, key>, kept as attnT[img][j][i]
+            const int sr = idx / n, j = idx - sr * n;
+            const int img = sr / S, i = sr - img * S;
+            const float4* sp = reinterpret_cast<const float4*>(slots + sr * XD);
+            const float4* kp = reinterpret_cast<const float4*>(K + (img * n + j) * LDX);
+            float acc = 0.f;
+#pragma unroll
+            for (int e4 = 0; e4 < XD / 4; ++e4) {
+                const float4 s4 = sp[e4], k4 = kp[e4];
+                acc = fmaf(s4.x, k4.x, acc); acc = fmaf(s4.y, k4.y, acc);
+                acc = fmaf(s4.z, k4.z, acc); acc = fmaf(s4.w, k4.w, acc);
+            }
+            attnT[(img * n + j) * SP + i] = acc * 0.125f;
+        }
+        __syncthreads();
+        for (int sr = warp; sr < SR; sr += HW_) {           // row sums r_bi, lane-strided then a fixed shuffle tree
+            const int img = sr / S, i = sr - img * S;
+            float s = 0.f;
+            for (int j = lane; j < n; j += 32) s += attnT[(img * n + j) * SP + i];
+            s = warp_sum(s);
+            if (lane == 0) rsum[sr] = s;
+        }
+        __syncthreads();
+        if (warp < G) {                                      // per-image totals t_b
+            float s = 0.f;
+            for (int i = lane; i < S; i += 32) s += rsum[warp * S + i];
+            s = warp_sum(s);
+            if (lane == 0) misc[warp] = s;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < SR * n; idx += HT) {      // attn = sigmoid(D / r * t)
+            const int sr = idx / n, j = idx - sr * n;
+            const int img = sr / S, i = sr - img * S;
+            float* p = attnT + (img * n + j) * SP + i;
+            const float at = sigm(*p / rsum[sr] * misc[img]);
+            *p = at;
+            if (last && img < nimg && a.attn) a.attn[((size_t)(b0 + img) * S + i) * n + j] = at;
+        }
+        __syncthreads();
+        // updates[sr][e] = sum_j attn * X / d : thread = (image, e), four slots of the image in registers
+        for (int w = tid; w < G * XD * ((S + 3) / 4); w += HT) {
+            const int e = w % XD;
+            const int rest = w / XD;
+            const int img = rest % G, i0 = (rest / G) * 4;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* xp = Xs + img * n * LDX + e;
+            const float* ap = attnT + img * n * SP + i0;
+            for (int j = 0; j < n; ++j) {
+                const float xv = xp[j * LDX];
+                const float4 a4 = *reinterpret_cast<const float4*>(ap + j * SP);
+                acc[0] = fmaf(a4.x, xv, acc[0]); acc[1] = fmaf(a4.y, xv, acc[1]);
+                acc[2] = fmaf(a4.z, xv, acc[2]); acc[3] = fmaf(a4.w, xv, acc[3]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (i0 + r < S) upd[(img * S + i0 + r) * XD + e] = acc[r] * (1.0f / XD);
+        }
+        __syncthreads();
+        if (last) {
+            for (int sr = warp; sr < SR; sr += HW_) {
+                float s = upd[sr * XD + lane] + upd[sr * XD + 32 + lane];
+                s = warp_sum(s);
+                if (lane == 0) usum[sr] = s;
+            }
+        } else {
+            if (it == 0) {
+                cp_async_wait_all();
+                __syncthreads();
+            }
+            if (tid < 2 * XG) {                              // gate pre-activations: thread = ({ih,hh}, gate column)
+                const int which = tid / XG, g = tid - which * XG;
+                const float* WT = Wsm + which * XD * XG;
+                const float bias = Wsm[2 * XD * XG + which * XG + g];
+                const float* src = which ? slots : upd;
+                for (int r0 = 0; r0 < SR; r0 += 8) {
+                    float acc[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll 4
+                    for (int e4 = 0; e4 < XD / 4; ++e4) {
+                        const float w0 = WT[(e4 * 4 + 0) * XG + g], w1 = WT[(e4 * 4 + 1) * XG + g];
+                        const float w2 = WT[(e4 * 4 + 2) * XG + g], w3 = WT[(e4 * 4 + 3) * XG + g];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const float4 v = *reinterpret_cast<const float4*>(src + min(r0 + r, SR - 1) * XD + e4 * 4);
+                            acc[r] = fmaf(v.x, w0, acc[r]); acc[r] = fmaf(v.y, w1, acc[r]);
+                            acc[r] = fmaf(v.z, w2, acc[r]); acc[r] = fmaf(v.w, w3, acc[r]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r0 + r < SR) gates[(r0 + r) * 2 * XG + which * XG + g] = acc[r] + bias;
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < SR * XD; idx += HT) {   // GRU cell, gate order [r|z|n]
+                const int sr = idx / XD, e = idx - sr * XD;
+                const float* gi = gates + sr * 2 * XG;
+                const float* gh = gi + XG;
+                const float rg_ = sigm(gi[e] + gh[e]);
+                const float zg = sigm(gi[XD + e] + gh[XD + e]);
+                const float ng = tanhf(gi[2 * XD + e] + rg_ * gh[2 * XD + e]);
+                const float hp = slots[idx];
+                slots[idx] = (hp - ng) * zg + ng;              // ATen's form of (1-z)*n + z*h
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int idx = tid; idx < nimg * a.C; idx += HT) {
+        const int img = idx / a.C, c = idx - img * a.C;
+        float s = 0.f;
+        for (int m = 0; m < a.spc; ++m) s += usum[img * S + c * a.spc + m];
+        a.logits[(size_t)(b0 + img) * a.C + c] = (float)a.loss_status * s;
+    }
+    if (a.attn_sum) {
+        for (int img = warp; img < nimg; img += HW_) {        // per-image sum of the final attention (area loss), fixed order
+            float s = 0.f;
+            for (int k = lane; k < n * S; k += 32) {
+                const int j = k / S, i = k - j * S;
+                s += attnT[(img * n + j) * SP + i];
+            }
+            s = warp_sum(s);
+            if (lane == 0) a.attn_sum[b0 + img] = s;
+        }
+    }
+    PROF_END(loop);
+    if (tid == 0) { PROF_STORE(g_prof_head, 0, phaseA); PROF_STORE(g_prof_head, 1, mlp); PROF_STORE(g_prof_head, 2, loop); }
+    cluster_wait();       // the peer may still be arriving on this CTA's barriers until it has left phase A
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+    }
+    return fn;
+}
+
+// Shared-memory map for (G, n, S, L); returns total dynamic bytes (incl. alignment slack) or 0 when it does not fit.
+//   phase A: [NA feature stages][3 weight slots] ... [to_k weights (cp.async prefetch)]
+//   phase B: [X][Ka][Kb][slots, updates, sums][GRU block] alias the rings; the GRU block also aliases the to_k weights
+//            (it is fetched after the MLP)
+size_t layout(int G, int n, int S, int L, FusedArgs* out) {
+    const int R = G * n, SR = G * S;
+    const int R8 = (R + 7) & ~7;
+    const size_t a_stage = (size_t)R8 * 128;
+    const size_t tok_end = align_up((size_t)(2 * R * LDX + kb_floats(G, n, S)) * 4, 16);
+    const size_t small = align_up((size_t)(2 * SR * XD + 2 * SR + 64) * 4, 16);
+    const size_t off_small = tok_end;
+    const size_t off_gru = off_small + small;
+    static int nw_env = [] { const char* e = getenv("SCOUTER_HEAD_NW"); int v = e ? atoi(e) : 6; return v < 2 ? 2 : (v > MAX_NW ? MAX_NW : v); }();
+    // the weight tile comes from L2 through a multicast TMA whose latency is ~2-3 k-blocks: prefer a deep weight ring, then
+    // as many feature stages as fit
+    static int na_env = [] { const char* e = getenv("SCOUTER_HEAD_NA"); int v = e ? atoi(e) : MAX_NA; return v < 2 ? 2 : (v > MAX_NA ? MAX_NA : v); }();
+    for (int nw = nw_env; nw >= 2; --nw)
+        for (int na = na_env; na >= 2; --na) {
+            const size_t off_w = na * a_stage;
+            const size_t ring_end = off_w + (size_t)nw * W_SLOT;
+            const size_t off_tokw = align_up(std::max(ring_end, off_gru), 16);
+            const size_t body = std::max(off_tokw + (size_t)L * TOK_FLOATS * 4, off_gru + (size_t)W_FLOATS * 4);
+            const size_t off_bar = align_up(body, 16);
+            const size_t total = off_bar + 512 + 1024;
+            if (total <= 227 * 1024) {
+                if (out) {
+                    out->na = na; out->nw = nw; out->a_stage = (int)a_stage; out->off_w = (int)off_w;
+                    out->off_tokw = (int)off_tokw; out->off_gru = (int)off_gru; out->off_small = (int)off_small; out->off_bar = (int)off_bar;
+                }
+                return total;
+            }
+        }
+    return 0;
+}
+
+__global__ void split_w_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float v = w[i];
+    out[i] = __float2bfloat16_rn(v);
+    out[count + i] = __float2bfloat16_rn(v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u));
+}
+
+}  // namespace
+
+bool head_fused_supported(const scouter_xslot_desc_t* d, int batch, int n, int channel) {
+    static bool off = getenv("SCOUTER_NO_FUSED_HEAD") != nullptr;
+    const int S = d->num_classes * d->slots_per_class;
+    if (off || n > 128 || S > 32 || channel % 32 || d->to_k_layers < 1) return false;
+    const int G = std::max(1, std::min(128 / n, batch));
+    if (S * G > 128) return false;
+    return layout(G, n, S, d->to_k_layers, nullptr) != 0 && encode_fn() != nullptr;
+}
+
+size_t head_fused_workspace_bytes(int channel) { return align_up((size_t)2 * XD * channel * 2, 1024); }
+
+int head_fused_launch(const scouter_xslot_desc_t* d, const void* packed, const scouter_head_io_t* io, const float* feat_nhwc,
+                      void* workspace, cudaStream_t s) {
+    const int n = io->h * io->w;
+    FusedArgs a;
+    a.conv_b = io->conv_b; a.packed = (const float*)packed; a.pe = io->pe;
+    a.x_out = io->x_out; a.logits = io->logits; a.attn = io->attn; a.attn_sum = io->attn_sum;
+    a.B = io->batch; a.n = n; a.G = std::max(1, std::min(128 / n, io->batch));
+    a.S = d->num_classes * d->slots_per_class; a.C = d->num_classes; a.spc = d->slots_per_class; a.L = d->to_k_layers;
+    a.iters = d->iters; a.loss_status = d->loss_status;
+    a.kblocks = io->channel / 32;
+    static int issue_batch = [] { const char* e = getenv("SCOUTER_HEAD_BATCH"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    const size_t smem = layout(a.G, n, a.S, a.L, &a);
+    SC_CHECK_ARG(smem, SCOUTER_E_UNSUPPORTED, "head_fused: shared-memory layout does not fit");
+    a.issue_batch = std::min(issue_batch, a.na);
+    static int blocked = getenv("SCOUTER_HEAD_BLOCKED") != nullptr;   // timing experiment only
+    a.blocked = blocked;
+    EncodeTiledFn enc = encode_fn();
+    SC_CHECK_ARG(enc, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled is not available from the driver");
+    // bf16 [W ; W - trunc19(W)] of conv1x1.weight: given by the caller (packed once per parameter version) or derived here
+    const void* w_split = io->conv_w_split;
+    if (!w_split) {
+        const int count = XD * io->channel;
+        split_w_bf16_kernel<<<cdiv(count, 256), 256, 0, s>>>(io->conv_w, (__nv_bfloat16*)workspace, count);
+        SC_LAUNCH_CHECK();
+        w_split = workspace;
+    }
+    const int R = a.G * n;
+    const long long M = (long long)io->batch * n;
+    CUtensorMap tmA, tmB, tmB2;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)io->channel, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)io->channel * 4};
+        cuuint32_t box[2] = {32, (cuuint32_t)R};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r;
+        if (a.blocked) {
+            cuuint64_t dims3[3] = {32, (cuuint64_t)M, (cuuint64_t)io->channel / 32};
+            cuuint64_t strides3[2] = {128, (cuuint64_t)M * 128};
+            cuuint32_t box3[3] = {32, (cuuint32_t)R, 1};
+            cuuint32_t es3[3] = {1, 1, 1};
+            r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)feat_nhwc, dims3, strides3, box3, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else
+        r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)feat_nhwc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled(features) failed with %d", (int)r);
+        cuuint64_t dimsB[2] = {(cuuint64_t)io->channel, (cuuint64_t)XD};
+        cuuint32_t boxB[2] = {32, (cuuint32_t)XD};
+        r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)io->conv_w, dimsB, strides, boxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled(conv1x1.weight) failed with %d", (int)r);
+        cuuint64_t dimsB2[2] = {(cuuint64_t)io->channel, (cuuint64_t)2 * XD};
+        cuuint64_t stridesB2[1] = {(cuuint64_t)io->channel * 2};
+        cuuint32_t boxB2[2] = {32, (cuuint32_t)2 * XD};
+        r = enc(&tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_split, dimsB2, stridesB2, boxB2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled(bf16 weight pair) failed with %d", (int)r);
+    }
+    SC_CUDA(cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int units = cdiv(io->batch, a.G);
+    head_fused_kernel<<<2 * cdiv(units, 2), HT, smem, s>>>(tmA, tmB, tmB2, a);   // clusters of two (padding CTA when odd)
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace scouter
+
+#ifdef SCOUTER_PROF
+extern "C" int scouter_prof_read_head(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, scouter::g_prof_head, sizeof(unsigned long long) * n);
+}
+extern "C" int scouter_trace_read_head(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, scouter::g_trace_head, sizeof(unsigned long long) * n);
+}
+#endif

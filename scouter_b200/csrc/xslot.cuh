@@ -42,4 +42,11 @@ struct XSlotFastIO {
 bool xslot_fast_supported(const scouter_xslot_desc_t* d, int n);
 int xslot_fast_launch(const scouter_xslot_desc_t* d, const void* packed, const XSlotFastIO& io, cudaStream_t s);
 
+
+// Whole head in one kernel (head_fused.cu): projection on the tensor cores feeding the loop through shared memory.
+bool head_fused_supported(const scouter_xslot_desc_t* d, int batch, int n, int channel);
+size_t head_fused_workspace_bytes(int channel);   // bf16 [W ; W_r] of conv1x1.weight when the caller does not supply it
+int head_fused_launch(const scouter_xslot_desc_t* d, const void* packed, const scouter_head_io_t* io, const float* feat_nhwc,
+                      void* workspace, cudaStream_t s);
+
 }  // namespace scouter

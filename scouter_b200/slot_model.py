@@ -167,6 +167,15 @@ class SlotModel(nn.Module):
                 raise L.ScouterError("SlotModel: conv1x1 parameters must be contiguous fp32 on the input's device")
         st.io.conv_w = self.conv1x1.weight.data_ptr()
         st.io.conv_b = self.conv1x1.bias.data_ptr()
+        # bf16 [W ; W - trunc19(W)] for the fused head's correction products, re-packed when the parameter changes
+        w = self.conv1x1.weight
+        key = (w.data_ptr(), w._version, dev)
+        if getattr(self, "_conv_w_split_key", None) != key:
+            from .plan import split_weights_bf16
+            with torch.no_grad():
+                self._conv_w_split = split_weights_bf16(w.detach().reshape(w.shape[0], -1))
+            self._conv_w_split_key = key
+        st.io.conv_w_split = self._conv_w_split.data_ptr()
         desc, packed = self.slot.desc_and_pack(dev)
         if st.ws is None:
             nbytes = L.lib().scouter_head_workspace_bytes(C.byref(desc), C.byref(st.io))

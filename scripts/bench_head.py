@@ -1,0 +1,97 @@
+"""Times scouter_head_forward alone (debug tool; the judged number comes from bench.py's `roofline`).
+
+python scripts/bench_head.py [--batch 256] [--fs 7] [--classes 10] [--spc 1] [--prof]
+--prof loads the -DSCOUTER_PROF build (scripts/prof_roles.py --build-only) and prints the per-phase clocks of the
+fused kernel.  SCOUTER_NO_FUSED_HEAD=1 selects the two-kernel path."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import scouter_b200 as sb  # noqa: E402
+from scouter_b200 import _lib as L  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--fs", type=int, default=7)
+ap.add_argument("--ch", type=int, default=2048)
+ap.add_argument("--classes", type=int, default=10)
+ap.add_argument("--spc", type=int, default=1)
+ap.add_argument("--layers", type=int, default=3)
+ap.add_argument("--iters", type=int, default=50)
+ap.add_argument("--prof", action="store_true")
+a = ap.parse_args()
+if a.prof:
+    L.LIB_PATH = os.path.join(ROOT, "scouter_b200", "libscouter_b200_prof.so")
+lib = L.lib()
+dev = torch.device("cuda", 0)
+B, n, ch = a.batch, a.fs * a.fs, a.ch
+r = np.random.RandomState(5)
+feat = torch.from_numpy(np.maximum(r.standard_normal((B, n, ch)), 0).astype(np.float32)).to(dev)
+w = torch.from_numpy((r.standard_normal((64, ch)) / np.sqrt(ch)).astype(np.float32)).to(dev)
+b = torch.from_numpy(0.1 * r.standard_normal(64).astype(np.float32)).to(dev)
+m = sb.SlotAttention(a.classes, a.spc, 64, to_k_layer=a.layers, power=2).to(dev).eval()
+desc, packed = m.desc_and_pack(dev)
+pe = sb.build_position_encoding("sine", 64).table(a.fs, a.fs, dev)
+S = a.classes * a.spc
+logits = torch.empty(B, a.classes, device=dev)
+attn = torch.empty(B, S, n, device=dev)
+asum = torch.empty(B, device=dev)
+io = L.HeadIO()
+io.batch, io.h, io.w, io.channel, io.layout, io.math = B, a.fs, a.fs, ch, L.LAYOUT_NHWC, L.MATH_TC
+io.feat, io.conv_w, io.conv_b, io.pe = feat.data_ptr(), w.data_ptr(), b.data_ptr(), pe.data_ptr()
+io.logits, io.attn, io.attn_sum, io.x_out = logits.data_ptr(), attn.data_ptr(), asum.data_ptr(), 0
+from scouter_b200.plan import split_weights_bf16  # noqa: E402
+w_split = split_weights_bf16(w)
+io.conv_w_split = w_split.data_ptr()
+nbytes = lib.scouter_head_workspace_bytes(C.byref(desc), C.byref(io))
+ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+off = (-ws.data_ptr()) % 1024
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def run():
+    L.check(lib.scouter_head_forward(C.byref(desc), packed.data_ptr(), C.byref(io), ws.data_ptr() + off, nbytes,
+                                     torch.cuda.current_stream().cuda_stream))
+
+
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+ref_logits = logits.clone()
+ts = []
+for _ in range(a.iters):
+    flush.zero_()                      # evict the features from L2: the head reads them from HBM in the forward too
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+assert torch.equal(ref_logits, logits) or "SCOUTER_HEAD_BLOCKED" in os.environ, "head is not bit-reproducible"
+ts = np.array(ts)
+alg = B * n * ch * 4 + B * a.classes * 4 + B * S * n * 4
+peak = 6545.9
+print(f"head B={B} n={n} S={S} L={a.layers} fused={'SCOUTER_NO_FUSED_HEAD' not in os.environ}: median {np.median(ts):.1f} us, "
+      f"min {ts.min():.1f} us; algorithmic {alg / 1e6:.1f} MB -> {alg / np.median(ts) / 1e3:.0f} GB/s = "
+      f"{alg / np.median(ts) / 1e3 / peak:.3f} of {peak} GB/s")
+if a.prof:
+    units = (B + max(1, min(128 // n, B)) - 1) // max(1, min(128 // n, B))
+    buf = (C.c_ulonglong * (256 * 32))()
+    rc = lib.scouter_prof_read_head(buf, 256 * 32)
+    arr = np.array(buf[:], dtype=np.float64).reshape(256, 32)[:min(units, 256)]
+    names = {0: "phaseA", 1: "mlp", 2: "loop", 3: "prodA.wait_empty", 4: "prodW.wait_done", 5: "iss0.wait_cempty", 6: "iss0.wait_opfull",
+             7: "split0.wait_fullA", 8: "split0.wait_done", 9: "split0.wait_fullW", 10: "split0.tmem_st"}
+    print("per-CTA clocks (mean / max):", {names.get(i, i): (int(arr[:, i].mean()), int(arr[:, i].max())) for i in range(12) if arr[:, i].any()})
+    tb = (C.c_ulonglong * (128 * 8))()
+    lib.scouter_trace_read_head(tb, 128 * 8)
+    tr = np.array(tb[:], dtype=np.int64).reshape(128, 8)[:ch // 32]
+    t0 = tr[tr > 0].min()
+    print("trace (CTA 0, clocks since first event): kb prodA prodW sp.fullA sp.done sp.opfull is.opfull is.fullW is.commit")
+    for kb in range(tr.shape[0]):
+        print(kb, " ".join(f"{int(v - t0):7d}" for v in tr[kb]))

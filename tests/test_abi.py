@@ -19,7 +19,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = L.lib()
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.scouter_abi_version() == 1
+    assert lib.scouter_abi_version() == 2
 
 
 def test_argument_errors_without_gpu():
