@@ -66,7 +66,7 @@ struct FusedArgs {
     int na, nw, a_stage, off_w;
     int issue_batch;   // feature stages issued back to back (longer contiguous runs per feature row at the DRAM)
     int blocked;       // features are channel-block major: (ch/32, B*n, 32)
-    int off_tokw, off_gru, off_small, off_bar;
+    int off_gru, off_small, off_bar;
 };
 
 __host__ __device__ inline int kb_floats(int img, int n, int S) {
@@ -80,6 +80,31 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// updates: partial sum over the tokens j = j0, j0+jstep, ... of attn[j][i] * X[j][e..e+3] for C4*4 consecutive slots
+template <int C4>
+__device__ __forceinline__ void update_partial(const float* __restrict__ xp /* X[img][0][e] */, const float* __restrict__ ap /* attnT[img][0][i0] */,
+                                               int n, int SP, int j0, int jstep, float* __restrict__ out /* upart[..][i0][e] */, int nslots) {
+    float4 acc[4 * C4];
+#pragma unroll
+    for (int i = 0; i < 4 * C4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = j0; j < n; j += jstep) {
+        const float4 xv = *reinterpret_cast<const float4*>(xp + j * LDX);
+#pragma unroll
+        for (int c = 0; c < C4; ++c) {
+            const float4 a4 = *reinterpret_cast<const float4*>(ap + j * SP + 4 * c);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float4& o = acc[4 * c + t];
+                o.x = fmaf(av[t], xv.x, o.x); o.y = fmaf(av[t], xv.y, o.y); o.z = fmaf(av[t], xv.z, o.z); o.w = fmaf(av[t], xv.w, o.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * C4; ++i)
+        if (i < nslots) *reinterpret_cast<float4*>(out + i * XD) = acc[i];
+}
+
 #ifdef SCOUTER_PROF
 __device__ unsigned long long g_prof_head[256 * 32];
 __device__ unsigned long long g_trace_head[128 * 8];   // CTA 0: [k-block][event] clock64 timestamps
@@ -90,7 +115,8 @@ __device__ unsigned long long g_trace_head[128 * 8];   // CTA 0: [k-block][event
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HT, 1)
 head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmB2, const FusedArgs a) {
+                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmT,
+                  const __grid_constant__ CUtensorMap tmT2, const FusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int n = a.n, S = a.S, G = a.G;
@@ -110,14 +136,15 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* opfull = fullW + MAX_NW;      // [NO] operands of the k-block are in TMEM
     uint64_t* cfull = opfull + NO;          // [2 issuers][2] accumulator chunk complete
     uint64_t* cempty = cfull + 4;           // [2][2] chunk drained by the 128 accumulator owners
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cempty + 4);
+    uint64_t* mlp_in = cempty + 4;          // to_k layer input is in TMEM (128 accumulator owners)
+    uint64_t* mlp_out = mlp_in + 1;         // to_k layer MMAs retired
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mlp_out + 1);
 
     // phase-B views
     const int SP = (S + 3) & ~3;
     float* Xs = reinterpret_cast<float*>(smem);   // [R][LDX]
     float* Ka = Xs + R * LDX;                      // [R][LDX]
     float* Kb = Ka + R * LDX;                      // MLP ping-pong; afterwards gates / attention scratch
-    float* Wtok = reinterpret_cast<float*>(smem + a.off_tokw);   // to_k layers (beyond the rings: prefetched in phase A)
     float* Wsm = reinterpret_cast<float*>(smem + a.off_gru);     // GRU block (aliases rings / to_k weights; loaded after the MLP)
     float* slots = reinterpret_cast<float*>(smem + a.off_small); // [SR][64]
     float* upd = slots + SR * XD;
@@ -126,13 +153,13 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* misc = usum + SR;
     float* gates = Kb;
     float* attnT = Kb + SR * 2 * XG;
-    float* kin = (a.L & 1) ? Kb : Ka;              // after L ping-pong layers the keys end up in Ka
-    float* kout = (a.L & 1) ? Ka : Kb;
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         prefetch_tmap(&tmB2);
+        prefetch_tmap(&tmT);
+        prefetch_tmap(&tmT2);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < MAX_NA; ++i) {
@@ -146,6 +173,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&cfull[i], 1);
             mbar_init(&cempty[i], 128);
         }
+        mbar_init(mlp_in, 128);
+        mbar_init(mlp_out, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -205,6 +234,15 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 TRACE(kb, 1);
                 if (++ws == NW) ws = 0;
             }
+            // the to_k layers ride the same weight stream: layer l = two more "k-blocks" (its two 32-channel halves)
+            for (int v = 0; v < 2 * a.L; ++v) {
+                const int kb = kblocks + v, j = kb - NW;
+                if (j >= 0) mbar_wait(&done[j & (ND - 1)], (uint32_t)(j >> 3) & 1u);
+                mbar_arrive_expect_tx(&fullW[ws], (uint32_t)W_SLOT);
+                if (rank == 0) tma_load_2d_mc(w_ring + ws * W_SLOT, &tmT, &fullW[ws], (v & 1) * 32, (v >> 1) * XD, (uint16_t)3);
+                else tma_load_2d_mc(w_ring + ws * W_SLOT + W_F32, &tmT2, &fullW[ws], (v & 1) * 32, (v >> 1) * 2 * XD, (uint16_t)3);
+                if (++ws == NW) ws = 0;
+            }
             PROF_STORE(g_prof_head, 4, pw_wait);
         }
     } else if (warp == 1 || warp == 2) {
@@ -252,13 +290,39 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
             if (w == 0) { PROF_STORE(g_prof_head, 5, is_cempty); PROF_STORE(g_prof_head, 6, is_op); }
+            if (w == 0) {
+                // ----- to_k MLP: D[token, out] = A[token, in] * W_l^T, A = the previous layer's activations, re-split and
+                //       stored to TMEM by the accumulator owners; same error-compensated product, 16 MMAs per layer -----
+                const uint32_t a_tm = tmem_base + OP_COL0;     // [fp32 (64) | bf16 (32) | bf16 remainder (32)]
+                for (int l = 0; l < a.L; ++l) {
+                    mbar_wait(mlp_in, (uint32_t)l & 1u);
+                    tc_fence_after();
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int kb = kblocks + 2 * l + kk;
+                        const int ws2 = kb % NW;
+                        mbar_wait_a(fullw_a + 8 * ws2, (uint32_t)(kb / NW) & 1u);
+                        tc_fence_after();
+                        const uint32_t w_lo = w_lo0 + (uint32_t)ws2 * (W_SLOT >> 4);
+#pragma unroll
+                        for (uint32_t k = 0; k < 2; ++k)   // A * W_r
+                            umma_bf16_ts(tmem_base, a_tm + 64 + 16 * kk + 8 * k,
+                                         desc_make(DESC_HI_SW64, w_lo + ((W_F32 + W_F32 / 2) >> 4) + 2 * k), idesc_b, (uint32_t)kk | k);
+#pragma unroll
+                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W
+                            umma_bf16_ts(tmem_base, a_tm + 96 + 16 * kk + 8 * k, desc_make(DESC_HI_SW64, w_lo + (W_F32 >> 4) + 2 * k), idesc_b, 1);
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
+                            umma_tf32_ts(tmem_base, a_tm + 32 * kk + 8 * k, desc_make(DESC_HI_SW128, w_lo + 2 * k), idesc, 1);
+                        umma_commit_mc_a(done_a + 8 * (kb & (ND - 1)), (uint16_t)3);
+                    }
+                    umma_commit(mlp_out);
+                }
+            }
         }
     } else if (warp >= 4 && warp < 8) {
         // ----- accumulator owners: thread = token row, 64 running fp32 sums starting from the bias -----
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        for (int i = tid - 128; i < a.L * TOK_FLOATS / 4; i += 128)   // to_k weights -> shared memory, behind the stream
-            cp_async16(Wtok + i * 4, a.packed + pk.tok_wt(0) + i * 4);
         float acc[XD];
 #pragma unroll
         for (int j = 0; j < XD / 4; ++j) {
@@ -285,10 +349,32 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_arrive(&cempty[2 * w + buf]);
             }
         }
-        // every MMA has retired (the last commits cover them all): the rings are dead, X and X + PE take their place
-        if (row < R) {
-            const int img = row / n, j = row - img * n;
-            const bool live = img < nimg;
+        // every conv MMA has retired (the last commits cover them all): the feature ring is dead, X takes its place
+        const bool rowv = row < R;
+        const int img = rowv ? row / n : 0, j = rowv ? row - img * n : 0;
+        const bool live = rowv && img < nimg;
+        const uint32_t t_op = tmem_base + ((uint32_t)(q * 32) << 16) + OP_COL0;
+        auto to_tmem = [&](const float (&v)[XD]) {        // fp32 | bf16 | bf16 remainder forms of this row's 64 activations
+            uint32_t f[32], xb[16], rb[16];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float x0 = v[32 * h + 2 * i], x1 = v[32 * h + 2 * i + 1];
+                    f[2 * i] = __float_as_uint(x0); f[2 * i + 1] = __float_as_uint(x1);
+                    const float r0 = x0 - __uint_as_float(f[2 * i] & 0xFFFFE000u), r1 = x1 - __uint_as_float(f[2 * i + 1] & 0xFFFFE000u);
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xb[i]) : "f"(x1), "f"(x0));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rb[i]) : "f"(r1), "f"(r0));
+                }
+                tmem_st_32x32(t_op + 32 * h, f);
+                tmem_st_32x16(t_op + 64 + 16 * h, xb);
+                tmem_st_32x16(t_op + 96 + 16 * h, rb);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(mlp_in);
+        };
+        {
             float* xo = (a.x_out && live) ? a.x_out + ((size_t)(b0 + img) * n + j) * XD : nullptr;
 #pragma unroll
             for (int e4 = 0; e4 < XD / 4; ++e4) {
@@ -296,12 +382,40 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                         fmaxf(acc[4 * e4 + 3], 0.f));
                 if (!live) xv = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 pv = __ldg(reinterpret_cast<const float4*>(a.pe + j * XD + e4 * 4));
-                *reinterpret_cast<float4*>(Xs + row * LDX + e4 * 4) = xv;
-                *reinterpret_cast<float4*>(kin + row * LDX + e4 * 4) = make_float4(xv.x + pv.x, xv.y + pv.y, xv.z + pv.z, xv.w + pv.w);
+                if (rowv) *reinterpret_cast<float4*>(Xs + row * LDX + e4 * 4) = xv;
                 if (xo) *reinterpret_cast<float4*>(xo + e4 * 4) = xv;
+                acc[4 * e4] = xv.x + pv.x; acc[4 * e4 + 1] = xv.y + pv.y; acc[4 * e4 + 2] = xv.z + pv.z; acc[4 * e4 + 3] = xv.w + pv.w;
             }
         }
-        cp_async_wait_all();
+        to_tmem(acc);
+        for (int l = 0; l < a.L; ++l) {
+            const bool lastl = l + 1 == a.L;
+            const float* bp = a.packed + pk.tok_b(l);
+            mbar_wait(mlp_out, (uint32_t)l & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < XD / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + c * 32 + 4 * i4));
+                    float v0 = __uint_as_float(r[4 * i4]) + bv.x, v1 = __uint_as_float(r[4 * i4 + 1]) + bv.y;
+                    float v2 = __uint_as_float(r[4 * i4 + 2]) + bv.z, v3 = __uint_as_float(r[4 * i4 + 3]) + bv.w;
+                    if (!lastl) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                    acc[c * 32 + 4 * i4] = v0; acc[c * 32 + 4 * i4 + 1] = v1; acc[c * 32 + 4 * i4 + 2] = v2; acc[c * 32 + 4 * i4 + 3] = v3;
+                }
+            }
+            if (!lastl) {
+                tc_fence_before();
+                to_tmem(acc);
+            } else if (rowv) {
+#pragma unroll
+                for (int e4 = 0; e4 < XD / 4; ++e4)
+                    *reinterpret_cast<float4*>(Ka + row * LDX + e4 * 4) = make_float4(acc[4 * e4], acc[4 * e4 + 1], acc[4 * e4 + 2], acc[4 * e4 + 3]);
+            }
+        }
     } else if (warp >= 8) {
         // ----- splitters: two groups of four warps on alternate k-blocks; thread = token row -----
         const int sg = (warp - 8) >> 2;
@@ -362,151 +476,154 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // =========================================== phase B ===========================================================
     for (int idx = tid; idx < SR * XD; idx += HT) slots[idx] = __ldg(a.packed + pk.slots() + (idx % (S * XD)));
 
-    // ---- to_k MLP: thread = output feature o (weights of its column in registers), 4 token rows at a time ---------
-    {
-        const int o = tid % XD, rg = tid / XD;   // 8 row groups
-        for (int l = 0; l < a.L; ++l) {
-            const float* WT = Wtok + l * TOK_FLOATS;
-            float wreg[XD];
-#pragma unroll
-            for (int e = 0; e < XD; ++e) wreg[e] = WT[e * XD + o];
-            const float bias = WT[XD * XD + o];
-            const bool relu = l + 1 < a.L;
-            for (int j0 = rg * 4; j0 < R; j0 += (HT / XD) * 4) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const float* r0 = kin + min(j0 + 0, R - 1) * LDX;
-                const float* r1 = kin + min(j0 + 1, R - 1) * LDX;
-                const float* r2 = kin + min(j0 + 2, R - 1) * LDX;
-                const float* r3 = kin + min(j0 + 3, R - 1) * LDX;
-#pragma unroll
-                for (int e4 = 0; e4 < XD / 4; ++e4) {
-                    const float4 v0 = *reinterpret_cast<const float4*>(r0 + e4 * 4);
-                    const float4 v1 = *reinterpret_cast<const float4*>(r1 + e4 * 4);
-                    const float4 v2 = *reinterpret_cast<const float4*>(r2 + e4 * 4);
-                    const float4 v3 = *reinterpret_cast<const float4*>(r3 + e4 * 4);
-                    acc[0] = fmaf(v0.x, wreg[e4 * 4 + 0], acc[0]); acc[1] = fmaf(v1.x, wreg[e4 * 4 + 0], acc[1]);
-                    acc[2] = fmaf(v2.x, wreg[e4 * 4 + 0], acc[2]); acc[3] = fmaf(v3.x, wreg[e4 * 4 + 0], acc[3]);
-                    acc[0] = fmaf(v0.y, wreg[e4 * 4 + 1], acc[0]); acc[1] = fmaf(v1.y, wreg[e4 * 4 + 1], acc[1]);
-                    acc[2] = fmaf(v2.y, wreg[e4 * 4 + 1], acc[2]); acc[3] = fmaf(v3.y, wreg[e4 * 4 + 1], acc[3]);
-                    acc[0] = fmaf(v0.z, wreg[e4 * 4 + 2], acc[0]); acc[1] = fmaf(v1.z, wreg[e4 * 4 + 2], acc[1]);
-                    acc[2] = fmaf(v2.z, wreg[e4 * 4 + 2], acc[2]); acc[3] = fmaf(v3.z, wreg[e4 * 4 + 2], acc[3]);
-                    acc[0] = fmaf(v0.w, wreg[e4 * 4 + 3], acc[0]); acc[1] = fmaf(v1.w, wreg[e4 * 4 + 3], acc[1]);
-                    acc[2] = fmaf(v2.w, wreg[e4 * 4 + 3], acc[2]); acc[3] = fmaf(v3.w, wreg[e4 * 4 + 3], acc[3]);
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    if (j0 + r < R) {
-                        const float v = acc[r] + bias;
-                        kout[(j0 + r) * LDX + o] = relu ? fmaxf(v, 0.f) : v;
-                    }
-            }
-            __syncthreads();
-            float* t = kin; kin = kout; kout = t;
-        }
-    }
     PROF_END(mlp); PROF_BEGIN(loop);
     const float* K = Ka;
     // the to_k weights (and the ring) are dead: bring in the GRU block while the first attention pass runs
     if (a.iters > 1)
         for (int i = tid; i < W_FLOATS / 4; i += HT) cp_async16(Wsm + i * 4, a.packed + pk.gru_wih_t() + i * 4);
 
+    // Thread maps of the loop, computed once (no runtime integer division inside the iterations).  The shared-memory
+    // pipe delivers one wavefront per clock per SM against four FMA issue slots: every map below keeps its operands in
+    // registers across as many FMAs as possible.
+    //   dots / sigmoid: thread = (slot subset dq, token row dr): key row in registers, the subset's slot rows broadcast
+    //   update:         thread = (token subset uq, image, slot chunk, feature quad): <= 16 slots x 4 features in registers;
+    //                   the token subsets are merged in fixed order
+    //   gates:          thread = (row tile, {ih,hh}, gate quad): 4 slot rows x 4 gate columns in registers; 15 warps busy,
+    //                   i.e. the 491k MACs of a GRU step spread evenly over the four FMA issue ports
+    const int nq = min(HT / R, S);                   // slot subsets
+    const int sps = (S + nq - 1) / nq;               // slots per subset
+    const int dq = tid / R, dr = tid - dq * R;
+    const int dimg = dr / n, dj = dr - dimg * n;
+    const bool d_on = dq < nq && dq * sps < S;
+    const int di0 = dq * sps, di1 = min(S, di0 + sps);
+    const bool d_live = dimg < nimg;
+    const int SP4 = SP / 4, nsc = (SP4 + 3) / 4;     // slot quads per image, slot chunks of <= 4 quads
+    const int upt = G * nsc * 16;                    // update threads per token subset
+    const int nuq = min(6, HT / upt);                // 6 * 64 floats per slot row: the partials fit the gate scratch they alias
+    const int uq = tid / upt, ur = tid - uq * upt;
+    const int uimg = ur / (nsc * 16), usc = (ur / 16) % nsc, ue4 = ur % 16;
+    const int uc4 = min(4, SP4 - 4 * usc), ui0 = 16 * usc;
+    float* upart = gates;                            // [nuq][SR][64] partial updates (dead before the gates are written)
+    const int gct = tid % 96, grt = tid / 96;        // gates: column tile (48 quads x {ih,hh}), row-tile group (5 groups)
+    const int gwhich = gct / 48, gg0 = (gct - gwhich * 48) * 4;
+    constexpr int GR = 4;                            // slot rows per gate tile
+    const int n_rt = (SR + GR - 1) / GR;
+    const int rs_img0 = warp / S, rs_i0 = warp - rs_img0 * S;                  // row sums: this warp's first two slot rows
+    const int rs_img1 = (warp + HW_) / S, rs_i1 = warp + HW_ - rs_img1 * S;
+
+#ifdef SCOUTER_PROF
+    long long lp_t = clock64(), lp_acc[6] = {0, 0, 0, 0, 0, 0};
+#define LP_STAMP(k) do { const long long _n = clock64(); lp_acc[k] += _n - lp_t; lp_t = _n; } while (0)
+#else
+#define LP_STAMP(k)
+#endif
     for (int it = 0; it < a.iters; ++it) {
         const bool last = it == a.iters - 1;
-        for (int idx = tid; idx < SR * n; idx += HT) {      // dots[img][i][j] = scale * <slot, key>, kept as attnT[img][j][i]
-            const int sr = idx / n, j = idx - sr * n;
-            const int img = sr / S, i = sr - img * S;
-            const float4* sp = reinterpret_cast<const float4*>(slots + sr * XD);
-            const float4* kp = reinterpret_cast<const float4*>(K + (img * n + j) * LDX);
-            float acc = 0.f;
+        if (d_on) {                                  // dots[img][i][j] = scale * <slot, key>, kept as attnT[img][j][i]
+            float4 kreg[XD / 4];
+            const float4* kp = reinterpret_cast<const float4*>(K + dr * LDX);
 #pragma unroll
-            for (int e4 = 0; e4 < XD / 4; ++e4) {
-                const float4 s4 = sp[e4], k4 = kp[e4];
-                acc = fmaf(s4.x, k4.x, acc); acc = fmaf(s4.y, k4.y, acc);
-                acc = fmaf(s4.z, k4.z, acc); acc = fmaf(s4.w, k4.w, acc);
-            }
-            attnT[(img * n + j) * SP + i] = acc * 0.125f;
-        }
-        __syncthreads();
-        for (int sr = warp; sr < SR; sr += HW_) {           // row sums r_bi, lane-strided then a fixed shuffle tree
-            const int img = sr / S, i = sr - img * S;
-            float s = 0.f;
-            for (int j = lane; j < n; j += 32) s += attnT[(img * n + j) * SP + i];
-            s = warp_sum(s);
-            if (lane == 0) rsum[sr] = s;
-        }
-        __syncthreads();
-        if (warp < G) {                                      // per-image totals t_b
-            float s = 0.f;
-            for (int i = lane; i < S; i += 32) s += rsum[warp * S + i];
-            s = warp_sum(s);
-            if (lane == 0) misc[warp] = s;
-        }
-        __syncthreads();
-        for (int idx = tid; idx < SR * n; idx += HT) {      // attn = sigmoid(D / r * t)
-            const int sr = idx / n, j = idx - sr * n;
-            const int img = sr / S, i = sr - img * S;
-            float* p = attnT + (img * n + j) * SP + i;
-            const float at = sigm(*p / rsum[sr] * misc[img]);
-            *p = at;
-            if (last && img < nimg && a.attn) a.attn[((size_t)(b0 + img) * S + i) * n + j] = at;
-        }
-        __syncthreads();
-        // updates[sr][e] = sum_j attn * X / d : thread = (image, e), four slots of the image in registers
-        for (int w = tid; w < G * XD * ((S + 3) / 4); w += HT) {
-            const int e = w % XD;
-            const int rest = w / XD;
-            const int img = rest % G, i0 = (rest / G) * 4;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const float* xp = Xs + img * n * LDX + e;
-            const float* ap = attnT + img * n * SP + i0;
-            for (int j = 0; j < n; ++j) {
-                const float xv = xp[j * LDX];
-                const float4 a4 = *reinterpret_cast<const float4*>(ap + j * SP);
-                acc[0] = fmaf(a4.x, xv, acc[0]); acc[1] = fmaf(a4.y, xv, acc[1]);
-                acc[2] = fmaf(a4.z, xv, acc[2]); acc[3] = fmaf(a4.w, xv, acc[3]);
-            }
+            for (int e4 = 0; e4 < XD / 4; ++e4) kreg[e4] = kp[e4];
+            for (int i = di0; i < di1; ++i) {
+                const float4* sp = reinterpret_cast<const float4*>(slots + (dimg * S + i) * XD);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (i0 + r < S) upd[(img * S + i0 + r) * XD + e] = acc[r] * (1.0f / XD);
+                for (int e4 = 0; e4 < XD / 4; ++e4) {
+                    const float4 s4 = sp[e4];
+                    a0 = fmaf(s4.x, kreg[e4].x, a0); a1 = fmaf(s4.y, kreg[e4].y, a1);
+                    a2 = fmaf(s4.z, kreg[e4].z, a2); a3 = fmaf(s4.w, kreg[e4].w, a3);
+                }
+                attnT[dr * SP + i] = ((a0 + a1) + (a2 + a3)) * 0.125f;
+            }
         }
         __syncthreads();
+        LP_STAMP(0);
+        for (int sr = warp, k = 0; sr < SR; sr += HW_, ++k) {   // row sums r_bi, lane-strided then a fixed shuffle tree
+            int img, i;
+            if (k == 0) { img = rs_img0; i = rs_i0; } else if (k == 1) { img = rs_img1; i = rs_i1; } else { img = sr / S; i = sr - img * S; }
+            float s_ = 0.f;
+            for (int j = lane; j < n; j += 32) s_ += attnT[(img * n + j) * SP + i];
+            s_ = warp_sum(s_);
+            if (lane == 0) rsum[sr] = s_;
+        }
+        __syncthreads();
+        if (d_on) {                                  // attn = sigmoid(D / r * t), in place; t_b summed in fixed order by every thread
+            const float* rs = rsum + dimg * S;
+            float t_ = 0.f;
+            for (int i = 0; i < S; ++i) t_ += rs[i];
+            for (int i = di0; i < di1; ++i) {
+                float* p = attnT + dr * SP + i;
+                const float at = sigm(*p / rs[i] * t_);
+                *p = at;
+                if (last && d_live && a.attn) a.attn[((size_t)(b0 + dimg) * S + i) * n + dj] = at;
+            }
+        }
+        __syncthreads();
+        LP_STAMP(1);
+        if (uq < nuq) {                              // updates[sr][e] = sum_j attn * X / d
+            const float* xp = Xs + uimg * n * LDX + ue4 * 4;
+            const float* ap = attnT + uimg * n * SP + ui0;
+            float* out = upart + ((size_t)(uq * SR + uimg * S + ui0)) * XD + ue4 * 4;
+            const int ns = S - ui0;
+            switch (uc4) {
+                case 1: update_partial<1>(xp, ap, n, SP, uq, nuq, out, ns); break;
+                case 2: update_partial<2>(xp, ap, n, SP, uq, nuq, out, ns); break;
+                case 3: update_partial<3>(xp, ap, n, SP, uq, nuq, out, ns); break;
+                default: update_partial<4>(xp, ap, n, SP, uq, nuq, out, ns); break;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < SR * XD; idx += HT) {     // merge the token subsets in fixed order
+            float s_ = upart[idx];
+            for (int q = 1; q < nuq; ++q) s_ += upart[q * SR * XD + idx];
+            upd[idx] = s_ * (1.0f / XD);
+        }
+        __syncthreads();
+        LP_STAMP(2);
         if (last) {
             for (int sr = warp; sr < SR; sr += HW_) {
-                float s = upd[sr * XD + lane] + upd[sr * XD + 32 + lane];
-                s = warp_sum(s);
-                if (lane == 0) usum[sr] = s;
+                float s_ = upd[sr * XD + lane] + upd[sr * XD + 32 + lane];
+                s_ = warp_sum(s_);
+                if (lane == 0) usum[sr] = s_;
             }
         } else {
             if (it == 0) {
                 cp_async_wait_all();
                 __syncthreads();
             }
-            if (tid < 2 * XG) {                              // gate pre-activations: thread = ({ih,hh}, gate column)
-                const int which = tid / XG, g = tid - which * XG;
-                const float* WT = Wsm + which * XD * XG;
-                const float bias = Wsm[2 * XD * XG + which * XG + g];
-                const float* src = which ? slots : upd;
-                for (int r0 = 0; r0 < SR; r0 += 8) {
-                    float acc[8];
+            LP_STAMP(3);
+            if (grt < 5) {                                   // gate pre-activations gi = W_ih u + b_ih, gh = W_hh h + b_hh
+                const float* WT = Wsm + gwhich * XD * XG + gg0;                    // [e][192], this thread's gate quad
+                const float4 b4 = *reinterpret_cast<const float4*>(Wsm + 2 * XD * XG + gwhich * XG + gg0);
+                const float* src = gwhich ? slots : upd;
+                for (int rt = grt; rt < n_rt; rt += 5) {
+                    const int r0 = rt * GR;
+                    float4 acc[GR];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+                    for (int r = 0; r < GR; ++r) acc[r] = b4;
 #pragma unroll 4
                     for (int e4 = 0; e4 < XD / 4; ++e4) {
-                        const float w0 = WT[(e4 * 4 + 0) * XG + g], w1 = WT[(e4 * 4 + 1) * XG + g];
-                        const float w2 = WT[(e4 * 4 + 2) * XG + g], w3 = WT[(e4 * 4 + 3) * XG + g];
+                        const float4 w0 = *reinterpret_cast<const float4*>(WT + (e4 * 4 + 0) * XG);
+                        const float4 w1 = *reinterpret_cast<const float4*>(WT + (e4 * 4 + 1) * XG);
+                        const float4 w2 = *reinterpret_cast<const float4*>(WT + (e4 * 4 + 2) * XG);
+                        const float4 w3 = *reinterpret_cast<const float4*>(WT + (e4 * 4 + 3) * XG);
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) {
+                        for (int r = 0; r < GR; ++r) {
                             const float4 v = *reinterpret_cast<const float4*>(src + min(r0 + r, SR - 1) * XD + e4 * 4);
-                            acc[r] = fmaf(v.x, w0, acc[r]); acc[r] = fmaf(v.y, w1, acc[r]);
-                            acc[r] = fmaf(v.z, w2, acc[r]); acc[r] = fmaf(v.w, w3, acc[r]);
+                            float4& o = acc[r];
+                            o.x = fmaf(v.x, w0.x, o.x); o.y = fmaf(v.x, w0.y, o.y); o.z = fmaf(v.x, w0.z, o.z); o.w = fmaf(v.x, w0.w, o.w);
+                            o.x = fmaf(v.y, w1.x, o.x); o.y = fmaf(v.y, w1.y, o.y); o.z = fmaf(v.y, w1.z, o.z); o.w = fmaf(v.y, w1.w, o.w);
+                            o.x = fmaf(v.z, w2.x, o.x); o.y = fmaf(v.z, w2.y, o.y); o.z = fmaf(v.z, w2.z, o.z); o.w = fmaf(v.z, w2.w, o.w);
+                            o.x = fmaf(v.w, w3.x, o.x); o.y = fmaf(v.w, w3.y, o.y); o.z = fmaf(v.w, w3.z, o.z); o.w = fmaf(v.w, w3.w, o.w);
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        if (r0 + r < SR) gates[(r0 + r) * 2 * XG + which * XG + g] = acc[r] + bias;
+                    for (int r = 0; r < GR; ++r)
+                        if (r0 + r < SR) *reinterpret_cast<float4*>(gates + (r0 + r) * 2 * XG + gwhich * XG + gg0) = acc[r];
                 }
             }
             __syncthreads();
+            LP_STAMP(4);
             for (int idx = tid; idx < SR * XD; idx += HT) {   // GRU cell, gate order [r|z|n]
                 const int sr = idx / XD, e = idx - sr * XD;
                 const float* gi = gates + sr * 2 * XG;
@@ -519,7 +636,11 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
         __syncthreads();
+        LP_STAMP(5);
     }
+#ifdef SCOUTER_PROF
+    if (tid == 0) for (int k = 0; k < 6; ++k) g_prof_head[blockIdx.x * 32 + 12 + k] = (unsigned long long)lp_acc[k];
+#endif
 
     for (int idx = tid; idx < nimg * a.C; idx += HT) {
         const int img = idx / a.C, c = idx - img * a.C;
@@ -558,9 +679,8 @@ EncodeTiledFn encode_fn() {
 }
 
 // Shared-memory map for (G, n, S, L); returns total dynamic bytes (incl. alignment slack) or 0 when it does not fit.
-//   phase A: [NA feature stages][3 weight slots] ... [to_k weights (cp.async prefetch)]
-//   phase B: [X][Ka][Kb][slots, updates, sums][GRU block] alias the rings; the GRU block also aliases the to_k weights
-//            (it is fetched after the MLP)
+//   phase A + to_k MLP: [NA feature stages][NW weight slots]
+//   loop:               [X][K][scratch][slots, updates, sums][GRU block] alias the rings (the GRU block is fetched after the MLP)
 size_t layout(int G, int n, int S, int L, FusedArgs* out) {
     const int R = G * n, SR = G * S;
     const int R8 = (R + 7) & ~7;
@@ -574,17 +694,17 @@ size_t layout(int G, int n, int S, int L, FusedArgs* out) {
     // as many feature stages as fit
     static int na_env = [] { const char* e = getenv("SCOUTER_HEAD_NA"); int v = e ? atoi(e) : MAX_NA; return v < 2 ? 2 : (v > MAX_NA ? MAX_NA : v); }();
     for (int nw = nw_env; nw >= 2; --nw)
-        for (int na = na_env; na >= 2; --na) {
+        for (int na = na_env; na >= 3; --na) {
+            if ((size_t)na * a_stage < (size_t)R * LDX * 4) continue;   // X is written while the weight ring still feeds the MLP
             const size_t off_w = na * a_stage;
             const size_t ring_end = off_w + (size_t)nw * W_SLOT;
-            const size_t off_tokw = align_up(std::max(ring_end, off_gru), 16);
-            const size_t body = std::max(off_tokw + (size_t)L * TOK_FLOATS * 4, off_gru + (size_t)W_FLOATS * 4);
+            const size_t body = std::max(ring_end, off_gru + (size_t)W_FLOATS * 4);
             const size_t off_bar = align_up(body, 16);
             const size_t total = off_bar + 512 + 1024;
             if (total <= 227 * 1024) {
                 if (out) {
                     out->na = na; out->nw = nw; out->a_stage = (int)a_stage; out->off_w = (int)off_w;
-                    out->off_tokw = (int)off_tokw; out->off_gru = (int)off_gru; out->off_small = (int)off_small; out->off_bar = (int)off_bar;
+                    out->off_gru = (int)off_gru; out->off_small = (int)off_small; out->off_bar = (int)off_bar;
                 }
                 return total;
             }
@@ -641,7 +761,7 @@ int head_fused_launch(const scouter_xslot_desc_t* d, const void* packed, const s
     }
     const int R = a.G * n;
     const long long M = (long long)io->batch * n;
-    CUtensorMap tmA, tmB, tmB2;
+    CUtensorMap tmA, tmB, tmB2, tmT, tmT2;
     {
         cuuint64_t dims[2] = {(cuuint64_t)io->channel, (cuuint64_t)M};
         cuuint64_t strides[1] = {(cuuint64_t)io->channel * 4};
@@ -670,10 +790,22 @@ int head_fused_launch(const scouter_xslot_desc_t* d, const void* packed, const s
         r = enc(&tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_split, dimsB2, stridesB2, boxB2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled(bf16 weight pair) failed with %d", (int)r);
+        // to_k layers from the packed parameter block: (L*64, 64) fp32 and (L*128, 64) bf16 [W ; W_r]
+        const XSlotPacked pk{a.S, a.L};
+        cuuint64_t dimsT[2] = {(cuuint64_t)XD, (cuuint64_t)a.L * XD};
+        cuuint64_t stridesT[1] = {(cuuint64_t)XD * 4};
+        r = enc(&tmT, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(a.packed + pk.tok_w_raw(0)), dimsT, stridesT, boxB, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled(to_k weights) failed with %d", (int)r);
+        cuuint64_t dimsT2[2] = {(cuuint64_t)XD, (cuuint64_t)a.L * 2 * XD};
+        cuuint64_t stridesT2[1] = {(cuuint64_t)XD * 2};
+        r = enc(&tmT2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(a.packed + pk.tok_w_pair(0)), dimsT2, stridesT2, boxB2, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled(to_k bf16 pairs) failed with %d", (int)r);
     }
     SC_CUDA(cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int units = cdiv(io->batch, a.G);
-    head_fused_kernel<<<2 * cdiv(units, 2), HT, smem, s>>>(tmA, tmB, tmB2, a);   // clusters of two (padding CTA when odd)
+    head_fused_kernel<<<2 * cdiv(units, 2), HT, smem, s>>>(tmA, tmB, tmB2, tmT, tmT2, a);   // clusters of two (padding CTA when odd)
     SC_LAUNCH_CHECK();
     return 0;
 }

@@ -77,16 +77,25 @@ __global__ void xslot_pack_kernel(scouter_xslot_desc_t d, float* __restrict__ ou
             v = d.gru_w_hh[g * XD + e];
         } else if (i < pk.gru_bhh()) {
             v = d.gru_b_ih[i - pk.gru_bih()];
-        } else if (i < pk.tok_w_hi(0)) {
+        } else if (i < pk.tok_w_raw(0)) {
             v = d.gru_b_hh[i - pk.gru_bhh()];
+        } else if (i < pk.tok_w_pair(0)) {
+            size_t r = i - pk.tok_w_raw(0);
+            v = d.to_k_w[r / (XD * XD)][r % (XD * XD)];
         } else {
-            size_t r = i - pk.tok_w_hi(0);
-            int l = (int)(r / (2 * XD * XD));
-            size_t q = r - (size_t)l * 2 * XD * XD;
-            bool lo = q >= XD * XD;
-            float wv = d.to_k_w[l][lo ? q - XD * XD : q];
-            float hi = to_tf32(wv);
-            v = lo ? to_tf32(wv - hi) : hi;
+            // two bf16 per float slot: element index eb = 2*(i - pair(0)) + {0,1}; row = eb / 64 (0..127 per layer), col = eb % 64
+            size_t r = i - pk.tok_w_pair(0);
+            int l = (int)(r / (XD * XD));
+            size_t eb = 2 * (r - (size_t)l * XD * XD);
+            int row = (int)(eb / XD), col = (int)(eb % XD);
+            float w0 = d.to_k_w[l][(row & 63) * XD + col], w1 = d.to_k_w[l][(row & 63) * XD + col + 1];
+            if (row >= XD) {
+                w0 -= __uint_as_float(__float_as_uint(w0) & 0xFFFFE000u);
+                w1 -= __uint_as_float(__float_as_uint(w1) & 0xFFFFE000u);
+            }
+            uint32_t pr;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pr) : "f"(w1), "f"(w0));
+            v = __uint_as_float(pr);
         }
         out[i] = v;
     }

@@ -17,10 +17,12 @@ struct XSlotPacked {
     __host__ __device__ size_t gru_whh_t() const { return gru_wih_t() + XD * XG; }
     __host__ __device__ size_t gru_bih() const { return gru_whh_t() + XD * XG; }         // (192)
     __host__ __device__ size_t gru_bhh() const { return gru_bih() + XG; }
-    // tensor-core operands (SCOUTER_MATH_TC): row-major [out][in] hi/lo tf32 splits, K-major for UMMA B
-    __host__ __device__ size_t tok_w_hi(int l) const { return gru_bhh() + XG + (size_t)l * 2 * XD * XD; }
-    __host__ __device__ size_t tok_w_lo(int l) const { return tok_w_hi(l) + XD * XD; }
-    __host__ __device__ size_t total() const { return tok_w_hi(L); }
+    // tensor-core operands of the fused head's to_k MLP (K-major UMMA B tiles, fetched by TMA):
+    //   raw:  (L*64, 64) fp32, row l*64+o = to_k[l].weight[o][:]
+    //   pair: (L*128, 64) bf16, rows l*128+[0,64) = bf16(W), rows l*128+[64,128) = bf16(W - trunc19(W))
+    __host__ __device__ size_t tok_w_raw(int l) const { return gru_bhh() + XG + (size_t)l * XD * XD; }
+    __host__ __device__ size_t tok_w_pair(int l) const { return tok_w_raw(L) + (size_t)l * XD * XD; }   // 8192 bf16 = 4096 floats per layer
+    __host__ __device__ size_t total() const { return tok_w_pair(L); }
 };
 
 int validate_xslot_desc(const scouter_xslot_desc_t* d);
