@@ -114,6 +114,10 @@ def cpu_reference_rate(batch, size, steps, warmup):
     return batch * steps / dt, dt / steps, torch.get_num_threads()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one head_fused_kernel launch at B=256, 224^2 (ncu --set full)
+HEAD_DRAM_TRAFFIC = 104058880 + 4982016
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,8 +242,30 @@ def main():
         bb = lambda: st.cp.run(st.static_in)
         for _ in range(3):
             head(); bb()
-        ms_head = timed(head, a.steps) / a.steps
+        # the head reads 103 MB of features, less than the 126 MB L2: every timed call is preceded by a 256 MB write so
+        # that the features come from HBM as they do inside the forward (the flush is outside the events)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def timed_flushed(fn, steps):
+            tot = 0.0
+            for _ in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            ms = tot / steps
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t)
+            return ms
+
+        ms_head = timed_flushed(head, a.steps)
         ms_bb = timed(bb, a.steps) / a.steps
+        head_launches = lib.scouter_head_launch_count(C.byref(desc), C.byref(st.io))
 
     if rank != 0:
         if world > 1:
@@ -273,7 +299,11 @@ def main():
         "gpu_launches": launches * a.steps,
         "roofline": {"kernel": "xSlot head: scouter_head_forward (conv1x1+ReLU+PE+to_k+3x{QK^T,normalise,sigmoid,attn.V,GRU}+logits)",
                      "bound": "hbm", "achieved": head_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": head_gbs / pk["hbm"],
-                     "traffic": None, "ms": ms_head, "algorithmic_bytes": head_bytes, "peak_source": pk["src"] + " copy bandwidth"},
+                     "traffic": HEAD_DRAM_TRAFFIC if (a.batch, a.size) == (256, 224) else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of head_fused_kernel, one ncu --set full capture "
+                                       "(profiles/r01_ncu_head_fused.md)",
+                     "ms": ms_head, "algorithmic_bytes": head_bytes, "peak_source": pk["src"] + " copy bandwidth",
+                     "launches": head_launches, "timing": "CUDA events around each call, 256 MB L2 flush before each call"},
         "roofline_backbone": {"kernel": "backbone op program (47 convs + pools + split attention)", "bound": "tensor",
                               "achieved": bb_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": bb_tflops / tf32_peak,
                               "ms": ms_bb, "peak_source": pk["src"] + " bf16 sustained / 2 (tf32 assumed half of bf16)"},

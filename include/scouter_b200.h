@@ -149,6 +149,9 @@ typedef struct scouter_head_io {
 } scouter_head_io_t;
 
 size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io);
+/* Kernels one scouter_head_forward call launches for this geometry: 1 when the whole head runs as the fused kernel
+ * (a unit of images fits one 128-row tensor-core tile and S <= 32), else projection + loop (+ layout copy). */
+int scouter_head_launch_count(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io);
 int scouter_head_forward(const scouter_xslot_desc_t* desc, const void* packed, const scouter_head_io_t* io,
                          void* workspace, size_t workspace_bytes, scouter_stream_t stream);
 

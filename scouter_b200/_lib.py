@@ -94,6 +94,7 @@ SIGNATURES = {
     "scouter_conv_forward": (C.c_int, [C.POINTER(Op), _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "scouter_conv_path": (C.c_int, [C.POINTER(Op), C.c_int, C.c_int, C.c_int, C.c_int]),
     "scouter_head_workspace_bytes": (C.c_size_t, [C.POINTER(XSlotDesc), C.POINTER(HeadIO)]),
+    "scouter_head_launch_count": (C.c_int, [C.POINTER(XSlotDesc), C.POINTER(HeadIO)]),
     "scouter_head_forward": (C.c_int, [C.POINTER(XSlotDesc), _fp, C.POINTER(HeadIO), _fp, C.c_size_t, _fp]),
     "scouter_plan_create": (C.c_int, [C.POINTER(Op), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "scouter_plan_destroy": (None, [C.c_void_p]),

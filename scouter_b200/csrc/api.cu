@@ -322,6 +322,15 @@ extern "C" size_t scouter_head_workspace_bytes(const scouter_xslot_desc_t* desc,
     return head_ws_base(io) + head_fused_workspace_bytes(io->channel);
 }
 
+extern "C" int scouter_head_launch_count(const scouter_xslot_desc_t* desc, const scouter_head_io_t* io) {
+    if (validate_head(desc, io)) return 0;
+    const int n = io->h * io->w;
+    const int copy = io->layout == SCOUTER_LAYOUT_NCHW ? 1 : 0;
+    if (io->math != SCOUTER_MATH_FP32 && head_fused_supported(desc, io->batch, n, io->channel))
+        return copy + 1 + (io->conv_w_split ? 0 : 1);
+    return copy + 2;
+}
+
 extern "C" int scouter_head_forward(const scouter_xslot_desc_t* desc, const void* packed, const scouter_head_io_t* io,
                                     void* workspace, size_t workspace_bytes, scouter_stream_t stream) {
     if (int e = validate_head(desc, io)) return e;

@@ -64,8 +64,6 @@ struct FusedArgs {
     int kblocks;
     // shared-memory map (bytes from the 1024-aligned base); the phase-B regions alias the phase-A rings
     int na, nw, a_stage, off_w;
-    int issue_batch;   // feature stages issued back to back (longer contiguous runs per feature row at the DRAM)
-    int blocked;       // features are channel-block major: (ch/32, B*n, 32)
     int off_gru, off_small, off_bar;
 };
 
@@ -139,6 +137,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* mlp_in = cempty + 4;          // to_k layer input is in TMEM (128 accumulator owners)
     uint64_t* mlp_out = mlp_in + 1;         // to_k layer MMAs retired
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mlp_out + 1);
+    float* tokb = reinterpret_cast<float*>(smem + a.off_bar + 512);   // [L][64] to_k biases (read by every accumulator owner)
 
     // phase-B views
     const int SP = (S + 3) & ~3;
@@ -155,17 +154,22 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* attnT = Kb + SR * 2 * XG;
 
     if (warp == 0 && elect_one()) {
-        prefetch_tmap(&tmA);
+        // the feature stream starts before anything else is set up: its first boxes need ~1.5k clk to arrive
+        for (int i = 0; i < MAX_NA; ++i) {
+            mbar_init(&fullA[i], 1);
+            mbar_init(&emptyA[i], 4);
+        }
+        fence_barrier_init();
+        for (int kb = 0; kb < min(NA, a.kblocks); ++kb) {
+            mbar_arrive_expect_tx(&fullA[kb], (uint32_t)(R * 128));
+            tma_load_2d(smem + kb * a.a_stage, &tmA, &fullA[kb], kb * 32, blockIdx.x * R);
+        }
         prefetch_tmap(&tmB);
         prefetch_tmap(&tmB2);
         prefetch_tmap(&tmT);
         prefetch_tmap(&tmT2);
     }
     if (warp == 1 && elect_one()) {
-        for (int i = 0; i < MAX_NA; ++i) {
-            mbar_init(&fullA[i], 1);
-            mbar_init(&emptyA[i], 4);
-        }
         for (int i = 0; i < ND; ++i) mbar_init(&done[i], 2);
         for (int i = 0; i < MAX_NW; ++i) mbar_init(&fullW[i], 1);
         for (int i = 0; i < NO; ++i) mbar_init(&opfull[i], 4);
@@ -192,29 +196,17 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // =========================================== phase A ===========================================================
     if (warp == 0) {
         if (elect_one()) {
-            // ----- feature producer: runs NA k-blocks ahead of the MMAs -----
+            // ----- feature producer: runs NA k-blocks ahead of the MMAs (the first NA boxes went out during set-up) -----
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 1;
             const int row0 = blockIdx.x * R;
             PROF_DECL(pa_wait);
-            const int nb = a.issue_batch;
-            for (int kb0 = 0; kb0 < kblocks; kb0 += nb) {
-                const int kb1 = min(kb0 + nb, kblocks);
-                {                                      // all stages of the batch must be free before the first load goes out
-                    int st = stage;
-                    uint32_t ph = phase;
-                    for (int kb = kb0; kb < kb1; ++kb) {
-                        if (kb >= NA) PROF_T(pa_wait, mbar_wait(&emptyA[st], ph ^ 1));
-                        if (++st == NA) { st = 0; ph ^= 1; }
-                    }
-                }
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_arrive_expect_tx(&fullA[stage], (uint32_t)(R * 128));
-                    if (a.blocked) tma_load_3d(smem + stage * a.a_stage, &tmA, &fullA[stage], 0, row0, kb);
-                    else tma_load_2d(smem + stage * a.a_stage, &tmA, &fullA[stage], kb * 32, row0);
-                    TRACE(kb, 0);
-                    if (++stage == NA) { stage = 0; phase ^= 1; }
-                }
+            for (int kb = NA; kb < kblocks; ++kb) {
+                PROF_T(pa_wait, mbar_wait(&emptyA[stage], phase ^ 1));
+                mbar_arrive_expect_tx(&fullA[stage], (uint32_t)(R * 128));
+                tma_load_2d(smem + stage * a.a_stage, &tmA, &fullA[stage], kb * 32, row0);
+                TRACE(kb, 0);
+                if (++stage == NA) { stage = 0; phase ^= 1; }
             }
             PROF_STORE(g_prof_head, 3, pa_wait);
         }
@@ -323,6 +315,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ----- accumulator owners: thread = token row, 64 running fp32 sums starting from the bias -----
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        for (int i = tid - 128; i < a.L * XD; i += 128) tokb[i] = __ldg(a.packed + pk.tok_b(i / XD) + (i % XD));
+        named_bar_sync(1, 128);   // the four accumulator warps only
         float acc[XD];
 #pragma unroll
         for (int j = 0; j < XD / 4; ++j) {
@@ -390,7 +384,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         to_tmem(acc);
         for (int l = 0; l < a.L; ++l) {
             const bool lastl = l + 1 == a.L;
-            const float* bp = a.packed + pk.tok_b(l);
+            const float* bp = tokb + l * XD;
             mbar_wait(mlp_out, (uint32_t)l & 1u);
             tc_fence_after();
 #pragma unroll
@@ -400,7 +394,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tmem_ld_wait();
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + c * 32 + 4 * i4));
+                    const float4 bv = *reinterpret_cast<const float4*>(bp + c * 32 + 4 * i4);
                     float v0 = __uint_as_float(r[4 * i4]) + bv.x, v1 = __uint_as_float(r[4 * i4 + 1]) + bv.y;
                     float v2 = __uint_as_float(r[4 * i4 + 2]) + bv.z, v3 = __uint_as_float(r[4 * i4 + 3]) + bv.w;
                     if (!lastl) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
@@ -513,7 +507,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 #ifdef SCOUTER_PROF
     long long lp_t = clock64(), lp_acc[6] = {0, 0, 0, 0, 0, 0};
-#define LP_STAMP(k) do { const long long _n = clock64(); lp_acc[k] += _n - lp_t; lp_t = _n; } while (0)
+#define LP_STAMP(k) do { const long long _n = clock64(); lp_acc[k] += _n - lp_t; if (tid == 0 && blockIdx.x == 0) g_trace_head[64 * 8 + it * 8 + (k)] = (unsigned long long)(_n - lp_t); lp_t = _n; } while (0)
 #else
 #define LP_STAMP(k)
 #endif
@@ -700,7 +694,7 @@ size_t layout(int G, int n, int S, int L, FusedArgs* out) {
             const size_t ring_end = off_w + (size_t)nw * W_SLOT;
             const size_t body = std::max(ring_end, off_gru + (size_t)W_FLOATS * 4);
             const size_t off_bar = align_up(body, 16);
-            const size_t total = off_bar + 512 + 1024;
+            const size_t total = off_bar + 512 + (size_t)L * XD * 4 + 1024;   // barriers, to_k biases, alignment slack
             if (total <= 227 * 1024) {
                 if (out) {
                     out->na = na; out->nw = nw; out->a_stage = (int)a_stage; out->off_w = (int)off_w;
@@ -743,12 +737,8 @@ int head_fused_launch(const scouter_xslot_desc_t* d, const void* packed, const s
     a.S = d->num_classes * d->slots_per_class; a.C = d->num_classes; a.spc = d->slots_per_class; a.L = d->to_k_layers;
     a.iters = d->iters; a.loss_status = d->loss_status;
     a.kblocks = io->channel / 32;
-    static int issue_batch = [] { const char* e = getenv("SCOUTER_HEAD_BATCH"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
     const size_t smem = layout(a.G, n, a.S, a.L, &a);
     SC_CHECK_ARG(smem, SCOUTER_E_UNSUPPORTED, "head_fused: shared-memory layout does not fit");
-    a.issue_batch = std::min(issue_batch, a.na);
-    static int blocked = getenv("SCOUTER_HEAD_BLOCKED") != nullptr;   // timing experiment only
-    a.blocked = blocked;
     EncodeTiledFn enc = encode_fn();
     SC_CHECK_ARG(enc, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled is not available from the driver");
     // bf16 [W ; W - trunc19(W)] of conv1x1.weight: given by the caller (packed once per parameter version) or derived here
@@ -767,16 +757,7 @@ int head_fused_launch(const scouter_xslot_desc_t* d, const void* packed, const s
         cuuint64_t strides[1] = {(cuuint64_t)io->channel * 4};
         cuuint32_t box[2] = {32, (cuuint32_t)R};
         cuuint32_t es[2] = {1, 1};
-        CUresult r;
-        if (a.blocked) {
-            cuuint64_t dims3[3] = {32, (cuuint64_t)M, (cuuint64_t)io->channel / 32};
-            cuuint64_t strides3[2] = {128, (cuuint64_t)M * 128};
-            cuuint32_t box3[3] = {32, (cuuint32_t)R, 1};
-            cuuint32_t es3[3] = {1, 1, 1};
-            r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)feat_nhwc, dims3, strides3, box3, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        } else
-        r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)feat_nhwc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)feat_nhwc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled(features) failed with %d", (int)r);
         cuuint64_t dimsB[2] = {(cuuint64_t)io->channel, (cuuint64_t)XD};

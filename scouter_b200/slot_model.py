@@ -203,7 +203,9 @@ class SlotModel(nn.Module):
             dev = torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(dev):
             st = self._state(_MetaLike(x_shape, dev))
-        return st.cp.launches + 3    # + conv1x1 projection, xSlot loop, finalize
+            desc, _ = self._head_params(st, dev)
+            head = L.lib().scouter_head_launch_count(C.byref(desc), C.byref(st.io))
+        return st.cp.launches + head + 1    # backbone program + head (one fused kernel when it applies) + finalize
 
     # -- forward --------------------------------------------------------------------------------
     def forward(self, x, target=None):

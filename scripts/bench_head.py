@@ -91,7 +91,11 @@ if a.prof:
     print("per-CTA clocks (mean / max):", {names.get(i, i): (int(arr[:, i].mean()), int(arr[:, i].max())) for i in range(20) if arr[:, i].any()})
     tb = (C.c_ulonglong * (128 * 8))()
     lib.scouter_trace_read_head(tb, 128 * 8)
-    tr = np.array(tb[:], dtype=np.int64).reshape(128, 8)[:ch // 32]
+    full = np.array(tb[:], dtype=np.int64).reshape(128, 8)
+    print("loop phases per iteration (CTA 0): dots normalise update gru_wait gates cell")
+    for it in range(3):
+        print(it, " ".join(f"{int(v):7d}" for v in full[64 + it][:6]))
+    tr = full[:ch // 32]
     t0 = tr[tr > 0].min()
     print("trace (CTA 0, clocks since first event): kb prodA prodW sp.fullA sp.done sp.opfull is.opfull is.fullW is.commit")
     for kb in range(tr.shape[0]):

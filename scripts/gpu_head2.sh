@@ -1,8 +1,8 @@
 #!/bin/bash
 echo "== head tests"
-timeout 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_parity.py -m gpu -q -x -k "head or slot_model or small_and_odd or full_size or other_hot or xslot" 2>&1 | tail -8
+timeout 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_parity.py -m gpu -q -x -k "head or slot_model or small_and_odd or full_size or other_hot or xslot" 2>&1 | tail -3
 timeout 120 python scripts/bench_head.py --fs 7 --prof 2>&1 | grep "per-CTA" | cut -c1-1000
 timeout 120 python scripts/bench_head.py --fs 7 2>&1 | tail -1
 timeout 120 python scripts/bench_head.py --fs 9 2>&1 | tail -1
-timeout 120 python scripts/bench_head.py --fs 7 --classes 30 2>&1 | tail -1
-timeout 120 python scripts/bench_head.py --fs 8 --classes 16 --spc 2 2>&1 | tail -1
+timeout 120 python scripts/bench_head.py --fs 8 --classes 16 2>&1 | tail -1
+timeout 120 python scripts/bench_head.py --fs 7 --batch 7 2>&1 | tail -1
