@@ -88,6 +88,42 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const float* __restrict__ 
     }
 }
 
+// The shortcut pool AvgPool2d(2, 2, ceil_mode=True, count_include_pad=False) (resnet.py:300) with every load of the
+// thread's ROWS windows issued before the first add: 4*ROWS independent 16-byte loads in flight per thread.  Same
+// summation order and divisor as the generic kernel (bit-identical results).
+template <int ROWS>
+__global__ void __launch_bounds__(256) avgpool2x2_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int C,
+                                                         int Ho, int Wo, int round_out) {
+    SC_PIXEL_INDEX(ROWS);
+    const float* base = in + (size_t)b * H * W * C + q * 4;
+    const int wi0 = 2 * wo;
+    const bool w1 = wi0 + 1 < W;
+    float4 v[ROWS][4];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        const int hi0 = 2 * (ho0 + j);
+        const bool r0 = ho0 + j < Ho, r1 = r0 && hi0 + 1 < H;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j][0] = r0 ? ld4(base + ((size_t)hi0 * W + wi0) * C) : z;
+        v[j][1] = (r0 && w1) ? ld4(base + ((size_t)hi0 * W + wi0 + 1) * C) : z;
+        v[j][2] = r1 ? ld4(base + ((size_t)(hi0 + 1) * W + wi0) * C) : z;
+        v[j][3] = (r1 && w1) ? ld4(base + ((size_t)(hi0 + 1) * W + wi0 + 1) * C) : z;
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        if (ho0 + j >= Ho) continue;
+        const int hi0 = 2 * (ho0 + j);
+        const float div = (float)((hi0 + 1 < H ? 2 : 1) * (w1 ? 2 : 1));
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        add4(a, v[j][0]);
+        if (w1) add4(a, v[j][1]);
+        if (hi0 + 1 < H) { add4(a, v[j][2]); if (w1) add4(a, v[j][3]); }
+        a.x /= div; a.y /= div; a.z /= div; a.w /= div;
+        if (round_out) a = round4(a);
+        *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho0 + j) * Wo + wo) * C + q * 4) = a;
+    }
+}
+
 // ---- split attention --------------------------------------------------------------------------------------------
 // Stage 1: per (image, pixel slice) partial sums of all 2C channels: thread = one float4 channel group x one pixel
 // lane, four independent accumulators.  Stage 2 adds the slices in a fixed order and the two radix halves.
@@ -255,7 +291,10 @@ int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int 
                    int count_include_pad, int round_out, cudaStream_t s) {
     dim3 grid;
     if (int e = pixel_grid(B, Ho, Wo, C, 4, grid)) return e;
-    avgpool_kernel<4><<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, k, stride, pad, count_include_pad, round_out);
+    if (k == 2 && stride == 2 && pad == 0)
+        avgpool2x2_kernel<4><<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, round_out);
+    else
+        avgpool_kernel<4><<<grid, 256, 0, s>>>(in, out, H, W, C, Ho, Wo, k, stride, pad, count_include_pad, round_out);
     SC_LAUNCH_CHECK();
     return 0;
 }
