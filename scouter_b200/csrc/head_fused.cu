@@ -138,6 +138,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* mlp_out = mlp_in + 1;         // to_k layer MMAs retired
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mlp_out + 1);
     float* tokb = reinterpret_cast<float*>(smem + a.off_bar + 512);   // [L][64] to_k biases (read by every accumulator owner)
+    float* slots0 = tokb + a.L * XD;                                   // [S][64] initial slots, staged during phase A
 
     // phase-B views
     const int SP = (S + 3) & ~3;
@@ -316,6 +317,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;
         const int row = q * 32 + lane;
         for (int i = tid - 128; i < a.L * XD; i += 128) tokb[i] = __ldg(a.packed + pk.tok_b(i / XD) + (i % XD));
+        for (int i = tid - 128; i < S * XD / 4; i += 128) cp_async16(slots0 + i * 4, a.packed + pk.slots() + i * 4);
         named_bar_sync(1, 128);   // the four accumulator warps only
         float acc[XD];
 #pragma unroll
@@ -410,6 +412,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     *reinterpret_cast<float4*>(Ka + row * LDX + e4 * 4) = make_float4(acc[4 * e4], acc[4 * e4 + 1], acc[4 * e4 + 2], acc[4 * e4 + 3]);
             }
         }
+        cp_async_wait_all();   // the staged initial slots (issued long ago)
     } else if (warp >= 8) {
         // ----- splitters: two groups of four warps on alternate k-blocks; thread = token row -----
         const int sg = (warp - 8) >> 2;
@@ -463,12 +466,13 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    cluster_arrive();     // no more multicasts / remote arrivals from this CTA; matched by cluster_wait() before exit
+    cluster_arrive_relaxed();   // no more multicasts / remote arrivals from this CTA; matched by cluster_wait() before exit
     if (warp == 2) tmem_dealloc(tmem_base, 512);
     PROF_END(phaseA); PROF_BEGIN(mlp);
 
     // =========================================== phase B ===========================================================
-    for (int idx = tid; idx < SR * XD; idx += HT) slots[idx] = __ldg(a.packed + pk.slots() + (idx % (S * XD)));
+    for (int img = 0; img < G; ++img)
+        for (int idx = tid; idx < S * XD; idx += HT) slots[img * S * XD + idx] = slots0[idx];
 
     PROF_END(mlp); PROF_BEGIN(loop);
     const float* K = Ka;
@@ -694,7 +698,7 @@ size_t layout(int G, int n, int S, int L, FusedArgs* out) {
             const size_t ring_end = off_w + (size_t)nw * W_SLOT;
             const size_t body = std::max(ring_end, off_gru + (size_t)W_FLOATS * 4);
             const size_t off_bar = align_up(body, 16);
-            const size_t total = off_bar + 512 + (size_t)L * XD * 4 + 1024;   // barriers, to_k biases, alignment slack
+            const size_t total = off_bar + 512 + (size_t)(L + S) * XD * 4 + 1024;   // barriers, to_k biases, initial slots, slack
             if (total <= 227 * 1024) {
                 if (out) {
                     out->na = na; out->nw = nw; out->a_stage = (int)a_stage; out->off_w = (int)off_w;

@@ -131,6 +131,9 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     return r;
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// Arrival without release semantics: "this CTA issues no more remote operations" (no memory of ours is read by the peer,
+// so nothing has to be flushed -- the .release form stalls every warp on a membar).
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // TMA store (shared -> global), bulk async-group completion
