@@ -53,15 +53,25 @@ struct UmmaArgs {
     long long slab;  // floats between partial slabs
 };
 
-template <int BN, bool SPLIT, bool RES = false>
+// TS: the activation operands live in TENSOR MEMORY.  In SS mode every MMA reads its whole A slice from shared memory
+// (M128 x N128 x K8: 4 KB + 4 KB = 64 clk at 128 B/clk, exactly its tensor-pipe floor), so together with the TMA writes and
+// the split tiles a BN=128 k-block moves 160 KB through the shared-memory pipe: 1250 clk for 512 clk of MMAs (measured:
+// 1200 clk per k-block on the layer-4 1x1 convs).  With TS the splitter threads (thread = row) read their row of the TMA
+// tile once, derive the bf16 forms in registers and tcgen05.st [fp32 | bf16 | bf16 remainder] into the 64-column TMEM
+// operand buffer of the stage; the MMAs read only the weight tiles from shared memory (96 KB per k-block).
+template <int BN, bool SPLIT, bool RES = false, bool TS = false>
 struct Cfg {
+    static_assert(!TS || SPLIT, "TS is a variant of the error-compensated kernel");
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
-    static constexpr int STAGE = SPLIT ? 2 * RAW : RAW;      // SPLIT: [A | W | bf16 A | bf16 A_r | bf16 W | bf16 W_r]
-    static constexpr int OFF_AB = RAW, OFF_ARB = RAW + A_BYTES / 2, OFF_WB = RAW + A_BYTES, OFF_WRB = RAW + A_BYTES + B_BYTES / 2;
+    // SPLIT: [A | W | bf16 A | bf16 A_r | bf16 W | bf16 W_r];  TS: [A | W | bf16 W | bf16 W_r]
+    static constexpr int STAGE = TS ? RAW + B_BYTES : (SPLIT ? 2 * RAW : RAW);
+    static constexpr int OFF_AB = RAW, OFF_ARB = RAW + A_BYTES / 2;
+    static constexpr int OFF_WB = TS ? RAW : RAW + A_BYTES, OFF_WRB = OFF_WB + B_BYTES / 2;
+    static constexpr int OP_COL0 = 2 * BN;                   // TS: operand buffer of stage s = 64 columns at OP_COL0 + 64*s
 
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int TMEM_COLS = TS ? 512 : (2 * BN < 32 ? 32 : 2 * BN);
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
     // fp32 sums of the chunked accumulation fit in registers (64 per thread).
     static constexpr int EPI_GROUPS = (SPLIT && BN == 128) ? 2 : 1;
@@ -71,7 +81,9 @@ struct Cfg {
     // RES: the whole 128 x BN residual tile is TMA-loaded into BN/16 slabs; the epilogue adds it in place and the
     // same slabs are the source of the TMA stores (no staging double buffer, no row-per-thread residual loads).
     static constexpr int OUT_BYTES = RES ? (BN / 16) * OUT_STAGE : EPI_GROUPS * 2 * OUT_STAGE;
-    static constexpr int STAGES = ((224 * 1024 - OUT_BYTES) / STAGE) > 8 ? 8 : ((224 * 1024 - OUT_BYTES) / STAGE);
+    static constexpr int FIT = (224 * 1024 - OUT_BYTES) / STAGE;
+    static constexpr int CAP = TS ? (512 - 2 * BN) / 64 : 8;   // TS: one TMEM operand buffer per stage
+    static constexpr int STAGES = FIT < CAP ? (FIT > 8 ? 8 : FIT) : (CAP > 8 ? 8 : CAP);
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 1024 /*barriers*/ + OUT_BYTES;
 };
 
@@ -79,12 +91,12 @@ struct Cfg {
 __device__ unsigned long long g_prof_flat[256 * 32];
 #endif
 
-template <int BN, bool SPLIT, bool RES>
-__global__ void __launch_bounds__(Cfg<BN, SPLIT, RES>::THREADS, 1)
+template <int BN, bool SPLIT, bool RES, bool TS>
+__global__ void __launch_bounds__(Cfg<BN, SPLIT, RES, TS>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ CUtensorMap tmR, const UmmaArgs p) {
-    using C = Cfg<BN, SPLIT, RES>;
+    using C = Cfg<BN, SPLIT, RES, TS>;
     static_assert(!RES || SPLIT, "the in-place residual epilogue exists for the SPLIT kernel only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -217,7 +229,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     const uint32_t acc = in_chunk != 0;
                     // UMMA_K = 8 tf32 / 16 bf16 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
-                    if constexpr (SPLIT) {
+                    if constexpr (TS) {
+                        constexpr uint32_t idesc_b = idesc_bf16(128, BN);
+                        const uint32_t a_tm = tmem_base + C::OP_COL0 + 64u * (uint32_t)stage;   // [fp32 A | bf16 A | bf16 A_r]
+#pragma unroll
+                        for (uint32_t k = 0; k < 2; ++k)   // A * W_r
+                            umma_bf16_ts(d_tmem, a_tm + 32 + 8 * k, desc_make(DESC_HI_SW64, s_lo + (C::OFF_WRB >> 4) + 2 * k), idesc_b, acc | k);
+#pragma unroll
+                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W
+                            umma_bf16_ts(d_tmem, a_tm + 48 + 8 * k, desc_make(DESC_HI_SW64, s_lo + (C::OFF_WB >> 4) + 2 * k), idesc_b, 1);
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
+                            umma_tf32_ts(d_tmem, a_tm + 8 * k, desc_make(DESC_HI_SW128, s_lo + (C::A_BYTES >> 4) + 2 * k), idesc, 1);
+                    } else if constexpr (SPLIT) {
                         constexpr uint32_t idesc_b = idesc_bf16(128, BN);
 #pragma unroll
                         for (uint32_t k = 0; k < 2; ++k)   // A * W_r
@@ -481,9 +505,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 PROF_T(pfull, mbar_wait(&full[stage], phase));
                 uint8_t* st = smem + stage * C::STAGE;
-                split_tile_bf16<128>(st, st + C::OFF_AB, st + C::OFF_ARB, sl);
-                if (!p.rem_rows) split_tile_bf16<BN>(st + C::A_BYTES, st + C::OFF_WB, st + C::OFF_WRB, sl);
-                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                if constexpr (TS) {
+                    // thread = row of the tile: fp32 | bf16 | bf16 remainder of its 32 channels -> TMEM.  The operand buffer
+                    // is the stage's: full[stage] can only complete after the MMAs of its previous use have retired.
+                    const uint32_t sw = (uint32_t)(tid & 7);
+                    const uint8_t* src = st + tid * 128;
+                    uint32_t f[32], xb[16], rb[16];
+#pragma unroll
+                    for (uint32_t c = 0; c < 8; ++c) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));   // SWIZZLE_128B
+                        f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float x0 = __uint_as_float(f[2 * i]), x1 = __uint_as_float(f[2 * i + 1]);
+                        const float r0 = x0 - __uint_as_float(f[2 * i] & 0xFFFFE000u), r1 = x1 - __uint_as_float(f[2 * i + 1] & 0xFFFFE000u);
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xb[i]) : "f"(x1), "f"(x0));
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rb[i]) : "f"(r1), "f"(r0));
+                    }
+                    tc_fence_after();
+                    const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::OP_COL0 + 64u * (uint32_t)stage;
+                    tmem_st_32x32(t0, f);
+                    tmem_st_32x16(t0 + 32, xb);
+                    tmem_st_32x16(t0 + 48, rb);
+                    tmem_st_wait();
+                    tc_fence_before();
+                } else {
+                    split_tile_bf16<128>(st, st + C::OFF_AB, st + C::OFF_ARB, sl);
+                    if (!p.rem_rows) split_tile_bf16<BN>(st + C::A_BYTES, st + C::OFF_WB, st + C::OFF_WRB, sl);
+                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&split_done[stage]);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -535,14 +586,14 @@ int pick_bn(int cout_g) {
     return 0;
 }
 
-template <int BN, bool SPLIT, bool RES = false>
+template <int BN, bool SPLIT, bool RES = false, bool TS = false>
 int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const CUtensorMap& tO, const CUtensorMap& tR,
               const UmmaArgs& u, int grid, cudaStream_t s) {
-    using C = Cfg<BN, SPLIT, RES>;
+    using C = Cfg<BN, SPLIT, RES, TS>;
     static_assert(C::STAGES >= 2, "pipeline too shallow");
     static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
-    SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, SPLIT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    conv_umma_kernel<BN, SPLIT, RES><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, tB2, tO, tR, u);
+    SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, SPLIT, RES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    conv_umma_kernel<BN, SPLIT, RES, TS><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, tB2, tO, tR, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -672,6 +723,9 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     // residual convs (the block-final 1x1 conv3 + shortcut) take the in-place residual epilogue
     static bool no_res_tma = getenv("SCOUTER_NO_RES_TMA") != nullptr;
     const bool res_tma = a.split && a.res && u.tma_store && u.ksplit == 1 && !no_res_tma;
+    // activation operands in tensor memory (TS-mode MMAs): needs the host-pre-split weights
+    static bool no_ts = getenv("SCOUTER_UMMA_NO_TS") != nullptr;
+    const bool ts = presplit && !no_ts;
     if (res_tma) {
         if (!(reuse && plan.res == a.res)) {
             cuuint64_t dimsR[2] = {(cuuint64_t)a.Cout, (cuuint64_t)u.M};
@@ -684,6 +738,20 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
             SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(residual) failed with %d", (int)r);
             plan.res = a.res;
         }
+    }
+    if (res_tma && ts) {
+        switch (BN) {
+            case 32: return launch_bn<32, true, true, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmR, u, grid, s);
+            case 64: return launch_bn<64, true, true, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmR, u, grid, s);
+            case 128: return launch_bn<128, true, true, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmR, u, grid, s);
+        }
+    } else if (a.split && ts) {
+        switch (BN) {
+            case 32: return launch_bn<32, true, false, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
+            case 64: return launch_bn<64, true, false, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
+            case 128: return launch_bn<128, true, false, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmO, u, grid, s);
+        }
+    } else if (res_tma) {
         switch (BN) {
             case 32: return launch_bn<32, true, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmR, u, grid, s);
             case 64: return launch_bn<64, true, true>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, plan.tmR, u, grid, s);
