@@ -234,8 +234,6 @@ __global__ void __launch_bounds__(256) stem3x3s2_kernel(const float* __restrict_
     }
     __syncthreads();
     const int ty = threadIdx.x / TW, tx = threadIdx.x % TW;
-    const int ho = h0 + ty, wo = w0 + tx;
-    if (ho >= Ho || wo >= Wo) return;
     float acc[COUT];
 #pragma unroll
     for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
@@ -249,7 +247,12 @@ __global__ void __launch_bounds__(256) stem3x3s2_kernel(const float* __restrict_
 #pragma unroll
                 for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, cw.w[((r * 3 + s) * CIN + c) * COUT + co], acc[co]);
             }
-    float* op = out + (((long long)b * Ho + ho) * Wo + wo) * COUT;
+    // The tile's 32 pixels of one output row are one contiguous run of 32*COUT floats in NHWC: stage the results in shared
+    // memory (pixel stride COUT+4 floats: conflict-free 16-byte stores) and write whole 512-byte segments per warp
+    // instruction instead of 32 scattered 16-byte pieces.
+    extern __shared__ __align__(16) float stage[];
+    constexpr int LDS_ = COUT + 4;
+    float* sp = stage + threadIdx.x * LDS_;
 #pragma unroll
     for (int co = 0; co < COUT; co += 4) {
         float v[4];
@@ -259,7 +262,17 @@ __global__ void __launch_bounds__(256) stem3x3s2_kernel(const float* __restrict_
             if (relu) v[j] = fmaxf(v[j], 0.f);
             if (round_out) v[j] = to_tf32(v[j]);
         }
-        *reinterpret_cast<float4*>(op + co) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(sp + co) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+    constexpr int Q = COUT / 4;                 // float4 per pixel
+    for (int i = threadIdx.x; i < TH * TW * Q; i += 256) {
+        const int pix = i / Q, c4 = i - pix * Q;
+        const int py = pix / TW, px = pix - py * TW;
+        const int ho = h0 + py, wo = w0 + px;
+        if (ho < Ho && wo < Wo)
+            *reinterpret_cast<float4*>(out + (((long long)b * Ho + ho) * Wo + wo) * COUT + c4 * 4) =
+                *reinterpret_cast<const float4*>(stage + pix * LDS_ + c4 * 4);
     }
 }
 
@@ -272,7 +285,10 @@ int launch_stem_tiled(const StemArgs& a, cudaStream_t s) {
         for (int t = 0; t < 9 * CIN; ++t) cw.w[t * COUT + co] = a.w_host[co * 9 * CIN + t];
     for (int co = 0; co < COUT; ++co) cw.b[co] = a.b_host ? a.b_host[co] : 0.f;
     dim3 grid(cdiv(a.Wo, 32), cdiv(a.Ho, 8), a.B);
-    stem3x3s2_kernel<CIN, COUT><<<grid, 256, 0, s>>>(a.in, a.out, a.H, a.W, a.Ho, a.Wo, a.relu, a.round_out, cw);
+    constexpr int stage_bytes = 256 * (COUT + 4) * 4;
+    if (stage_bytes + (int)sizeof(float) * CIN * 17 * 67 > 48 * 1024)
+        SC_CUDA(cudaFuncSetAttribute(stem3x3s2_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
+    stem3x3s2_kernel<CIN, COUT><<<grid, 256, stage_bytes, s>>>(a.in, a.out, a.H, a.W, a.Ho, a.Wo, a.relu, a.round_out, cw);
     SC_LAUNCH_CHECK();
     return 0;
 }

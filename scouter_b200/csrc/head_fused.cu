@@ -720,13 +720,18 @@ __global__ void split_w_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* 
 
 }  // namespace
 
+// Images per unit: as many as fit a 128-row tile AND the shared-memory map (many slots need more scratch per image).
+static int pick_group(int batch, int n, int S, int L) {
+    for (int G = std::max(1, std::min(128 / n, batch)); G >= 1; --G)
+        if (S * G <= 128 && layout(G, n, S, L, nullptr) != 0) return G;
+    return 0;
+}
+
 bool head_fused_supported(const scouter_xslot_desc_t* d, int batch, int n, int channel) {
     static bool off = getenv("SCOUTER_NO_FUSED_HEAD") != nullptr;
     const int S = d->num_classes * d->slots_per_class;
     if (off || n > 128 || S > 32 || channel % 32 || d->to_k_layers < 1) return false;
-    const int G = std::max(1, std::min(128 / n, batch));
-    if (S * G > 128) return false;
-    return layout(G, n, S, d->to_k_layers, nullptr) != 0 && encode_fn() != nullptr;
+    return pick_group(batch, n, S, d->to_k_layers) != 0 && encode_fn() != nullptr;
 }
 
 size_t head_fused_workspace_bytes(int channel) { return align_up((size_t)2 * XD * channel * 2, 1024); }
@@ -737,8 +742,10 @@ int head_fused_launch(const scouter_xslot_desc_t* d, const void* packed, const s
     FusedArgs a;
     a.conv_b = io->conv_b; a.packed = (const float*)packed; a.pe = io->pe;
     a.x_out = io->x_out; a.logits = io->logits; a.attn = io->attn; a.attn_sum = io->attn_sum;
-    a.B = io->batch; a.n = n; a.G = std::max(1, std::min(128 / n, io->batch));
+    a.B = io->batch; a.n = n;
     a.S = d->num_classes * d->slots_per_class; a.C = d->num_classes; a.spc = d->slots_per_class; a.L = d->to_k_layers;
+    a.G = pick_group(io->batch, n, a.S, a.L);
+    SC_CHECK_ARG(a.G > 0, SCOUTER_E_UNSUPPORTED, "head_fused: no unit size fits");
     a.iters = d->iters; a.loss_status = d->loss_status;
     a.kblocks = io->channel / 32;
     const size_t smem = layout(a.G, n, a.S, a.L, &a);
