@@ -69,7 +69,7 @@ struct Cfg {
     static constexpr int STAGE = TS ? RAW + B_BYTES : (SPLIT ? 2 * RAW : RAW);
     static constexpr int OFF_AB = RAW, OFF_ARB = RAW + A_BYTES / 2;
     static constexpr int OFF_WB = TS ? RAW : RAW + A_BYTES, OFF_WRB = OFF_WB + B_BYTES / 2;
-    static constexpr int OP_COL0 = 2 * BN;                   // TS: operand buffer of stage s = 64 columns at OP_COL0 + 64*s
+    static constexpr int OP_COL0 = 2 * BN;                   // TS: operand buffer b = 64 columns at OP_COL0 + 64*b
 
     static constexpr int TMEM_COLS = TS ? 512 : (2 * BN < 32 ? 32 : 2 * BN);
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
@@ -82,9 +82,18 @@ struct Cfg {
     // same slabs are the source of the TMA stores (no staging double buffer, no row-per-thread residual loads).
     static constexpr int OUT_BYTES = RES ? (BN / 16) * OUT_STAGE : EPI_GROUPS * 2 * OUT_STAGE;
     static constexpr int FIT = (224 * 1024 - OUT_BYTES) / STAGE;
-    static constexpr int CAP = TS ? (512 - 2 * BN) / 64 : 8;   // TS: one TMEM operand buffer per stage
-    static constexpr int STAGES = FIT < CAP ? (FIT > 8 ? 8 : FIT) : (CAP > 8 ? 8 : CAP);
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 1024 /*barriers*/ + OUT_BYTES;
+    static constexpr int STAGES = TS ? 1 : (FIT > 8 ? 8 : FIT);
+    // TS: two rings instead of stages.  The activation tile is dead as soon as the splitters hold it in registers, so its
+    // ring (NA x 16 KB, fed from HBM) runs far ahead; the weight tiles (fp32 + bf16 pair, from L2) need NW slots; NO TMEM
+    // operand buffers sit between the splitters and the MMAs.
+    static constexpr int W_SLOT = 2 * B_BYTES;               // [W fp32 | bf16 W | bf16 W_r]
+    static constexpr int BUDGET = 224 * 1024 - OUT_BYTES;
+    static constexpr int NW = (BUDGET - 3 * W_SLOT) / A_BYTES >= 4 ? 3 : 2;
+    static constexpr int NA_FIT = (BUDGET - NW * W_SLOT) / A_BYTES;
+    static constexpr int NA = NA_FIT > 8 ? 8 : NA_FIT;
+    static constexpr int NO = 4;
+    static constexpr int RING_BYTES = TS ? NA * A_BYTES + NW * W_SLOT : STAGES * STAGE;
+    static constexpr int SMEM = RING_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + OUT_BYTES;
 };
 
 #ifdef SCOUTER_PROF
@@ -100,7 +109,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     static_assert(!RES || SPLIT, "the in-place residual epilogue exists for the SPLIT kernel only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
     uint64_t* empty = full + C::STAGES;
     uint64_t* cfull = empty + C::STAGES;   // [2] accumulator chunk complete (tcgen05.commit)
     uint64_t* cempty = cfull + 2;          // [2] accumulator chunk drained by every epilogue thread
@@ -108,7 +117,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* rfull = split_done + C::STAGES;   // RES: residual tile landed (TMA)
     uint64_t* rempty = rfull + 1;               // RES: every store of the tile has read its slab (one arrival per epilogue group)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rempty + 1);
-    uint8_t* out_stage = smem + C::STAGES * C::STAGE + 1024;   // [EPI_GROUPS][2][OUT_STAGE], 1024-aligned
+    uint8_t* out_stage = smem + C::RING_BYTES + 1024;   // [EPI_GROUPS][2][OUT_STAGE], 1024-aligned
+    // TS rings
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES + 512);   // [8] activation tile landed
+    uint64_t* emptyA = fullA + 8;           // [8] tile read into registers by the four splitter warps
+    uint64_t* fullW = emptyA + 8;           // [4] weight slot landed
+    uint64_t* done = fullW + 4;             // [4] MMAs of k-block (index gk & 3) retired: frees weight slot and operand buffer
+    uint64_t* opfull = done + 4;            // [4] operands of the k-block are in TMEM
+    uint8_t* const w_ring = smem + C::NA * C::A_BYTES;
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (warp == 0 && elect_one()) {
@@ -127,6 +143,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         mbar_init(rfull, 1);
         mbar_init(rempty, C::EPI_GROUPS);
+        if constexpr (TS) {
+            for (int i = 0; i < 8; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 4); }
+            for (int i = 0; i < 4; ++i) { mbar_init(&fullW[i], 1); mbar_init(&done[i], 1); mbar_init(&opfull[i], 4); }
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -142,7 +162,122 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // chain to chunk*4*(SPLIT?3:1) steps; with one chunk per tile it degenerates to plain double buffering.
     const int nchunks = (p.kblocks + p.chunk - 1) / p.chunk;
 
-    if (warp == 0) {
+    if (TS && warp == 0) {
+        if (elect_one()) {
+            // ===== activation producer (TS): runs NA k-blocks ahead; also fetches the residual tile (RES) =====
+            int sa_i = 0;
+            uint32_t aphase = 0;
+            int gk = 0;
+            uint32_t rphase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int sp = t % p.ksplit;
+                const int tt = t / p.ksplit;
+                const int nt = tt % p.n_tiles;
+                const int mt = (tt / p.n_tiles) % p.m_tiles;
+                const int g = tt / (p.n_tiles * p.m_tiles);
+                int w0 = 0, h0 = 0, b0 = 0;
+                if (p.mode) {
+                    w0 = (mt % p.tw) * p.Wb;
+                    h0 = ((mt / p.tw) % p.th) * p.Hb;
+                    b0 = (mt / (p.tw * p.th)) * p.Nb;
+                }
+                bool res_pending = RES;
+                auto issue_residual = [&]() {
+                    mbar_arrive_expect_tx(rfull, (uint32_t)(128 * BN * 4));
+#pragma unroll
+                    for (int j = 0; j < BN / 16; ++j)
+                        tma_load_2d(out_stage + j * C::OUT_STAGE, &tmR, rfull, g * p.cout_g + nt * BN + j * 16, mt * 128);
+                    res_pending = false;
+                    rphase ^= 1;
+                };
+                for (int kb = 0; kb < p.kblocks; ++kb, ++gk) {
+                    if (RES && res_pending && mbar_try_wait(rempty, rphase ^ 1)) issue_residual();
+                    if (gk >= C::NA) mbar_wait(&emptyA[sa_i], aphase ^ 1);
+                    uint8_t* sa = smem + sa_i * C::A_BYTES;
+                    mbar_arrive_expect_tx(&fullA[sa_i], (uint32_t)p.a_bytes);
+                    const int kbg = sp * p.kblocks + kb;
+                    const int tap = kbg / p.cblocks;
+                    const int c0 = p.cin_g * g + (kbg - tap * p.cblocks) * 32;
+                    if (p.mode) {
+                        const int r = tap / p.kw, s_ = tap - r * p.kw;
+                        tma_load_4d(sa, &tmA, &fullA[sa_i], c0, w0 + s_ - p.pad, h0 + r - p.pad, b0);
+                    } else {
+                        tma_load_2d(sa, &tmA, &fullA[sa_i], c0, mt * 128);
+                    }
+                    if (++sa_i == C::NA) { sa_i = 0; aphase ^= 1; }
+                }
+                if (RES && res_pending) {
+                    mbar_wait(rempty, rphase ^ 1);
+                    issue_residual();
+                }
+            }
+        }
+    } else if (TS && warp == 3) {
+        if (elect_one()) {
+            // ===== weight producer (TS): fp32 tile + pre-split bf16 [W ; W_r] tiles, NW slots =====
+            int ws = 0, gk = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int sp = t % p.ksplit;
+                const int tt = t / p.ksplit;
+                const int nt = tt % p.n_tiles;
+                const int g = tt / (p.n_tiles * p.m_tiles);
+                for (int kb = 0; kb < p.kblocks; ++kb, ++gk) {
+                    if (gk >= C::NW) {
+                        const int j = gk - C::NW;
+                        mbar_wait(&done[j & 3], (uint32_t)(j >> 2) & 1u);
+                    }
+                    uint8_t* sw = w_ring + ws * C::W_SLOT;
+                    mbar_arrive_expect_tx(&fullW[ws], (uint32_t)C::W_SLOT);
+                    const int kbg = sp * p.kblocks + kb;
+                    tma_load_2d(sw, &tmB, &fullW[ws], kbg * 32, g * p.cout_g + nt * BN);
+                    tma_load_2d(sw + C::B_BYTES, &tmB2, &fullW[ws], kbg * 32, g * p.cout_g + nt * BN);
+                    tma_load_2d(sw + C::B_BYTES + C::B_BYTES / 2, &tmB2, &fullW[ws], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
+                    if (++ws == C::NW) ws = 0;
+                }
+            }
+        }
+    } else if (TS && warp == 1) {
+        if (elect_one()) {
+            // ===== MMA issuer (TS): A operands from the TMEM operand buffers, weights from the weight ring =====
+            constexpr uint32_t idesc = idesc_tf32(128, BN);
+            constexpr uint32_t idesc_b = idesc_bf16(128, BN);
+            const uint32_t w_lo0 = desc_lo(smem_u32(w_ring));
+            const uint32_t opfull_a = smem_u32(opfull), fullw_a = smem_u32(fullW), done_a = smem_u32(done), cfull_a = smem_u32(cfull),
+                           cempty_a = smem_u32(cempty);
+            const int kblocks = p.kblocks, chunk = p.chunk;
+            int ws = 0, in_chunk = 0;
+            uint32_t wphase = 0, gk = 0, cc = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                for (int kb = 0; kb < kblocks; ++kb, ++gk) {
+                    const uint32_t buf = cc & 1, ob = gk & 3;
+                    if (in_chunk == 0) mbar_wait_a(cempty_a + 8 * buf, ((cc >> 1) & 1) ^ 1);
+                    mbar_wait_a(opfull_a + 8 * ob, (gk >> 2) & 1);
+                    mbar_wait_a(fullw_a + 8 * ws, wphase);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * BN;
+                    const uint32_t acc = in_chunk != 0;
+                    const uint32_t a_tm = tmem_base + C::OP_COL0 + 64u * ob;        // [fp32 A | bf16 A | bf16 A_r]
+                    const uint32_t w_lo = w_lo0 + (uint32_t)ws * (C::W_SLOT >> 4);   // [W fp32 | bf16 W | bf16 W_r]
+#pragma unroll
+                    for (uint32_t k = 0; k < 2; ++k)   // A * W_r
+                        umma_bf16_ts(d_tmem, a_tm + 32 + 8 * k, desc_make(DESC_HI_SW64, w_lo + ((C::B_BYTES + C::B_BYTES / 2) >> 4) + 2 * k), idesc_b, acc | k);
+#pragma unroll
+                    for (uint32_t k = 0; k < 2; ++k)   // A_r * W
+                        umma_bf16_ts(d_tmem, a_tm + 48 + 8 * k, desc_make(DESC_HI_SW64, w_lo + (C::B_BYTES >> 4) + 2 * k), idesc_b, 1);
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
+                        umma_tf32_ts(d_tmem, a_tm + 8 * k, desc_make(DESC_HI_SW128, w_lo + 2 * k), idesc, 1);
+                    umma_commit_a(done_a + 8 * ob);    // frees the weight slot and the operand buffer
+                    if (++ws == C::NW) { ws = 0; wphase ^= 1; }
+                    if (++in_chunk == chunk || kb + 1 == kblocks) {
+                        umma_commit_a(cfull_a + 8 * buf);
+                        ++cc;
+                        in_chunk = 0;
+                    }
+                }
+            }
+        }
+    } else if (warp == 0) {
         if (elect_one()) {
             // ===== TMA producer =====
             int stage = 0;
@@ -229,19 +364,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     const uint32_t acc = in_chunk != 0;
                     // UMMA_K = 8 tf32 / 16 bf16 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
-                    if constexpr (TS) {
-                        constexpr uint32_t idesc_b = idesc_bf16(128, BN);
-                        const uint32_t a_tm = tmem_base + C::OP_COL0 + 64u * (uint32_t)stage;   // [fp32 A | bf16 A | bf16 A_r]
-#pragma unroll
-                        for (uint32_t k = 0; k < 2; ++k)   // A * W_r
-                            umma_bf16_ts(d_tmem, a_tm + 32 + 8 * k, desc_make(DESC_HI_SW64, s_lo + (C::OFF_WRB >> 4) + 2 * k), idesc_b, acc | k);
-#pragma unroll
-                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W
-                            umma_bf16_ts(d_tmem, a_tm + 48 + 8 * k, desc_make(DESC_HI_SW64, s_lo + (C::OFF_WB >> 4) + 2 * k), idesc_b, 1);
-#pragma unroll
-                        for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
-                            umma_tf32_ts(d_tmem, a_tm + 8 * k, desc_make(DESC_HI_SW128, s_lo + (C::A_BYTES >> 4) + 2 * k), idesc, 1);
-                    } else if constexpr (SPLIT) {
+                    if constexpr (SPLIT) {
                         constexpr uint32_t idesc_b = idesc_bf16(128, BN);
 #pragma unroll
                         for (uint32_t k = 0; k < 2; ++k)   // A * W_r
@@ -497,19 +620,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (SPLIT && warp >= 8 && warp < 12) {
         // ===== operand splitters: bf16(x) and bf16(x - trunc19(x)) tiles of the activation (and, unless pre-split, weight) tile =====
         const int tid = threadIdx.x - 256;  // 0..127
-        const SplitLane sl = split_lane(tid);
-        int stage = 0;
-        uint32_t phase = 0;
         PROF_DECL(pfull); PROF_DECL(spl); PROF_BEGIN(spl);
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-                PROF_T(pfull, mbar_wait(&full[stage], phase));
-                uint8_t* st = smem + stage * C::STAGE;
-                if constexpr (TS) {
-                    // thread = row of the tile: fp32 | bf16 | bf16 remainder of its 32 channels -> TMEM.  The operand buffer
-                    // is the stage's: full[stage] can only complete after the MMAs of its previous use have retired.
-                    const uint32_t sw = (uint32_t)(tid & 7);
-                    const uint8_t* src = st + tid * 128;
+        if constexpr (TS) {
+            // thread = row of the tile: fp32 | bf16 | bf16 remainder of its 32 channels -> TMEM operand buffer gk & 3
+            const uint32_t sw = (uint32_t)(tid & 7);
+            const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::OP_COL0;
+            int sa_i = 0;
+            uint32_t aphase = 0, gk = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                for (int kb = 0; kb < p.kblocks; ++kb, ++gk) {
+                    PROF_T(pfull, mbar_wait(&fullA[sa_i], aphase));
+                    const uint8_t* src = smem + sa_i * C::A_BYTES + tid * 128;
                     uint32_t f[32], xb[16], rb[16];
 #pragma unroll
                     for (uint32_t c = 0; c < 8; ++c) {
@@ -523,21 +644,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xb[i]) : "f"(x1), "f"(x0));
                         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rb[i]) : "f"(r1), "f"(r0));
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&emptyA[sa_i]);          // the tile lives in registers now
+                    if (gk >= (uint32_t)C::NO) {
+                        const uint32_t j = gk - C::NO;
+                        mbar_wait(&done[j & 3], (j >> 2) & 1u);         // the MMAs that read this operand buffer have retired
+                    }
                     tc_fence_after();
-                    const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::OP_COL0 + 64u * (uint32_t)stage;
+                    const uint32_t t0 = t_lane + 64u * (gk & 3);
                     tmem_st_32x32(t0, f);
                     tmem_st_32x16(t0 + 32, xb);
                     tmem_st_32x16(t0 + 48, rb);
                     tmem_st_wait();
                     tc_fence_before();
-                } else {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&opfull[gk & 3]);
+                    if (++sa_i == C::NA) { sa_i = 0; aphase ^= 1; }
+                }
+            }
+        } else {
+            const SplitLane sl = split_lane(tid);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    PROF_T(pfull, mbar_wait(&full[stage], phase));
+                    uint8_t* st = smem + stage * C::STAGE;
                     split_tile_bf16<128>(st, st + C::OFF_AB, st + C::OFF_ARB, sl);
                     if (!p.rem_rows) split_tile_bf16<BN>(st + C::A_BYTES, st + C::OFF_WB, st + C::OFF_WRB, sl);
                     fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&split_done[stage]);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&split_done[stage]);
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
         PROF_END(spl);
@@ -590,7 +729,7 @@ template <int BN, bool SPLIT, bool RES = false, bool TS = false>
 int launch_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const CUtensorMap& tO, const CUtensorMap& tR,
               const UmmaArgs& u, int grid, cudaStream_t s) {
     using C = Cfg<BN, SPLIT, RES, TS>;
-    static_assert(C::STAGES >= 2, "pipeline too shallow");
+    static_assert(TS ? (C::NA >= 3 && C::NW >= 2) : C::STAGES >= 2, "pipeline too shallow");
     static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
     SC_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, SPLIT, RES, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     conv_umma_kernel<BN, SPLIT, RES, TS><<<grid, C::THREADS, C::SMEM, s>>>(tA, tB, tB2, tO, tR, u);
