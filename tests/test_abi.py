@@ -34,6 +34,23 @@ def test_argument_errors_without_gpu():
     assert lib.scouter_plan_create(None, 0, 0, 0, ctypes.byref(h)) == -1
 
 
+def test_head_launch_count_and_workspace_are_host_logic():
+    """scouter_head_launch_count / _workspace_bytes validate their arguments and answer without touching a device:
+    1 launch when the fused kernel applies (needs the driver's tensor-map encoder, i.e. a GPU box), else projection + loop."""
+    lib = L.lib()
+    d = L.XSlotDesc()
+    d.d, d.num_classes, d.slots_per_class, d.to_k_layers, d.iters, d.loss_status, d.power = 64, 10, 1, 3, 3, 1, 2.0
+    io = L.HeadIO()
+    io.batch, io.h, io.w, io.channel, io.layout, io.math = 256, 7, 7, 2048, L.LAYOUT_NHWC, L.MATH_TC
+    n = lib.scouter_head_launch_count(ctypes.byref(d), ctypes.byref(io))
+    assert n in (1, 2, 3)                                  # 2 = fused kernel + on-the-fly weight split (no conv_w_split given)
+    ws = lib.scouter_head_workspace_bytes(ctypes.byref(d), ctypes.byref(io))
+    assert ws >= 4 * 256 * 49 * 64 * 4 + 2 * 64 * 2048 * 2  # split-K slabs + bf16 [W ; W_r] of conv1x1.weight
+    io.channel = 2050                                      # not a multiple of 16
+    assert lib.scouter_head_launch_count(ctypes.byref(d), ctypes.byref(io)) == 0
+    assert lib.scouter_head_workspace_bytes(ctypes.byref(d), ctypes.byref(io)) == 0
+
+
 def test_plan_shape_inference_on_cpu():
     """Shape inference and arena placement are host code: check both geometries without a GPU."""
     import scouter_b200 as sb
