@@ -49,11 +49,20 @@ constexpr int MAX_NW = 8;                        // weight slots (a.nw of them)
 constexpr int NO = 4;                            // TMEM operand buffers of 64 columns: [fp32 A (32) | bf16 A (16) | bf16 A_r (16)]
 constexpr int ND = 8;                            // "k-block retired" barriers (>= MAX_NW, NO); power of two (index = kb & 7)
 constexpr int OP_COL0 = 4 * XD;                  // operand buffers start after the four 64-column accumulators
+// Loop phase, tensor-core GRU gates: weight tiles t = matrix*2 + gate-half as [fp32 (64) | bf16 remainder (32)] and the four
+// 32-column accumulators.  Tiles 0-2 sit in columns the to_k MLP does not touch (it uses 0-63 and 256-383), so they can be
+// filled while the MLP runs; tile 3 and the accumulators take the MLP's columns afterwards.
+__device__ __forceinline__ uint32_t gw_col(int t) { return t == 0 ? 64u : (t == 1 ? 160u : (t == 2 ? 384u : 256u)); }
+__device__ __forceinline__ uint32_t gd_col(int t) { return t == 0 ? 0u : (t == 1 ? 32u : (t == 2 ? 352u : 480u)); }
 constexpr int MAX_NA = 8;
 constexpr int CHUNK = 4;                         // k-blocks per TMEM accumulation chunk (per issuer; see umma_conv.cu)
 
 struct FusedArgs {
     const float* conv_b;
+    const float* gru_w_ih;   // (192, 64) row-major, PyTorch layout: K-major rows for the tensor-core gate GEMM
+    const float* gru_w_hh;
+    const float* gru_b_ih;
+    const float* gru_b_hh;
     const float* packed;
     const float* pe;
     float* x_out;
@@ -65,6 +74,9 @@ struct FusedArgs {
     // shared-memory map (bytes from the 1024-aligned base); the phase-B regions alias the phase-A rings
     int na, nw, a_stage, off_w;
     int off_gru, off_small, off_bar;
+    int tc_gates;      // GRU gate GEMMs on the tensor cores (W_ih / W_hh resident in TMEM); needs G*S <= 32
+    int gw_early;      // byte offset of a 52 KB staging area inside the dead feature ring: the idle splitter warps move
+                       // W_ih / W_hh into TMEM while the to_k MLP runs (0 = no room: staged inside the first iteration)
 };
 
 __host__ __device__ inline int kb_floats(int img, int n, int S) {
@@ -136,7 +148,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* cempty = cfull + 4;           // [2][2] chunk drained by the 128 accumulator owners
     uint64_t* mlp_in = cempty + 4;          // to_k layer input is in TMEM (128 accumulator owners)
     uint64_t* mlp_out = mlp_in + 1;         // to_k layer MMAs retired
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mlp_out + 1);
+    uint64_t* gbar = mlp_out + 1;           // gate GEMMs of a GRU step retired (4 issuing threads)
+    uint64_t* acc_done = gbar + 1;          // every conv accumulator has been drained (128 accumulator owners)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_done + 1);
     float* tokb = reinterpret_cast<float*>(smem + a.off_bar + 512);   // [L][64] to_k biases (read by every accumulator owner)
     float* slots0 = tokb + a.L * XD;                                   // [S][64] initial slots, staged during phase A
 
@@ -180,6 +194,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         mbar_init(mlp_in, 128);
         mbar_init(mlp_out, 1);
+        mbar_init(gbar, 4);
+        mbar_init(acc_done, 128);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -346,6 +362,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
         // every conv MMA has retired (the last commits cover them all): the feature ring is dead, X takes its place
+        mbar_arrive(acc_done);
         const bool rowv = row < R;
         const int img = rowv ? row / n : 0, j = rowv ? row - img * n : 0;
         const bool live = rowv && img < nimg;
@@ -463,11 +480,82 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             stage += 2; if (stage >= NA) { stage -= NA; aphase ^= 1; }
         }
         if (tid == 256) { PROF_STORE(g_prof_head, 7, sp_fullA); PROF_STORE(g_prof_head, 8, sp_done); PROF_STORE(g_prof_head, 9, sp_fullW); PROF_STORE(g_prof_head, 10, sp_st); }
+        if (a.tc_gates && a.gw_early && a.iters > 1) {
+            // ----- these eight warps are idle until the loop: W_ih, then W_hh -> staging (inside the dead feature ring,
+            //       above X and K) -> TMEM, while the accumulator owners and issuer 0 run the to_k MLP -----
+            constexpr int GW_LD = XD * 4 + 16;
+            uint8_t* wst = smem + a.gw_early;
+            const int t8 = tid - 256, w8 = warp - 8;
+            const int grow = (w8 >> 2) * 128 + (w8 & 3) * 32 + lane;          // gate row of this thread within a matrix
+            const bool gv = grow < XG;
+            const uint32_t tm = tmem_base + ((uint32_t)((w8 & 3) * 32) << 16);
+            auto stage = [&](const float* w) {
+                for (int i = t8; i < XG * (XD / 4); i += 256) cp_async16(wst + (i >> 4) * GW_LD + (i & 15) * 16, w + (size_t)(i >> 4) * XD + (i & 15) * 4);
+                cp_async_wait_all();
+                named_bar_sync(2, 256);
+            };
+            auto load_row = [&](uint32_t (&f)[64], uint32_t (&rb)[32]) {
+                const uint8_t* wrow = wst + min(grow, XG - 1) * GW_LD;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (gv) v = *reinterpret_cast<const uint4*>(wrow + 16 * c);
+                    f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float r0 = __uint_as_float(f[2 * i]) - __uint_as_float(f[2 * i] & 0xFFFFE000u);
+                    const float r1 = __uint_as_float(f[2 * i + 1]) - __uint_as_float(f[2 * i + 1] & 0xFFFFE000u);
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rb[i]) : "f"(r1), "f"(r0));
+                }
+            };
+            auto store_tile = [&](int t, const uint32_t (&f)[64], const uint32_t (&rb)[32]) {
+                const uint32_t c0 = tm + gw_col(t);
+                uint32_t x[32], y[16];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) x[i] = f[32 * h + i];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = rb[16 * h + i];
+                    tmem_st_32x32(c0 + 32 * h, x);
+                    tmem_st_32x16(c0 + 64 + 16 * h, y);
+                }
+            };
+            uint32_t f[64], rb[32];
+            named_bar_sync(2, 256);              // both splitter groups have read their last feature stage
+            stage(a.gru_w_ih);
+            load_row(f, rb);
+            mbar_wait(acc_done, 0);              // conv accumulators (columns 64-255) and operand buffers are dead
+            tc_fence_after();
+            store_tile(w8 >> 2, f, rb);          // tiles 0, 1
+            tmem_st_wait();
+            named_bar_sync(2, 256);              // every row of W_ih has been read
+            stage(a.gru_w_hh);
+            load_row(f, rb);
+            if ((w8 >> 2) == 0) {                // tile 2 now; tile 3 (columns of the MLP operands) after the MLP
+                store_tile(2, f, rb);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            named_bar_sync(0, HT);               // the phase-A barrier (bar.sync 0 from this branch, same barrier as below)
+            if ((w8 >> 2) == 1) {
+                tc_fence_after();
+                store_tile(3, f, rb);
+                tmem_st_wait();
+                tc_fence_before();
+            }
+        } else {
+            tc_fence_before();
+            named_bar_sync(0, HT);
+        }
     }
-    tc_fence_before();
-    __syncthreads();
+    if (warp < 8) {
+        tc_fence_before();
+        named_bar_sync(0, HT);                   // end of phase A + MLP (the splitter warps arrive from their branch)
+    }
     cluster_arrive_relaxed();   // no more multicasts / remote arrivals from this CTA; matched by cluster_wait() before exit
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    tc_fence_after();
     PROF_END(phaseA); PROF_BEGIN(mlp);
 
     // =========================================== phase B ===========================================================
@@ -476,9 +564,77 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     PROF_END(mlp); PROF_BEGIN(loop);
     const float* K = Ka;
-    // the to_k weights (and the ring) are dead: bring in the GRU block while the first attention pass runs
-    if (a.iters > 1)
+    // ---- GRU gate GEMMs on the tensor cores (SR <= 32) ---------------------------------------------------------------
+    // gates^T[g, sr] = W[g, :] . x[sr, :]: the 192 gate rows are the M side (two 128-lane tiles per matrix), the slot rows
+    // the N side (32 columns).  W_ih and W_hh live in TMEM for the whole loop as [fp32 (64 cols) | bf16 remainder (32)]
+    // per tile (4 x 96 = 384 columns) -- thread = gate row, straight from the PyTorch (3d, d) layout; the per-step
+    // operands (updates, slots) are small K-major tiles in shared memory in three forms: fp32 (read as tf32), fp32
+    // remainder x - trunc19(x), bf16.  Same compensated product: W_t x_t + W_t x_r + W_r x.  80 MMAs of N = 32 per
+    // step (16-clk floor) issued by four threads, against 491k FMAs on the CUDA cores.
+    const bool tcg = a.tc_gates != 0 && a.iters > 1;
+    constexpr int GB_TILE32 = 2 * 32 * 128, GB_TILE16 = 2 * 32 * 64;     // two 32-channel k-blocks of 32 rows
+    uint8_t* gb = reinterpret_cast<uint8_t*>(Wsm);                        // [x | h] x [fp32 | fp32 rem | bf16]
+    constexpr int GB_OP = 2 * GB_TILE32 + GB_TILE16;
+    const int g_t = warp >> 2, g_row = (g_t & 1) * 128 + (warp & 3) * 32 + lane;   // this thread's (tile, gate row) for W / D
+    const bool g_valid = g_row < XG;
+    const uint32_t g_tm = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    float g_bias = 0.f;
+    auto put_operand = [&](int o, int sr, int e, float v) {              // element (sr, e) of operand o into its three tiles
+        uint8_t* base = gb + o * GB_OP;
+        const int kb = e >> 5, c = e & 31;
+        const int o32 = kb * (32 * 128) + sr * 128 + (((c >> 2) ^ (sr & 7)) << 4) + ((c & 3) << 2);
+        *reinterpret_cast<float*>(base + o32) = v;
+        *reinterpret_cast<float*>(base + GB_TILE32 + o32) = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        const int o16 = kb * (32 * 64) + sr * 64 + (((c >> 3) ^ ((sr >> 1) & 3)) << 4) + ((c & 7) << 1);
+        *reinterpret_cast<__nv_bfloat16*>(base + 2 * GB_TILE32 + o16) = __float2bfloat16_rn(v);
+    };
+    // W_ih, then W_hh: global -> shared memory with coalesced cp.async (row stride 272 bytes: the row-per-thread reads are
+    // conflict-free; reading the rows straight from global costs 32 L1 lines per load instruction) -> TMEM.  Each transfer
+    // (48 KB) hides behind a phase of the first iteration: W_ih behind the dots, W_hh behind normalise + update.
+    constexpr int GW_LD = XD * 4 + 16;
+    uint8_t* wst = gb + 2 * GB_OP;                                       // staging for one matrix: 192 rows x 272 B
+    auto stage_w = [&](const float* w) {
+        for (int i = tid; i < XG * (XD / 4); i += HT) cp_async16(wst + (i >> 4) * GW_LD + (i & 15) * 16, w + (size_t)(i >> 4) * XD + (i & 15) * 4);
+    };
+    auto w_to_tmem = [&](int mat) {                                     // all threads call; warps of matrix `mat` convert
+        cp_async_wait_all();
+        __syncthreads();
+        if ((g_t >> 1) == mat) {
+            uint32_t f[32], rb[16];
+            const uint8_t* wrow = wst + min(g_row, XG - 1) * GW_LD;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (g_valid) v = *reinterpret_cast<const uint4*>(wrow + 128 * h + 16 * c);
+                    f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float r0 = __uint_as_float(f[2 * i]) - __uint_as_float(f[2 * i] & 0xFFFFE000u);
+                    const float r1 = __uint_as_float(f[2 * i + 1]) - __uint_as_float(f[2 * i + 1] & 0xFFFFE000u);
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rb[i]) : "f"(r1), "f"(r0));
+                }
+                tmem_st_32x32(g_tm + gw_col(g_t) + 32 * h, f);
+                tmem_st_32x16(g_tm + gw_col(g_t) + 64 + 16 * h, rb);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+        }
+        __syncthreads();      // the staging area is free again; W of this matrix is visible to the issuers
+    };
+    const bool gw_late = tcg && a.gw_early == 0;     // no room for the early staging: W moves to TMEM inside iteration 0
+    if (tcg) {
+        if (gw_late) stage_w(a.gru_w_ih);
+        g_bias = g_valid ? __ldg((g_t >> 1 ? a.gru_b_hh : a.gru_b_ih) + g_row) : 0.f;
+        for (int i = tid; i < 2 * GB_OP / 16; i += HT) reinterpret_cast<uint4*>(gb)[i] = make_uint4(0u, 0u, 0u, 0u);   // rows >= SR stay zero
+        __syncthreads();
+        for (int idx = tid; idx < SR * XD; idx += HT) put_operand(1, idx / XD, idx % XD, slots[idx]);
+    } else if (a.iters > 1) {
+        // the to_k weights (and the ring) are dead: bring in the GRU block while the first attention pass runs
         for (int i = tid; i < W_FLOATS / 4; i += HT) cp_async16(Wsm + i * 4, a.packed + pk.gru_wih_t() + i * 4);
+    }
 
     // Thread maps of the loop, computed once (no runtime integer division inside the iterations).  The shared-memory
     // pipe delivers one wavefront per clock per SM against four FMA issue slots: every map below keeps its operands in
@@ -510,6 +666,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int rs_img1 = (warp + HW_) / S, rs_i1 = warp + HW_ - rs_img1 * S;
 
 #ifdef SCOUTER_PROF
+    if (tid == 0) g_prof_head[blockIdx.x * 32 + 18] = (unsigned long long)(clock64() - prof_begin_loop);   // loop set-up
     long long lp_t = clock64(), lp_acc[6] = {0, 0, 0, 0, 0, 0};
 #define LP_STAMP(k) do { const long long _n = clock64(); lp_acc[k] += _n - lp_t; if (tid == 0 && blockIdx.x == 0) g_trace_head[64 * 8 + it * 8 + (k)] = (unsigned long long)(_n - lp_t); lp_t = _n; } while (0)
 #else
@@ -535,6 +692,10 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
         __syncthreads();
+        if (gw_late && it == 0) {
+            w_to_tmem(0);
+            stage_w(a.gru_w_hh);
+        }
         LP_STAMP(0);
         for (int sr = warp, k = 0; sr < SR; sr += HW_, ++k) {   // row sums r_bi, lane-strided then a fixed shuffle tree
             int img, i;
@@ -575,7 +736,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             float s_ = upart[idx];
             for (int q = 1; q < nuq; ++q) s_ += upart[q * SR * XD + idx];
             upd[idx] = s_ * (1.0f / XD);
+            if (tcg && !last) put_operand(0, idx / XD, idx % XD, s_ * (1.0f / XD));
         }
+        if (tcg && !last) fence_proxy_async();   // operand tiles (updates here, slots in the cell pass) -> tensor-core reads
         __syncthreads();
         LP_STAMP(2);
         if (last) {
@@ -586,11 +749,45 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         } else {
             if (it == 0) {
-                cp_async_wait_all();
-                __syncthreads();
+                if (gw_late) {
+                    w_to_tmem(1);
+                } else if (!tcg) {
+                    cp_async_wait_all();
+                    __syncthreads();
+                }
             }
             LP_STAMP(3);
-            if (grt < 5) {                                   // gate pre-activations gi = W_ih u + b_ih, gh = W_hh h + b_hh
+            if (tcg) {
+                if (warp < 4 && lane == 0) {                 // issuer of tile `warp`: (matrix, gate half)
+                    constexpr uint32_t idesc = idesc_tf32(128, 32), idesc_b = idesc_bf16(128, 32);
+                    const uint32_t t = (uint32_t)warp, o = t >> 1;
+                    const uint32_t d_t = tmem_base + gd_col((int)t), w_t = tmem_base + gw_col((int)t);
+                    const uint32_t b32 = desc_lo(smem_u32(gb + o * GB_OP)), br32 = b32 + (GB_TILE32 >> 4), b16 = b32 + (2 * GB_TILE32 >> 4);
+                    tc_fence_after();
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j)     // W_t x_t
+                        umma_tf32_ts(d_t, w_t + 8 * j, desc_make(DESC_HI_SW128, b32 + (j >> 2) * (32 * 128 >> 4) + 2 * (j & 3)), idesc, j != 0);
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j)     // W_t x_r
+                        umma_tf32_ts(d_t, w_t + 8 * j, desc_make(DESC_HI_SW128, br32 + (j >> 2) * (32 * 128 >> 4) + 2 * (j & 3)), idesc, 1);
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j)     // W_r x (bf16)
+                        umma_bf16_ts(d_t, w_t + 64 + 8 * j, desc_make(DESC_HI_SW64, b16 + (j >> 1) * (32 * 64 >> 4) + 2 * (j & 1)), idesc_b, 1);
+                    umma_commit(gbar);
+                }
+                mbar_wait(gbar, (uint32_t)it & 1u);
+                tc_fence_after();
+                uint32_t r[32];
+                tmem_ld_32x32(g_tm + gd_col(g_t), r);
+                tmem_ld_wait();
+                if (g_valid) {
+                    float* gp = gates + (g_t >> 1) * XG + g_row;         // [sr][ih | hh][gate]
+#pragma unroll
+                    for (int sr = 0; sr < 32; ++sr)
+                        if (sr < SR) gp[sr * 2 * XG] = __uint_as_float(r[sr]) + g_bias;
+                }
+                tc_fence_before();
+            } else if (grt < 5) {                            // gate pre-activations gi = W_ih u + b_ih, gh = W_hh h + b_hh
                 const float* WT = Wsm + gwhich * XD * XG + gg0;                    // [e][192], this thread's gate quad
                 const float4 b4 = *reinterpret_cast<const float4*>(Wsm + 2 * XD * XG + gwhich * XG + gg0);
                 const float* src = gwhich ? slots : upd;
@@ -630,7 +827,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const float zg = sigm(gi[XD + e] + gh[XD + e]);
                 const float ng = tanhf(gi[2 * XD + e] + rg_ * gh[2 * XD + e]);
                 const float hp = slots[idx];
-                slots[idx] = (hp - ng) * zg + ng;              // ATen's form of (1-z)*n + z*h
+                const float hn = (hp - ng) * zg + ng;          // ATen's form of (1-z)*n + z*h
+                slots[idx] = hn;
+                if (tcg) put_operand(1, sr, e, hn);
             }
         }
         __syncthreads();
@@ -659,6 +858,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     PROF_END(loop);
     if (tid == 0) { PROF_STORE(g_prof_head, 0, phaseA); PROF_STORE(g_prof_head, 1, mlp); PROF_STORE(g_prof_head, 2, loop); }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
     cluster_wait();       // the peer may still be arriving on this CTA's barriers until it has left phase A
 }
 
@@ -686,7 +888,7 @@ size_t layout(int G, int n, int S, int L, FusedArgs* out) {
     const size_t tok_end = align_up((size_t)(2 * R * LDX + kb_floats(G, n, S)) * 4, 16);
     const size_t small = align_up((size_t)(2 * SR * XD + 2 * SR + 64) * 4, 16);
     const size_t off_small = tok_end;
-    const size_t off_gru = off_small + small;
+    const size_t off_gru = align_up(off_small + small, 1024);   // GRU block / tensor-core gate operand tiles (swizzled: 1024-aligned)
     static int nw_env = [] { const char* e = getenv("SCOUTER_HEAD_NW"); int v = e ? atoi(e) : 6; return v < 2 ? 2 : (v > MAX_NW ? MAX_NW : v); }();
     // the weight tile comes from L2 through a multicast TMA whose latency is ~2-3 k-blocks: prefer a deep weight ring, then
     // as many feature stages as fit
@@ -696,6 +898,8 @@ size_t layout(int G, int n, int S, int L, FusedArgs* out) {
             if ((size_t)na * a_stage < (size_t)R * LDX * 4) continue;   // X is written while the weight ring still feeds the MLP
             const size_t off_w = na * a_stage;
             const size_t ring_end = off_w + (size_t)nw * W_SLOT;
+            // GRU block of the FMA path (99.8 KB) or the [W_ih ; W_hh] staging of the tensor-core path (384 rows x 272 B)
+            // GRU block of the FMA path (99.8 KB), or operand tiles (40 KB) + one-matrix staging (51 KB) of the tensor-core path
             const size_t body = std::max(ring_end, off_gru + (size_t)W_FLOATS * 4);
             const size_t off_bar = align_up(body, 16);
             const size_t total = off_bar + 512 + (size_t)(L + S) * XD * 4 + 1024;   // barriers, to_k biases, initial slots, slack
@@ -741,15 +945,23 @@ int head_fused_launch(const scouter_xslot_desc_t* d, const void* packed, const s
     const int n = io->h * io->w;
     FusedArgs a;
     a.conv_b = io->conv_b; a.packed = (const float*)packed; a.pe = io->pe;
+    a.gru_w_ih = d->gru_w_ih; a.gru_w_hh = d->gru_w_hh; a.gru_b_ih = d->gru_b_ih; a.gru_b_hh = d->gru_b_hh;
     a.x_out = io->x_out; a.logits = io->logits; a.attn = io->attn; a.attn_sum = io->attn_sum;
     a.B = io->batch; a.n = n;
     a.S = d->num_classes * d->slots_per_class; a.C = d->num_classes; a.spc = d->slots_per_class; a.L = d->to_k_layers;
     a.G = pick_group(io->batch, n, a.S, a.L);
     SC_CHECK_ARG(a.G > 0, SCOUTER_E_UNSUPPORTED, "head_fused: no unit size fits");
-    a.iters = d->iters; a.loss_status = d->loss_status;
+    static bool no_tc_gates = getenv("SCOUTER_HEAD_FMA_GATES") != nullptr;
+    a.tc_gates = (!no_tc_gates && a.G * a.S <= 32) ? 1 : 0;
     a.kblocks = io->channel / 32;
     const size_t smem = layout(a.G, n, a.S, a.L, &a);
     SC_CHECK_ARG(smem, SCOUTER_E_UNSUPPORTED, "head_fused: shared-memory layout does not fit");
+    {   // staging for one GRU matrix (192 rows x 272 B) above X and K, inside the feature ring that is dead by then
+        const size_t lo = align_up((size_t)2 * a.G * n * LDX * 4, 1024), need = (size_t)XG * (XD * 4 + 16);
+        static bool no_early = getenv("SCOUTER_HEAD_GW_LATE") != nullptr;
+        a.gw_early = (a.tc_gates && !no_early && lo + need <= (size_t)a.off_w) ? (int)lo : 0;
+    }
+    a.iters = d->iters; a.loss_status = d->loss_status;
     EncodeTiledFn enc = encode_fn();
     SC_CHECK_ARG(enc, SCOUTER_E_UNSUPPORTED, "head_fused: cuTensorMapEncodeTiled is not available from the driver");
     // bf16 [W ; W - trunc19(W)] of conv1x1.weight: given by the caller (packed once per parameter version) or derived here

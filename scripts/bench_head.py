@@ -87,7 +87,7 @@ if a.prof:
     arr = np.array(buf[:], dtype=np.float64).reshape(256, 32)[:min(units, 256)]
     names = {0: "phaseA", 1: "mlp", 2: "loop", 3: "prodA.wait_empty", 4: "prodW.wait_done", 5: "iss0.wait_cempty", 6: "iss0.wait_opfull",
              7: "split0.wait_fullA", 8: "split0.wait_done", 9: "split0.wait_fullW", 10: "split0.tmem_st",
-             12: "loop.dots", 13: "loop.normalise", 14: "loop.update", 15: "loop.gru_wait", 16: "loop.gates", 17: "loop.cell"}
+             12: "loop.dots", 13: "loop.normalise", 14: "loop.update", 15: "loop.gru_wait", 16: "loop.gates", 17: "loop.cell", 18: "loop.setup"}
     print("per-CTA clocks (mean / max):", {names.get(i, i): (int(arr[:, i].mean()), int(arr[:, i].max())) for i in range(20) if arr[:, i].any()})
     tb = (C.c_ulonglong * (128 * 8))()
     lib.scouter_trace_read_head(tb, 128 * 8)

@@ -1,7 +1,6 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "stream or host" 2>&1 | tail -3
-timeout 600 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tee gpurun_out/bench_tc.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'], d['e2e']['synchronous_call_value'], 'head', d['roofline']['ms'], d['roofline']['frac'], d['clocks'])"
-tail -2 gpurun_out/bench.err
+echo "== head tests"
+timeout 600 python -m pytest tests/test_gpu_head_fused.py tests/test_gpu_conv.py tests/test_gpu_parity.py -m gpu -q -x -k "head or slot_model or small_and_odd or full_size or other_hot or xslot or fused" 2>&1 | tail -3
+timeout 120 python scripts/bench_head.py --fs 7 --prof 2>&1 | grep "per-CTA" | cut -c1-1100
+timeout 120 python scripts/bench_head.py --fs 7 2>&1 | tail -1
+timeout 120 python scripts/bench_head.py --fs 9 2>&1 | tail -1
