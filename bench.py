@@ -118,6 +118,17 @@ def cpu_reference_rate(batch, size, steps, warmup):
 HEAD_DRAM_TRAFFIC = 104132608 + 4102656
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """Print the result line on the real stdout (see main)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(line, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -131,6 +142,12 @@ def main():
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that write banners to file descriptor 1 (NCCL prints its version
+    # there at communicator creation) go to stderr until the line is printed
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = (f"cfg3: ImageNet-10 resnest26d + negative xSlot (loss_status -1, to_k_layer 3, 10x1 slots), "
@@ -141,7 +158,7 @@ def main():
             return
         rate, spb, cores = cpu_reference_rate(a.cpu_sample, a.size, a.steps, min(a.warmup, 1))
         sample = f"{a.cpu_sample} images/step x {a.steps} steps of the same workload (oracle port of the reference, torch CPU ops)"
-        print(json.dumps({
+        emit(json.dumps({
             "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": min(a.warmup, 1), "ms_per_step": spb * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -282,7 +299,7 @@ def main():
     tf32_peak = pk["bf16_sustained"] / 2
     cpu_rate, cpu_spb, cores = cpu_reference_rate(a.cpu_sample, a.size, 3, 1)
     launches = m.launches_per_forward(tuple(x.shape), dev)
-    print(json.dumps({
+    emit(json.dumps({
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"tc": "tf32 + 2 bf16 correction products (error-compensated, fp32-class; fp32 accumulate)", "tc_fast": "tf32", "fp32": "f32"}[a.math], "data": "synthetic",
