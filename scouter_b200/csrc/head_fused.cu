@@ -40,7 +40,6 @@ namespace {
 constexpr int HT = 512, HW_ = HT / 32;
 constexpr int LDX = XD + 4;
 constexpr int W_FLOATS = 2 * XD * XG + 2 * XG;   // GRU block: WihT[64][192], WhhT[64][192], b_ih[192], b_hh[192]
-constexpr int TOK_FLOATS = XD * XD + XD;         // one to_k layer: WT[64][64], b[64]
 
 // phase-A shared memory: [NA feature stages | NW weight slots]; tensor memory: [4 accumulators | NO operand buffers]
 constexpr int W_F32 = XD * 128;                  // 64 rows x 32 tf32
@@ -164,7 +163,6 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* upd = slots + SR * XD;
     float* rsum = upd + SR * XD;
     float* usum = rsum + SR;
-    float* misc = usum + SR;
     float* gates = Kb;
     float* attnT = Kb + SR * 2 * XG;
 

@@ -27,6 +27,8 @@
 #include "ptx.cuh"
 #include "umma.cuh"
 
+#pragma nv_diag_suppress 177   // Cfg members that only some instantiations reference
+
 namespace scouter {
 using namespace ptx;
 

@@ -56,7 +56,6 @@ struct HCfg {
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr int EPI_GROUPS = BN == 128 ? 2 : 1;
     static constexpr int NC = BN / EPI_GROUPS;
-    static constexpr int THREADS = 512;
     static constexpr int MAX_ST = 8;
     static constexpr int OUT_STAGE = 128 * 64;   // staging of 16 columns x <=128 compact tile rows, SWIZZLE_64B
     static constexpr int OUT_BYTES = EPI_GROUPS * 2 * OUT_STAGE;
