@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscouter_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "head_fused.cu", "umma_conv.cu", "umma_halo.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "head_fused.cu", "stem_ts.cu", "umma_conv.cu", "umma_halo.cu"]
 
 OK = 0
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1

@@ -257,7 +257,7 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
                 StemArgs a{ptr(o.src), o.w, o.b, ptr(o.dst), sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.stride, o.pad,
                            (o.flags & SCOUTER_F_RELU) ? 1 : 0, rnd,
                            plan->host_w[i].empty() ? nullptr : plan->host_w[i].data(),
-                           plan->host_b[i].empty() ? nullptr : plan->host_b[i].data()};
+                           plan->host_b[i].empty() ? nullptr : plan->host_b[i].data(), split};
                 rc = launch_stem_conv(a, s);
                 break;
             }

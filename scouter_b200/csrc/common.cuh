@@ -89,8 +89,11 @@ struct StemArgs {
     int round_out;
     const float* w_host;  // host copies of w / bias (plan-owned) for the constant-bank stem kernel, or null
     const float* b_host;
+    int tc;               // SCOUTER_MATH_TC: the tensor-core stem (stem_ts.cu) may take it
 };
 int launch_stem_conv(const StemArgs& a, cudaStream_t s);
+bool stem_ts_supported(const StemArgs& a);
+int launch_stem_ts(const StemArgs& a, cudaStream_t s);
 
 int launch_maxpool(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo, int k, int stride,
                    int pad, cudaStream_t s);

@@ -332,6 +332,7 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
 }
 
 int launch_stem_conv(const StemArgs& a, cudaStream_t s) {
+    if (stem_ts_supported(a)) return launch_stem_ts(a, s);
     if (a.w_host && a.k == 3 && a.stride == 2 && a.pad == 1 && a.B <= 65535) {
         if (a.Cin == 3 && a.Cout == 32) return launch_stem_tiled<3, 32>(a, s);
         if (a.Cin == 1 && a.Cout == 64) return launch_stem_tiled<1, 64>(a, s);
