@@ -6,9 +6,9 @@
 * ``BackboneRunner``   ``backbone(x)`` standalone: same return value as the reference's
                        ``ResNet.forward`` (classifier output, or the NCHW-flattened features once
                        pool/fc are ``Identical``).
-* ``SlotModelRunner``  the whole ``SlotModel.forward`` (slot_model.py:105-127): backbone program + fused
-                       xSlot head + finalize, optionally captured in a CUDA graph, plus the
-                       host-buffer entry (``forward_host``) that bench.py times end to end.
+* ``CompiledProgram``  a ``scouter_plan_t`` handle bound to one input shape and its torch-allocated arena;
+                       ``slot_model.SlotModel`` runs it followed by the fused xSlot head + finalize
+                       (slot_model.py:105-127), optionally inside a CUDA graph.
 
 All device memory (arena, workspaces, outputs) is torch-allocated and cached per input shape; the
 library only sees raw pointers.  Weight packs are rebuilt when any parameter/buffer version changes.

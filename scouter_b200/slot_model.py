@@ -182,7 +182,17 @@ class SlotModel(nn.Module):
             st.ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
             st.ws_off = (-st.ws.data_ptr()) % 1024
             st.ws_bytes = nbytes
+        # every device pointer a captured graph bakes in besides the arena: a re-packed parameter block or
+        # re-assigned conv1x1 parameters make captured graphs of this state stale (see _graph_current)
+        st.head_sig = (st.io.conv_w, st.io.conv_b, st.io.conv_w_split, packed.data_ptr())
         return desc, packed
+
+    def _graph_current(self, st, dev) -> bool:
+        """True if graphs captured for ``st`` still point at the live head parameters; refreshes ``st.head_sig``.
+        (Backbone changes drop the whole state in ``_program``; in-place updates of conv1x1 keep their pointers
+        and are read by the replay directly.)"""
+        self._head_params(st, dev)
+        return getattr(st, "graph_sig", None) == st.head_sig
 
     def _launch(self, st, x, target):
         """Enqueue backbone program + head + finalize on the current stream (no sync, graph-capturable)."""
@@ -236,6 +246,12 @@ class SlotModel(nn.Module):
             return output
 
     def _replay(self, st, x):
+        if not self._graph_current(st, x.device):
+            st.graph = None                               # head parameters were re-packed since the capture
+            hs = getattr(st, "host_stream", None)
+            if hs is not None:
+                hs["graphs"], hs["used"] = [None, None], [False, False]
+            st.graph_sig = st.head_sig
         if st.graph is None:
             st.static_in = x.clone()
             self._launch(st, st.static_in, None)          # warm-up outside capture (lazy module init, attributes)
@@ -358,6 +374,10 @@ class SlotModel(nn.Module):
                       "outs": [torch.empty(st.log_probs.shape, dtype=torch.float32).pin_memory() for _ in range(2)],
                       "graphs": [None, None], "used": [False, False]}
                 st.host_stream = hs
+            if not self._graph_current(st, dev):              # head parameters re-packed since the captures
+                st.graph = None
+                hs["graphs"], hs["used"] = [None, None], [False, False]
+                st.graph_sig = st.head_sig
             bufs, outs, used = hs["bufs"], hs["outs"], hs["used"]
             graphs = hs["graphs"] if (self.use_cuda_graph and dataset is None) else None
             ev_in = [torch.cuda.Event() for _ in range(2)]

@@ -226,6 +226,28 @@ def test_forward_host_and_cuda_graph_agree_with_eager(dev):
     assert torch.equal(eager, host) and torch.equal(eager, g1) and torch.equal(g1, g2)
 
 
+def test_cuda_graph_follows_head_parameter_updates(dev):
+    """A captured forward graph bakes in the packed head-parameter block and the bf16 split of conv1x1.weight;
+    updating head parameters re-packs both, so the stale graph must be dropped (backbone updates drop the whole
+    shape state in ``_program``) -- never replayed against freed or outdated weights."""
+    z, meta = load_golden("cfg2_resnest26d_pos_224")
+    m = build(meta, dev, L.MATH_TC)
+    m.keep_attn = False
+    x = synth_images(meta["batch"], meta["cin"], meta["size"], meta["size"]).to(dev)
+    with torch.no_grad():
+        m.use_cuda_graph = True
+        g0, g0b = m(x).cpu(), m(x).cpu()
+        m.slot.initial_slots.mul_(1.25)
+        m.slot.gru.bias_ih_l0.add_(0.05)
+        m.conv1x1.weight.mul_(0.9)
+        g1, g1b = m(x).cpu(), m(x).cpu()
+        m.use_cuda_graph = False
+        e1 = m(x).cpu()
+    assert torch.equal(g0, g0b) and torch.equal(g1, g1b)
+    assert not torch.equal(g0, g1)
+    assert torch.equal(g1, e1)
+
+
 def test_training_mode_raises_not_falls_back(dev):
     m = sb.SlotModel(make_args()).to(dev).train()
     with pytest.raises(NotImplementedError):
