@@ -119,6 +119,16 @@ int scouter_head_finalize(const float* logits, const float* attn_sum, const int6
 int scouter_vis_maps_u8(const float* attn /* (B,S,n) */, int batch, int num_classes, int slots_per_class, int n,
                         int vis_id, uint8_t* maps, scouter_stream_t stream);
 
+/* f3  the explanation output path (test.py:33-35, 40-44): the PNG round trip
+ *     np.array(Image.open('sloter/vis/slot_{id}.png').resize(image_raw.size, resample=Image.BILINEAR))
+ * on the device.  `maps` = `count` uint8 maps of h x w (the output of scouter_vis_maps_u8, h*w = n); `out` =
+ * (count, out_h, out_w) uint8, bit-identical to Pillow's 8-bit bilinear resampler (Resample.c: triangle filter of
+ * support max(1, in/out), 22-bit fixed-point coefficients, horizontal then vertical pass with a uint8 image in
+ * between); `ratios` = (count) float64 attention ratios sum(map)/(h*w*255) of the un-resized maps (test.py:43).
+ * Either output may be NULL.  Down-scaling works too (same filter); no workspace, graph-capturable. */
+int scouter_vis_upsample_u8(const uint8_t* maps /* (count,h,w) */, int count, int h, int w, int out_h, int out_w,
+                            uint8_t* out, double* ratios, scouter_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a6 + a7 + a9  the fused xSlot head: conv1x1 + ReLU (slot_model.py:108-109), + PE (:110-111),
  * SlotAttention (:116).  `feat` is the backbone output.

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscouter_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "head_fused.cu", "stem_ts.cu", "umma_conv.cu", "umma_halo.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "head_fused.cu", "stem_ts.cu", "vis.cu", "umma_conv.cu", "umma_halo.cu"]
 
 OK = 0
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
@@ -91,6 +91,7 @@ SIGNATURES = {
     "scouter_head_finalize": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                         _fp, _fp, _fp]),
     "scouter_vis_maps_u8": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp]),
+    "scouter_vis_upsample_u8": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "scouter_conv_forward": (C.c_int, [C.POINTER(Op), _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "scouter_conv_path": (C.c_int, [C.POINTER(Op), C.c_int, C.c_int, C.c_int, C.c_int]),
     "scouter_head_workspace_bytes": (C.c_size_t, [C.POINTER(XSlotDesc), C.POINTER(HeadIO)]),

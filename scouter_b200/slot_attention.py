@@ -97,13 +97,42 @@ class SlotAttention(nn.Module):
         return d, packed
 
     # -- vis branch (:68-85) ------------------------------------------------------------------
-    def emit_vis(self, attn: torch.Tensor, logits: torch.Tensor):
+    def vis_maps(self, attn: torch.Tensor, vis_id=None, out_size=None, hw=None):
+        """The explanation outputs on the device, all CUDA tensors:
+
+        * ``maps`` (C,h,w) uint8 -- per-class sum of ``attn[vis_id]``, joint min-max, *255, truncation (:68-80);
+        * ``heat`` (C,H,W) uint8 -- ``maps`` resized to ``out_size=(H,W)``, bit-identical to the reference's
+          ``Image.open(slot_{id}.png).resize(image.size, Image.BILINEAR)`` (test.py:35); None without ``out_size``;
+        * ``ratios`` (C) float64 -- ``sum(map)/(h*w*255)`` (test.py:43).
+        """
         b, s, n = attn.shape
-        maps = torch.empty(self.num_classes, n, dtype=torch.uint8, device=attn.device)
-        L.check(L.lib().scouter_vis_maps_u8(attn.data_ptr(), b, self.num_classes, self.slots_per_class, n, self.vis_id,
-                                            maps.data_ptr(), L.stream_ptr()), "scouter_vis_maps_u8")
-        fs = int(n ** 0.5)
-        self.last_vis_maps = maps.view(self.num_classes, fs, fs).cpu().numpy()
+        vis_id = self.vis_id if vis_id is None else vis_id
+        if hw is None:
+            fs = int(n ** 0.5)                                   # the reference's square-map assumption (:76)
+            hw = (fs, fs)
+        if hw[0] * hw[1] != n:
+            raise L.ScouterError(f"vis_maps: {n} tokens do not form a {hw[0]}x{hw[1]} map")
+        if not attn.is_cuda or attn.dtype != torch.float32 or not attn.is_contiguous():
+            raise L.ScouterError("vis_maps: attn must be a contiguous fp32 CUDA tensor (no CPU path)")
+        dev = attn.device
+        c = self.num_classes
+        with torch.cuda.device(dev):
+            maps = torch.empty(c, hw[0], hw[1], dtype=torch.uint8, device=dev)
+            L.check(L.lib().scouter_vis_maps_u8(attn.data_ptr(), b, c, self.slots_per_class, n, vis_id, maps.data_ptr(),
+                                                L.stream_ptr()), "scouter_vis_maps_u8")
+            ratios = torch.empty(c, dtype=torch.float64, device=dev)
+            heat = None
+            oh = ow = 0
+            if out_size is not None:
+                oh, ow = int(out_size[0]), int(out_size[1])
+                heat = torch.empty(c, oh, ow, dtype=torch.uint8, device=dev)
+            L.check(L.lib().scouter_vis_upsample_u8(maps.data_ptr(), c, hw[0], hw[1], oh, ow, L.ptr(heat), ratios.data_ptr(),
+                                                    L.stream_ptr()), "scouter_vis_upsample_u8")
+        return maps, heat, ratios
+
+    def emit_vis(self, attn: torch.Tensor, logits: torch.Tensor):
+        maps, _, _ = self.vis_maps(attn)
+        self.last_vis_maps = maps.cpu().numpy()
         if self.vis_dir:
             from PIL import Image
             os.makedirs(self.vis_dir, exist_ok=True)

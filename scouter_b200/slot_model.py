@@ -227,6 +227,7 @@ class SlotModel(nn.Module):
         with torch.cuda.device(x.device):
             st = self._state(x)
             self.feature_size = st.fh
+            self._last_fhw = (st.fh, st.fw)
             if target is not None:
                 target = target.to(device=x.device, dtype=torch.int64).contiguous()
             if self.use_cuda_graph and target is None:
@@ -244,6 +245,28 @@ class SlotModel(nn.Module):
                 ls = st.losses.clone()
                 return [output, [ls[0], ls[1], ls[2]]]
             return output
+
+    # -- f3: explanation output path (test.py:20-44 without the PNG round trip) ---------------------
+    def explain(self, x, vis_id=0, out_size=None):
+        """Forward + explanation maps of image ``vis_id``, everything on the device.  Returns a dict of CUDA tensors:
+        ``log_probs`` (B,C); ``maps`` (C,fh,fw) uint8 = the arrays the reference saves as ``slot_{id}.png``
+        (slot_attention.py:68-83); ``heat`` (C,H,W) uint8 = those maps resized to ``out_size`` (default: the input's
+        H,W), bit-identical to ``Image.resize(image.size, Image.BILINEAR)`` (test.py:35); ``ratios`` (C) float64 =
+        the attention ratio of test.py:43 for every class map.  The jet-colormap overlay (sloter/utils/vis.py:7-28,
+        matplotlib) stays on the host."""
+        if not self.use_slot:
+            raise L.ScouterError("explain: the model has no slot head (use_slot=False)")
+        keep = self.keep_attn
+        self.keep_attn = True
+        try:
+            log_probs = self.forward(x)
+        finally:
+            self.keep_attn = keep
+        if not 0 <= vis_id < x.shape[0]:
+            raise L.ScouterError(f"explain: vis_id={vis_id} outside the batch of {x.shape[0]}")
+        size = tuple(x.shape[-2:]) if out_size is None else out_size
+        maps, heat, ratios = self.slot.vis_maps(self.last_attn, vis_id, size, hw=self._last_fhw)
+        return {"log_probs": log_probs, "maps": maps, "heat": heat, "ratios": ratios}
 
     def _replay(self, st, x):
         if not self._graph_current(st, x.device):

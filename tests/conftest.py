@@ -22,10 +22,17 @@ def load_golden(name):
     return z, meta
 
 
+def vis_cases():
+    """{name: (maps, heat, ratios)} of tests/golden/vis_upsample.npz (Pillow's own outputs, oracle/make_golden_vis.py)."""
+    z = np.load(os.path.join(GOLDEN, "vis_upsample.npz"), allow_pickle=False)
+    meta = json.loads(bytes(z["meta"]).decode())
+    return {n: (z[n + ".maps"], z[n + ".heat"], z[n + ".ratios"]) for n in meta["cases"]}, meta
+
+
 def golden_names(kind):
     out = []
     for f in sorted(os.listdir(GOLDEN)):
-        if f.endswith(".npz") and f not in ("pe_sine.npz", "preprocess_u8.npz"):
+        if f.endswith(".npz") and f not in ("pe_sine.npz", "preprocess_u8.npz", "vis_upsample.npz"):
             if (kind == "head") == f.startswith("head_"):
                 out.append(f[:-4])
     return out

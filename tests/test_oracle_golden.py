@@ -66,3 +66,26 @@ def test_preprocess_oracle_vs_reference_golden(dataset):
     mean, std = sb.SlotModel.NORMALIZE[dataset]
     got = oh.preprocess_u8(z[dataset + "_u8"], mean, std).numpy()
     assert got.dtype == np.float32 and np.array_equal(got, z[dataset + "_f32"])
+
+
+def test_vis_upsample_oracle_vs_pillow_golden():
+    """f3: the numpy restatement of Pillow's 8-bit bilinear resampler equals Pillow's own output, bit for bit."""
+    from conftest import vis_cases
+    from oracle import vis as ov
+    cases, meta = vis_cases()
+    assert len(cases) == 8
+    for name, (maps, heat, ratios) in cases.items():
+        got = ov.resize_bilinear_u8(maps, heat.shape[1], heat.shape[2])
+        assert got.dtype == np.uint8 and np.array_equal(got, heat), name
+        assert np.array_equal(np.array([ov.attention_ratio(m) for m in maps]), ratios), name
+
+
+def test_vis_upsample_oracle_vs_installed_pillow():
+    """Same check against whatever Pillow is installed where the tests run, on fresh random maps and sizes."""
+    Image = pytest.importorskip("PIL.Image")
+    from oracle import vis as ov
+    rng = np.random.RandomState(7)
+    for h, w, oh_, ow in [(7, 7, 224, 224), (9, 9, 260, 260), (7, 9, 61, 35), (9, 9, 3, 4), (5, 5, 5, 40)]:
+        m = rng.randint(0, 256, (h, w)).astype(np.uint8)
+        ref = np.array(Image.fromarray(m).resize((ow, oh_), resample=Image.BILINEAR), dtype=np.uint8)
+        assert np.array_equal(ov.resize_bilinear_u8(m, oh_, ow), ref), (h, w, oh_, ow)
