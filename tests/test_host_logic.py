@@ -109,3 +109,28 @@ def test_round_tf32_is_round_to_nearest_ties_away():
     assert torch.all((r.view(torch.int32) & 0x1FFF) == 0)                     # 13 low mantissa bits cleared
     assert r[0] == 1.0 and r[1] == 1.0 + 2 ** -10 and r[3] == -1.0 - 2 ** -10   # ties away from zero
     assert float((r - x).abs().max() / x.abs().max()) <= 2 ** -11
+
+
+def test_reference_checkpoint_flow_stage1_to_stage2(tmp_path, monkeypatch):
+    """Row f4, host side: the reference's two-stage recipe on its own checkpoint format.  Stage 1 (``use_slot False``)
+    saves ``{'model': state_dict, ...}`` (train.py:188-194) with ``backbone.``-prefixed keys incl. ``backbone.fc.*``;
+    stage 2 (``use_slot True, use_pre True``) strips the prefix and loads it into the trunk before pool/fc become
+    ``Identical`` (slot_model.py:26-40); test.py:117-120 loads a stage-2 checkpoint with strict keys."""
+    monkeypatch.chdir(tmp_path)
+    stage1 = sb.SlotModel(make_args(use_slot=False))
+    sd1 = fill_state_dict(stage1.state_dict(), seed=5)
+    assert "backbone.fc.weight" in sd1 and all(k.startswith("backbone.") for k in sd1)
+    (tmp_path / "saved_model").mkdir()
+    torch.save({"model": sd1, "epoch": 3}, tmp_path / "saved_model" / "ImageNet_no_slot_checkpoint.pth")
+
+    stage2 = sb.SlotModel(make_args(use_slot=True, use_pre=True))
+    sd2 = stage2.state_dict()
+    assert not any(k.startswith("backbone.fc.") for k in sd2)                 # fc is Identical after the load
+    trunk = [k for k in sd1 if not k.startswith("backbone.fc.")]
+    assert trunk and all(torch.equal(sd1[k], sd2[k]) for k in trunk)         # every trunk tensor came from stage 1
+
+    torch.save({"model": fill_state_dict(sd2, seed=6), "epoch": 9, "args": None}, tmp_path / "ImageNet_use_slot_checkpoint.pth")
+    fresh = sb.SlotModel(make_args())
+    ck = torch.load(tmp_path / "ImageNet_use_slot_checkpoint.pth", map_location="cpu", weights_only=False)
+    fresh.load_state_dict(ck["model"])                                        # strict
+    assert all(torch.equal(v, ck["model"][k]) for k, v in fresh.state_dict().items())
