@@ -297,7 +297,9 @@ def main():
     head_gbs = head_bytes / (ms_head / 1e3) / 1e9
     bb_tflops = BACKBONE_GFLOP.get(a.size, 7.24 * (a.size / 224.0) ** 2) * a.batch / (ms_bb / 1e3) / 1e3
     tf32_peak = pk["bf16_sustained"] / 2
-    cpu_rate, cpu_spb, cores = cpu_reference_rate(a.cpu_sample, a.size, 3, 1)
+    # bounded CPU sample: ~10 s of host work at N=1 (the reported baseline), a token 3 steps on multi-GPU lines
+    cpu_steps = 24 if world == 1 else 3
+    cpu_rate, cpu_spb, cores = cpu_reference_rate(a.cpu_sample, a.size, cpu_steps, 1)
     launches = m.launches_per_forward(tuple(x.shape), dev)
     emit(json.dumps({
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -325,7 +327,8 @@ def main():
                               "achieved": bb_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": bb_tflops / tf32_peak,
                               "ms": ms_bb, "peak_source": pk["src"] + " bf16 sustained / 2 (tf32 assumed half of bf16)"},
         "cpu_baseline": {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{a.cpu_sample} images/step x 3 steps (oracle port of the reference forward, torch CPU ops)"},
+                         "sample": f"{a.cpu_sample} images/step x {cpu_steps} steps after 1 warm-up (oracle port of the reference "
+                                   "forward, torch CPU ops, all host threads)"},
     }))
     if world > 1:
         dist.destroy_process_group()
