@@ -113,6 +113,11 @@ static int pool_out(int H, int k, int s, int p, bool ceil_mode) {
 extern "C" int scouter_plan_bind(scouter_plan_t* plan, int batch, int cin, int h, int w) {
     SC_CHECK_ARG(plan && batch > 0 && cin > 0 && h > 0 && w > 0, SCOUTER_E_INVALID, "plan_bind: bad arguments");
     plan->bound = false;
+    // the kernels index elements with 32-bit integers and put the image index in gridDim.z: refuse (loudly) what
+    // would overflow instead of computing garbage -- the caller splits the batch
+    SC_CHECK_ARG(batch <= 65535, SCOUTER_E_UNSUPPORTED, "plan_bind: batch %d > 65535 images per call", batch);
+    SC_CHECK_ARG((long long)batch * cin * h * w < (1ll << 31), SCOUTER_E_UNSUPPORTED,
+                 "plan_bind: input of %d x %d x %d x %d has 2^31 or more elements", batch, cin, h, w);
     for (auto& b : plan->bufs) b = Buf();
     Buf& in = plan->bufs[0];
     in.B = batch; in.H = h; in.W = w; in.C = cin; in.defined = true; in.first_def = -1;
@@ -161,6 +166,8 @@ extern "C" int scouter_plan_bind(scouter_plan_t* plan, int batch, int cin, int h
                 break;
         }
         SC_CHECK_ARG(d.H > 0 && d.W > 0, SCOUTER_E_INVALID, "plan_bind: op %d produces an empty %dx%d map (input too small)", i, d.H, d.W);
+        SC_CHECK_ARG((long long)d.B * d.H * d.W * d.C < (1ll << 31), SCOUTER_E_UNSUPPORTED,
+                     "plan_bind: op %d produces %d x %d x %d x %d = 2^31 or more elements (split the batch)", i, d.B, d.H, d.W, d.C);
         if (o.src2 >= 0) {
             const Buf& r = plan->bufs[o.src2];
             SC_CHECK_ARG(r.defined, SCOUTER_E_STATE, "plan_bind: op %d reads buffer %d before it is written", i, o.src2);

@@ -2,6 +2,8 @@
 import ctypes
 import re
 
+import pytest
+
 from scouter_b200 import _lib as L
 
 
@@ -68,3 +70,23 @@ def test_plan_shape_inference_on_cpu():
         assert tuple(s) == (4, fs, fs, 2048)
         assert L.lib().scouter_plan_arena_bytes(cp.handle) > 0
         assert L.lib().scouter_plan_launch_count(cp.handle) == len(prog.ops) + 8     # split-attention GAP = 2 launches
+
+
+def test_plan_bind_refuses_sizes_that_overflow_32bit_indexing():
+    """Unsupported sizes are a loud error of the C ABI (no silent wrap-around): >= 2^31 elements in any buffer, > 65535 images, wrong channel count."""
+    import scouter_b200 as sb
+    from oracle.refshim import make_args
+    from scouter_b200.plan import CompiledProgram, lower_backbone
+    prog, feat = lower_backbone(sb.SlotModel(make_args()).backbone)
+    cp = CompiledProgram(prog, L.MATH_FP32)
+    lib = L.lib()
+    assert lib.scouter_plan_bind(cp.handle, 256, 3, 224, 224) == 0
+    assert lib.scouter_plan_arena_bytes(cp.handle) < 4 << 30                   # DESIGN section 2: ~2.6 GB at B=256
+    assert lib.scouter_plan_bind(cp.handle, 4096, 3, 224, 224) == -2           # 4096 x 112 x 112 x 64 elements after conv1.6
+    assert b"2^31" in lib.scouter_last_error()
+    assert lib.scouter_plan_arena_bytes(cp.handle) == 0                        # a failed bind leaves the plan unbound
+    assert lib.scouter_plan_bind(cp.handle, 70000, 3, 32, 32) == -2
+    assert lib.scouter_plan_bind(cp.handle, 2, 4, 224, 224) == -1              # channel mismatch with the stem
+    with pytest.raises(sb.ScouterError):
+        L.check(lib.scouter_plan_bind(cp.handle, 0, 3, 224, 224))
+    assert lib.scouter_plan_bind(cp.handle, 2, 3, 224, 224) == 0               # and the plan is still usable
