@@ -10,7 +10,12 @@ Functional restatement, driven only by a reference-format ``state_dict`` (SURVEY
                             ``:276-289`` (conv shortcut), with the MNIST stem swap of
                             ``sloter/slot_model.py:23-24`` (1-channel 3x3 s2 conv instead of the 7x7).
 
-Eval mode only (BatchNorm uses running statistics, eps 1e-5).  The arithmetic primitives are
+Eval mode (BatchNorm uses running statistics, eps 1e-5) is what the shipped CUDA path is checked against.  For row f1
+(backward + train-mode BatchNorm, not built yet) the same restatement runs in TRAIN mode when the
+``state_dict`` is wrapped in ``TrainState``: BatchNorm then uses batch statistics (biased variance for the
+normalisation, unbiased for the running update, momentum 0.1 -- ``nn.BatchNorm2d`` defaults, resnet.py:401-420) and the
+updated running statistics are collected; everything is plain differentiable torch, so ``oracle/train.py`` gets the
+reference's gradients from autograd.  The arithmetic primitives are
 PyTorch's (``F.conv2d`` ...), exactly as in the reference, whose numeric kernel library (torch) is a
 dependency that is not vendored under /root/reference (requirements.txt:27-28 pin torch==1.6.0).
 Pinned against the imported reference by ``oracle/make_golden.py`` / ``tests/test_oracle_golden.py``.
@@ -21,7 +26,22 @@ import torch
 import torch.nn.functional as F
 
 
+class TrainState(dict):
+    """A ``state_dict`` whose BatchNorms run in training mode; ``updates`` collects the new running statistics."""
+
+    def __init__(self, *a, momentum: float = 0.1, **k):
+        super().__init__(*a, **k)
+        self.momentum = momentum
+        self.updates = {}
+
+
 def _bn(sd, p, x, dtype):
+    if isinstance(sd, TrainState):
+        rm = sd[p + ".running_mean"].detach().to(dtype).clone()
+        rv = sd[p + ".running_var"].detach().to(dtype).clone()
+        y = F.batch_norm(x, rm, rv, sd[p + ".weight"].to(dtype), sd[p + ".bias"].to(dtype), True, sd.momentum, 1e-5)
+        sd.updates[p + ".running_mean"], sd.updates[p + ".running_var"] = rm, rv
+        return y
     return F.batch_norm(x, sd[p + ".running_mean"].to(dtype), sd[p + ".running_var"].to(dtype),
                         sd[p + ".weight"].to(dtype), sd[p + ".bias"].to(dtype), False, 0.0, 1e-5)
 

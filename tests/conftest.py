@@ -33,7 +33,10 @@ def golden_names(kind):
     out = []
     for f in sorted(os.listdir(GOLDEN)):
         if f.endswith(".npz") and f not in ("pe_sine.npz", "preprocess_u8.npz", "vis_upsample.npz"):
-            if (kind == "head") == f.startswith("head_"):
+            if f.startswith("train_"):                       # row f1 goldens (oracle/make_golden_train.py)
+                if kind == "train":
+                    out.append(f[:-4])
+            elif kind != "train" and (kind == "head") == f.startswith("head_"):
                 out.append(f[:-4])
     return out
 
