@@ -128,3 +128,49 @@ def test_train_step_oracle_vs_reference_golden(name):
             assert float((gg - ref).abs().max()) / den < bar, n
     for k in [f for f in z.files if f.startswith("bn.")]:
         assert torch.equal(o["bn_updates"][k[3:]], torch.from_numpy(z[k])), k
+
+
+@pytest.mark.parametrize("case", [(10, 1, 3, 1, 2, 3, 64, 7, 7), (5, 2, 1, -1, 1, 2, 32, 3, 4), (4, 3, 2, -1, 3, 1, 16, 2, 2)])
+def test_hand_written_head_backward_equals_autograd(case):
+    """oracle/head_backward.py (the explicit formulas a CUDA backward will implement) == autograd of oracle/head.py, fp64."""
+    from oracle.head_backward import head_backward
+    C, spc, L, ls, pw, B, ch, h, w = case
+    m = sb.SlotModel(make_args(num_classes=C, slots_per_class=spc, to_k_layer=L, loss_status=ls, power=pw, channel=ch))
+    sd = {k: v for k, v in fill_state_dict(m.state_dict(), seed=2).items() if not k.startswith("backbone.")}
+    g = torch.Generator().manual_seed(11)
+    params = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    feat = torch.randn(B, ch, h, w, dtype=torch.float64, generator=g).abs().requires_grad_(True)
+    o = oh.head_forward(params, feat, num_classes=C, slots_per_class=spc, loss_status=ls, power=pw, dtype=torch.float64)
+    gl, ga = torch.randn(B, C, dtype=torch.float64, generator=g), 0.7
+    keys = [k for k in params if not k.startswith("slot.to_q")]
+    grads = torch.autograd.grad((gl * o["logits"]).sum() + ga * o["attn_loss"], [feat] + [params[k] for k in keys])
+    mine = head_backward(sd, feat, gl, ga, num_classes=C, slots_per_class=spc, loss_status=ls, power=pw)
+    for k, ref in zip(["feat"] + keys, grads):
+        assert rel_err(mine[k], ref) < 1e-10, k
+
+
+def test_hand_written_head_backward_vs_reference_train_golden():
+    """The same formulas, fed with the train-mode backbone features and d(loss)/d(logits) of nll(log_softmax), give the
+    head gradients the unmodified reference's loss.backward() produced (train_cfg2 golden)."""
+    from oracle.backbone import TrainState, backbone_features
+    from oracle.head_backward import head_backward
+    z, meta = load_golden("train_cfg2_resnest26d_224")
+    a = meta["args"]
+    m = sb.SlotModel(make_args(**a))
+    sd = fill_state_dict(m.state_dict(), seed=0)
+    x = synth_images(meta["batch"], meta["cin"], meta["size"], meta["size"])
+    tgt = torch.from_numpy(z["target"])
+    with torch.no_grad():
+        feat = backbone_features(a["model"], TrainState(sd), x)
+        o = oh.head_forward(sd, feat, num_classes=a["num_classes"], slots_per_class=a["slots_per_class"],
+                            loss_status=a["loss_status"], power=a["power"], dtype=torch.float64)
+    g_logits = (o["log_probs"].exp() - torch.nn.functional.one_hot(tgt, a["num_classes"])) / meta["batch"]   # d nll / d logits
+    mine = head_backward(sd, feat, g_logits, a["lambda_value"], num_classes=a["num_classes"],
+                         slots_per_class=a["slots_per_class"], loss_status=a["loss_status"], power=a["power"])
+    checked = 0
+    for k in [f[5:] for f in z.files if f.startswith("grad.") and not f.startswith("grad.backbone.")]:
+        ref = torch.from_numpy(z["grad." + k])
+        got = mine[k][:, ::8] if k == "conv1x1.weight" else mine[k]
+        assert rel_err(got, ref) < 1e-3, k
+        checked += 1
+    assert checked == 13          # conv1x1 (2) + initial_slots + 3 to_k layers (6) + gru (4)
