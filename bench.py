@@ -97,8 +97,7 @@ def cpu_reference_rate(batch, size, steps, warmup):
     """The reference algorithm (oracle port: oracle/backbone.py + oracle/head.py) on the host cores."""
     import scouter_b200 as sb
     from oracle import backbone as ob
-    from oracle.refshim import make_args
-    from scouter_b200.synth import fill_state_dict, synth_images
+    from scouter_b200.synth import fill_state_dict, make_args, synth_images
     torch.set_num_threads(os.cpu_count())
     m = sb.SlotModel(make_args(**ARGS))
     sd = fill_state_dict(m.state_dict(), seed=0)
@@ -170,9 +169,8 @@ def main():
 
     import torch.distributed as dist
     import scouter_b200 as sb
-    from oracle.refshim import make_args  # argparse.Namespace builder only (no oracle compute on this arm)
     from scouter_b200 import _lib as L
-    from scouter_b200.synth import fill_state_dict
+    from scouter_b200.synth import fill_state_dict, make_args     # nothing under oracle/ is imported on this arm
 
     from scouter_b200 import dist as sdist
     torch.cuda.set_device(local)

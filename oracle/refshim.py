@@ -13,7 +13,6 @@ edited:
 """
 from __future__ import annotations
 
-import argparse
 import collections.abc
 import os
 import sys
@@ -51,13 +50,7 @@ def install_shims():
         sys.path.insert(0, REFERENCE_ROOT)
 
 
-def make_args(**over) -> argparse.Namespace:
-    """The hot-path-relevant subset of reference ``train.py:18-79`` after ``param_translation``."""
-    a = dict(model="resnest26d", dataset="ImageNet", channel=2048, num_classes=10, pre_trained=False,
-             use_slot=True, use_pre=False, grad=False, loss_status=1, freeze_layers=0, hidden_dim=64,
-             slots_per_class=1, power=2, to_k_layer=3, lambda_value=1.0, vis=False, vis_id=0, img_size=260)
-    a.update(over)
-    return argparse.Namespace(**a)
+from scouter_b200.synth import make_args  # noqa: E402,F401  (the args Namespace builder lives with the synthetic inputs)
 
 
 def reference_slot_model(**over):

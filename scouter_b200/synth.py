@@ -12,10 +12,21 @@ would make every conv2 / split-attention / conv3 weight invisible to a parity te
 """
 from __future__ import annotations
 
+import argparse
 import zlib
 
 import numpy as np
 import torch
+
+
+def make_args(**over) -> argparse.Namespace:
+    """The attributes ``SlotModel(args)`` reads, with the defaults of the reference's parser after
+    ``param_translation`` (train.py:18-79) for the resnest26d + xSlot recipe (README.md:39-42); override by keyword."""
+    a = dict(model="resnest26d", dataset="ImageNet", channel=2048, num_classes=10, pre_trained=False,
+             use_slot=True, use_pre=False, grad=False, loss_status=1, freeze_layers=0, hidden_dim=64,
+             slots_per_class=1, power=2, to_k_layer=3, lambda_value=1.0, vis=False, vis_id=0, img_size=260)
+    a.update(over)
+    return argparse.Namespace(**a)
 
 
 def _rng(name: str, seed: int) -> np.random.RandomState:

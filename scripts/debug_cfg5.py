@@ -6,7 +6,7 @@ from conftest import load_golden
 import scouter_b200 as sb
 from scouter_b200 import _lib as L
 from scouter_b200.synth import fill_state_dict, synth_images
-from oracle.refshim import make_args
+from scouter_b200.synth import make_args
 dev = torch.device("cuda", 0)
 for name in ("cfg4_context30_224", "cfg5_cub200x2_224", "cfg2_resnest26d_pos_224"):
     z, meta = load_golden(name)

@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import scouter_b200 as sb
-from oracle.refshim import make_args
+from scouter_b200.synth import make_args
 from scouter_b200 import _lib as L
 from scouter_b200.synth import fill_state_dict
 
