@@ -65,6 +65,18 @@ def split_weights_bf16(w: torch.Tensor) -> torch.Tensor:
     return torch.cat([w, trunc19_remainder(w)], dim=0).to(torch.bfloat16).contiguous()
 
 
+def dgrad_weights(w_ohwi: torch.Tensor, groups: int = 1) -> torch.Tensor:
+    """Row f1 groundwork (host side; no backward program exists yet): the data gradient of a stride-1 convolution is
+    itself a convolution -- ``dX = conv(dY, W')`` with the taps flipped, input/output channels swapped inside each
+    group and padding ``k - 1 - pad`` -- so it can run on the forward kernels unchanged.  ``w_ohwi`` is the forward
+    weight in this library's layout (Cout, kh, kw, Cin/g); returns W' as (Cin, kh, kw, Cout/g)."""
+    cout, kh, kw, cin_g = w_ohwi.shape
+    if cout % groups:
+        raise L.ScouterError(f"dgrad_weights: {cout} output channels do not split into {groups} groups")
+    w = w_ohwi.reshape(groups, cout // groups, kh, kw, cin_g).flip(2, 3)          # flip the taps
+    return w.permute(0, 4, 2, 3, 1).reshape(groups * cin_g, kh, kw, cout // groups).contiguous()
+
+
 class Program:
     """Accumulates ops; keeps every packed tensor alive."""
 

@@ -134,3 +134,21 @@ def test_reference_checkpoint_flow_stage1_to_stage2(tmp_path, monkeypatch):
     ck = torch.load(tmp_path / "ImageNet_use_slot_checkpoint.pth", map_location="cpu", weights_only=False)
     fresh.load_state_dict(ck["model"])                                        # strict
     assert all(torch.equal(v, ck["model"][k]) for k, v in fresh.state_dict().items())
+
+
+@pytest.mark.parametrize("cin,cout,k,pad,groups", [(8, 6, 3, 1, 2), (16, 32, 1, 0, 1), (4, 4, 3, 1, 1), (6, 12, 3, 0, 3)])
+def test_dgrad_weights_turn_the_data_gradient_into_a_forward_conv(cin, cout, k, pad, groups):
+    """f1 groundwork: dX of a stride-1 conv == a forward conv of dY with ``dgrad_weights`` (flipped taps, channels swapped
+    per group, padding k-1-pad), i.e. the backward-data pass can run on the forward tcgen05 kernels."""
+    from scouter_b200.plan import dgrad_weights
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, cin, 9, 7, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin // groups, k, k, generator=g, dtype=torch.float64)
+    y = torch.nn.functional.conv2d(x, w, None, 1, pad, 1, groups)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    w_ohwi = w.permute(0, 2, 3, 1).contiguous()                       # the library's weight layout
+    wd = dgrad_weights(w_ohwi, groups)                                # (Cin, kh, kw, Cout/g)
+    assert wd.shape == (cin, k, k, cout // groups)
+    got = torch.nn.functional.conv2d(dy, wd.permute(0, 3, 1, 2), None, 1, k - 1 - pad, 1, groups)
+    assert got.shape == dx.shape and torch.allclose(got, dx, rtol=1e-12, atol=1e-12)
