@@ -130,8 +130,8 @@ class SlotAttention(nn.Module):
                                                     L.stream_ptr()), "scouter_vis_upsample_u8")
         return maps, heat, ratios
 
-    def emit_vis(self, attn: torch.Tensor, logits: torch.Tensor):
-        maps, _, _ = self.vis_maps(attn)
+    def emit_vis(self, attn: torch.Tensor, logits: torch.Tensor, hw=None):
+        maps, _, _ = self.vis_maps(attn, hw=hw)
         self.last_vis_maps = maps.cpu().numpy()
         if self.vis_dir:
             from PIL import Image

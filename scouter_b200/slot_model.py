@@ -240,7 +240,7 @@ class SlotModel(nn.Module):
                 self.last_attn = st.attn
                 self.slot.last_attn = st.attn
             if self.slot.vis:
-                self.slot.emit_vis(st.attn, st.logits)
+                self.slot.emit_vis(st.attn, st.logits, hw=(st.fh, st.fw))    # non-square maps keep their shape
             if target is not None:
                 ls = st.losses.clone()
                 return [output, [ls[0], ls[1], ls[2]]]
