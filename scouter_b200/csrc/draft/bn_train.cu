@@ -1,0 +1,16 @@
+// DRAFT (row f1) -- see bn_train.cuh.  Not listed in scouter_b200/_lib.py SOURCES: the library does not contain it.
+#include <cuda_runtime.h>
+
+#include "bn_train.cuh"
+
+namespace scouter_draft {
+
+// `sums` must be zero on entry (cudaMemsetAsync by the caller); grids are multiples of the SM count.
+int bn_train_launch(const BnTrainArgs& a, int sms, cudaStream_t stream) {
+    bn_stats_kernel<<<sms * 4, 256, 0, stream>>>(a);
+    bn_finalize_kernel<<<(a.C + 127) / 128, 128, 0, stream>>>(a);
+    bn_apply_kernel<<<sms * 8, 256, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace scouter_draft

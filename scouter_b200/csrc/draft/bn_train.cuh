@@ -1,0 +1,103 @@
+// DRAFT -- row f1, NOT part of libscouter_b200.so and never run on a GPU yet.
+//
+// Train-mode BatchNorm2d of the backbone (nn.BatchNorm2d defaults: eps 1e-5, momentum 0.1; timm/models/resnet.py:401-420,
+// resnest.py:84-105, split_attn.py:46-50) on NHWC activations viewed as (M = B*H*W rows, C channels): in train mode the
+// statistics come from the batch, so BatchNorm cannot be folded into the conv weights as the eval path does.
+//   1. bn_stats_partial   per-channel sum and sum of squares; thread = (row lane, channel quad), float4 loads that are
+//                         coalesced across the quads of a row, fp64 accumulators (E[x^2] - mean^2 cancels badly in fp32
+//                         when |mean| >> std), one fp64 atomicAdd pair per thread and channel into a (C, 2) workspace;
+//   2. bn_finalize        per channel: batch mean / biased variance -> scale = gamma * rstd, shift = beta - mean * scale,
+//                         running_mean / running_var (unbiased) momentum update;
+//   3. bn_apply           y = x * scale + shift [+ residual] [ReLU], float4 per thread.
+// All three are HBM-bound: one read of x for the statistics, one read + one write for the apply (the apply can later
+// move into the consumer conv's TS-mode splitter, which already touches every element).
+// The bodies compile as host code for the emulation in tests/test_bn_train_draft.py.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+
+#ifdef __CUDACC__
+#define BN_HD __device__ __forceinline__
+#define BN_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#else
+#define BN_HD static inline
+#define BN_ATOMIC_ADD(p, v) (*(p) += (v))
+#endif
+
+namespace scouter_draft {
+
+struct BnTrainArgs {
+    long long M;                 // rows = B*H*W
+    int C;                       // channels, multiple of 4
+    const float* x;              // (M, C)
+    double* sums;                // (C, 2) workspace, zeroed by the caller: [sum, sum of squares]
+    const float *gamma, *beta;   // (C)
+    float *running_mean, *running_var;   // (C), updated in place
+    float *scale, *shift;        // (C) outputs of bn_finalize, inputs of bn_apply
+    float eps, momentum;
+    const float* residual;       // (M, C) or NULL
+    float* y;                    // (M, C); may alias x
+    int relu;
+};
+
+// CTA `cta` of `n_ctas` owns a contiguous slab of rows; inside it thread `tid` owns channel quad tid % qpr and the rows
+// r0 + tid / qpr, + lanes, + 2*lanes ... (qpr = quads per row handled at once = min(C/4, nthreads)).
+BN_HD void bn_stats_partial(const BnTrainArgs& a, int cta, int n_ctas, int tid, int nthreads) {
+    const int quads = a.C / 4;
+    const int qpr = quads < nthreads ? quads : nthreads;
+    const int lanes = nthreads / qpr;
+    if (tid >= lanes * qpr) return;
+    const long long per = (a.M + n_ctas - 1) / n_ctas;
+    const long long r0 = (long long)cta * per, r1 = r0 + per < a.M ? r0 + per : a.M;
+    const int lane = tid / qpr;
+    for (int q = tid % qpr; q < quads; q += qpr) {       // more than nthreads quads per row: loop
+        double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+        for (long long r = r0 + lane; r < r1; r += lanes) {
+            const float* p = a.x + r * a.C + 4 * q;
+            for (int k = 0; k < 4; ++k) { const double v = p[k]; s[k] += v; ss[k] += v * v; }
+        }
+        for (int k = 0; k < 4; ++k) {
+            BN_ATOMIC_ADD(a.sums + 2 * (4 * q + k), s[k]);
+            BN_ATOMIC_ADD(a.sums + 2 * (4 * q + k) + 1, ss[k]);
+        }
+    }
+}
+
+BN_HD void bn_finalize(const BnTrainArgs& a, int c) {
+    const double n = (double)a.M;
+    const double mean = a.sums[2 * c] / n;
+    double var = a.sums[2 * c + 1] / n - mean * mean;    // biased: what the normalisation uses
+    if (var < 0) var = 0;
+    const double rstd = 1.0 / sqrt(var + (double)a.eps);
+    const double sc = (double)a.gamma[c] * rstd;
+    a.scale[c] = (float)sc;
+    a.shift[c] = (float)((double)a.beta[c] - mean * sc);
+    const double unbiased = a.M > 1 ? var * n / (n - 1.0) : var;
+    a.running_mean[c] = (float)((1.0 - a.momentum) * a.running_mean[c] + a.momentum * mean);
+    a.running_var[c] = (float)((1.0 - a.momentum) * a.running_var[c] + a.momentum * unbiased);
+}
+
+BN_HD void bn_apply(const BnTrainArgs& a, long long i4) {    // i4 indexes float4s of the (M, C) map
+    const int c = (int)((i4 * 4) % a.C);
+    for (int k = 0; k < 4; ++k) {
+        const long long i = i4 * 4 + k;
+        float v = fmaf(a.x[i], a.scale[c + k], a.shift[c + k]);
+        if (a.residual) v += a.residual[i];
+        if (a.relu && v < 0.f) v = 0.f;
+        a.y[i] = v;
+    }
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(256) bn_stats_kernel(BnTrainArgs a) { bn_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
+__global__ void bn_finalize_kernel(BnTrainArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < a.C) bn_finalize(a, c);
+}
+__global__ void __launch_bounds__(256) bn_apply_kernel(BnTrainArgs a) {
+    const long long n4 = a.M * a.C / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) bn_apply(a, i);
+}
+#endif
+
+}  // namespace scouter_draft
