@@ -41,7 +41,11 @@ struct HeadBwdArgs {
     const float *slots0;                       // (S, 64) initial_slots
     const float *g_logits;                     // (B, C)
     const float *attn_coef;                    // scalar on the device
-    float *d_feat;                             // (B, n, ch)
+    float *d_feat;                             // (B, n, ch), or NULL when d_pre is requested instead
+    float *d_pre;                              // (B, n, 64) gradient at the conv1x1 pre-activation, or NULL.  With it the
+                                               // two ch-sized products leave this kernel: d_feat = d_pre W is a 1x1
+                                               // conv (64 -> ch) the forward tcgen05 kernel already runs, and
+                                               // g_conv_w = d_pre^T feat is a wgrad GEMM over K = B*n rows
     float *g_conv_w, *g_conv_b, *g_to_k_w[HB_MAX_L], *g_to_k_b[HB_MAX_L];
     float *g_w_ih, *g_w_hh, *g_b_ih, *g_b_hh, *g_slots0;     // zero-initialised by the caller, accumulated here
     float *scratch;                            // B * scratch_floats(...)
@@ -352,6 +356,15 @@ HB_HD void head_backward_image(const HeadBwdArgs& a, int b, int tid, int nthread
     }
     HB_SYNC();
     const float* dpre = w + o.DX;
+    HB_PHASE(HD) {                                 // conv1x1.bias gradient (always here: it is 64 sums)
+        float s = 0.f;
+        for (int j = 0; j < n; ++j) s += dpre[(size_t)j * HD + idx];
+        HB_ATOMIC_ADD(a.g_conv_b + idx, s);
+    }
+    if (a.d_pre) {                                 // hand the ch-sized products to the GEMM kernels
+        HB_PHASE(nd) a.d_pre[(size_t)b * nd + idx] = dpre[idx];
+        return;
+    }
     HB_PHASE((size_t)n * ch) {                     // d feat = d pre W
         const int j = (int)(idx / ch), c = (int)(idx % ch);
         float s = 0.f;
@@ -363,11 +376,6 @@ HB_HD void head_backward_image(const HeadBwdArgs& a, int b, int tid, int nthread
         float s = 0.f;
         for (int j = 0; j < n; ++j) s = fmaf(dpre[(size_t)j * HD + e], feat[(size_t)j * ch + c], s);
         HB_ATOMIC_ADD(a.g_conv_w + idx, s);
-    }
-    HB_PHASE(HD) {
-        float s = 0.f;
-        for (int j = 0; j < n; ++j) s += dpre[(size_t)j * HD + idx];
-        HB_ATOMIC_ADD(a.g_conv_b + idx, s);
     }
 }
 

@@ -28,7 +28,7 @@ class Args(C.Structure):            # scouter_draft::HeadBwdArgs
     _fields_ = [(k, C.c_int) for k in ("B", "n", "ch", "S", "C", "spc", "L", "iters", "loss_status")] + \
                [("feat", _f), ("conv_w", _f), ("conv_b", _f), ("pe", _f), ("to_k_w", _f * MAX_L), ("to_k_b", _f * MAX_L),
                 ("w_ih", _f), ("w_hh", _f), ("b_ih", _f), ("b_hh", _f), ("slots0", _f), ("g_logits", _f), ("attn_coef", _f),
-                ("d_feat", _f), ("g_conv_w", _f), ("g_conv_b", _f), ("g_to_k_w", _f * MAX_L), ("g_to_k_b", _f * MAX_L),
+                ("d_feat", _f), ("d_pre", _f), ("g_conv_w", _f), ("g_conv_b", _f), ("g_to_k_w", _f * MAX_L), ("g_to_k_b", _f * MAX_L),
                 ("g_w_ih", _f), ("g_w_hh", _f), ("g_b_ih", _f), ("g_b_hh", _f), ("g_slots0", _f),
                 ("scratch", _f), ("scratch_per_image", C.c_size_t)]
 
@@ -101,6 +101,24 @@ def test_draft_kernel_body_matches_oracle(emu, case):
     for l in range(L):
         got[f"slot.to_k.{2 * l}.weight"], got[f"slot.to_k.{2 * l}.bias"] = torch.from_numpy(gkw[l]), torch.from_numpy(gkb[l])
     assert set(got) == set(ref)
+    got = {k: v.clone() for k, v in got.items()}             # the arrays are reused by the second run
+    # second mode: the kernel stops at d_pre (B, n, 64); the two ch-sized products are then plain GEMMs
+    d_pre = np.full((B, n, 64), np.nan, np.float32)
+    for v in list(out.values()) + gkw + gkb:
+        v[...] = 0
+    scratch[...] = np.nan
+    a.d_feat, a.d_pre = None, ptr(d_pre)
+    emu.head_backward_host(C.byref(a), 1)
+    dp = torch.from_numpy(d_pre).double()
+    tokens = torch.from_numpy(keep["feat"]).double()
+    wc = torch.from_numpy(keep["conv_w"]).double()
+    via_gemm = {"feat": (dp @ wc).permute(0, 2, 1).reshape(B, ch, h, w),
+                "conv1x1.weight": (dp.reshape(-1, 64).t() @ tokens.reshape(-1, ch)).reshape(64, ch, 1, 1),
+                "conv1x1.bias": torch.from_numpy(out["g_conv_b"]).double()}
+    assert not out["g_conv_w"].any() and not out["d_feat"].any()            # untouched in this mode
     for k, r in ref.items():
+        if k in via_gemm:
+            e2 = float((via_gemm[k] - r).abs().max() / r.abs().max().clamp_min(1e-30))
+            assert e2 < 5e-4, (k, e2)
         err = float((got[k].double() - r).abs().max() / r.abs().max().clamp_min(1e-30))
         assert err < 5e-4, (k, err)       # fp32 kernel vs fp64 formulas (measured: <= 3e-5 on these cases)
