@@ -13,4 +13,13 @@ int bn_train_launch(const BnTrainArgs& a, int sms, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
+// out = [relu](bn(x) [+ residual]) backward; `sums` zero on entry.  NOTE the apply pass must not start before the
+// statistics pass has read all of d_out when dx aliases d_out: stream order between the launches guarantees it.
+int bn_train_backward_launch(const BnBwdArgs& a, int sms, cudaStream_t stream) {
+    bn_bwd_stats_kernel<<<sms * 4, 256, 0, stream>>>(a);
+    bn_bwd_finalize_kernel<<<(a.C + 127) / 128, 128, 0, stream>>>(a);
+    bn_bwd_apply_kernel<<<sms * 8, 256, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace scouter_draft

@@ -34,6 +34,7 @@ struct BnTrainArgs {
     const float *gamma, *beta;   // (C)
     float *running_mean, *running_var;   // (C), updated in place
     float *scale, *shift;        // (C) outputs of bn_finalize, inputs of bn_apply
+    float *save_mean, *save_rstd;// (C) batch mean and 1/sqrt(var + eps), kept for the backward (or NULL)
     float eps, momentum;
     const float* residual;       // (M, C) or NULL
     float* y;                    // (M, C); may alias x
@@ -72,6 +73,7 @@ BN_HD void bn_finalize(const BnTrainArgs& a, int c) {
     const double sc = (double)a.gamma[c] * rstd;
     a.scale[c] = (float)sc;
     a.shift[c] = (float)((double)a.beta[c] - mean * sc);
+    if (a.save_mean) { a.save_mean[c] = (float)mean; a.save_rstd[c] = (float)rstd; }
     const double unbiased = a.M > 1 ? var * n / (n - 1.0) : var;
     a.running_mean[c] = (float)((1.0 - a.momentum) * a.running_mean[c] + a.momentum * mean);
     a.running_var[c] = (float)((1.0 - a.momentum) * a.running_var[c] + a.momentum * unbiased);
@@ -88,7 +90,86 @@ BN_HD void bn_apply(const BnTrainArgs& a, long long i4) {    // i4 indexes float
     }
 }
 
+// ---- backward of  out = [relu]( bn(x) [+ residual] )  ---------------------------------------------------------------
+//   dy = d_out * [out > 0]  (ReLU mask from the saved output);  d_residual = dy (the caller aliases / accumulates it);
+//   d_beta = sum dy;  d_gamma = sum dy * xhat,  xhat = (x - mean) * rstd;
+//   dx = gamma * rstd * (dy - d_beta / M - xhat * d_gamma / M).
+// Same decomposition as the forward: one statistics pass (fp64 sums, atomics), a per-channel finalize, one apply pass.
+struct BnBwdArgs {
+    long long M;
+    int C;
+    const float *x, *out, *d_out;        // (M, C): conv output, block output (for the ReLU mask; may be NULL when !relu), its gradient
+    const float *gamma, *save_mean, *save_rstd;
+    double* sums;                        // (C, 2) zeroed workspace: [sum dy, sum dy * xhat]
+    float *d_gamma, *d_beta;             // (C) accumulated into (+=): parameters can be shared across calls of a step
+    float *coef;                         // (C, 3) from finalize: gamma*rstd, d_beta/M, d_gamma/M
+    float *dx;                           // (M, C); may alias d_out
+    float *d_residual;                   // (M, C) or NULL: receives dy
+    int relu;
+};
+
+BN_HD float bn_bwd_dy(const BnBwdArgs& a, long long i) {
+    const float g = a.d_out[i];
+    return (a.relu && !(a.out[i] > 0.f)) ? 0.f : g;
+}
+
+BN_HD void bn_bwd_stats_partial(const BnBwdArgs& a, int cta, int n_ctas, int tid, int nthreads) {
+    const int quads = a.C / 4;
+    const int qpr = quads < nthreads ? quads : nthreads;
+    const int lanes = nthreads / qpr;
+    if (tid >= lanes * qpr) return;
+    const long long per = (a.M + n_ctas - 1) / n_ctas;
+    const long long r0 = (long long)cta * per, r1 = r0 + per < a.M ? r0 + per : a.M;
+    const int lane = tid / qpr;
+    for (int q = tid % qpr; q < quads; q += qpr) {
+        double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
+        for (long long r = r0 + lane; r < r1; r += lanes) {
+            for (int k = 0; k < 4; ++k) {
+                const int c = 4 * q + k;
+                const long long i = r * a.C + c;
+                const double dy = bn_bwd_dy(a, i);
+                s[k] += dy;
+                sx[k] += dy * (((double)a.x[i] - a.save_mean[c]) * a.save_rstd[c]);
+            }
+        }
+        for (int k = 0; k < 4; ++k) {
+            BN_ATOMIC_ADD(a.sums + 2 * (4 * q + k), s[k]);
+            BN_ATOMIC_ADD(a.sums + 2 * (4 * q + k) + 1, sx[k]);
+        }
+    }
+}
+
+BN_HD void bn_bwd_finalize(const BnBwdArgs& a, int c) {
+    const double n = (double)a.M;
+    a.d_beta[c] += (float)a.sums[2 * c];
+    a.d_gamma[c] += (float)a.sums[2 * c + 1];
+    a.coef[3 * c] = a.gamma[c] * a.save_rstd[c];
+    a.coef[3 * c + 1] = (float)(a.sums[2 * c] / n);
+    a.coef[3 * c + 2] = (float)(a.sums[2 * c + 1] / n);
+}
+
+BN_HD void bn_bwd_apply(const BnBwdArgs& a, long long i4) {
+    const int c0 = (int)((i4 * 4) % a.C);
+    for (int k = 0; k < 4; ++k) {
+        const long long i = i4 * 4 + k;
+        const int c = c0 + k;
+        const float dy = bn_bwd_dy(a, i);
+        const float xhat = (a.x[i] - a.save_mean[c]) * a.save_rstd[c];
+        if (a.d_residual) a.d_residual[i] = dy;
+        a.dx[i] = a.coef[3 * c] * (dy - a.coef[3 * c + 1] - xhat * a.coef[3 * c + 2]);
+    }
+}
+
 #ifdef __CUDACC__
+__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(BnBwdArgs a) { bn_bwd_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
+__global__ void bn_bwd_finalize_kernel(BnBwdArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < a.C) bn_bwd_finalize(a, c);
+}
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
+    const long long n4 = a.M * a.C / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) bn_bwd_apply(a, i);
+}
 __global__ void __launch_bounds__(256) bn_stats_kernel(BnTrainArgs a) { bn_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
 __global__ void bn_finalize_kernel(BnTrainArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;

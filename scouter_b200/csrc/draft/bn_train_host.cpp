@@ -8,3 +8,10 @@ extern "C" void bn_train_host(const scouter_draft::BnTrainArgs* a, int n_ctas, i
     for (int c = 0; c < a->C; ++c) scouter_draft::bn_finalize(*a, c);
     for (long long i = 0; i < a->M * a->C / 4; ++i) scouter_draft::bn_apply(*a, i);
 }
+
+extern "C" void bn_train_backward_host(const scouter_draft::BnBwdArgs* a, int n_ctas, int nthreads) {
+    for (int cta = 0; cta < n_ctas; ++cta)
+        for (int tid = 0; tid < nthreads; ++tid) scouter_draft::bn_bwd_stats_partial(*a, cta, n_ctas, tid, nthreads);
+    for (int c = 0; c < a->C; ++c) scouter_draft::bn_bwd_finalize(*a, c);
+    for (long long i = 0; i < a->M * a->C / 4; ++i) scouter_draft::bn_bwd_apply(*a, i);
+}
