@@ -14,4 +14,9 @@ int conv_wgrad_launch(const WgradArgs& a, int sms, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
+int conv_dgrad_launch(const DgradArgs& a, int sms, cudaStream_t stream) {
+    conv_dgrad_kernel<<<sms * 8, 256, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace scouter_draft

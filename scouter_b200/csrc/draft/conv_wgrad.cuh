@@ -60,7 +60,49 @@ WG_HD void conv_bgrad_element(const WgradArgs& a, int o, long long m0, long long
     WG_ATOMIC_ADD(a.db + o, acc);
 }
 
+// Data gradient for ANY stride as a gather (thread = one input element): the strided convs of resnet18 (3x3 s2 and the
+// 1x1 s2 shortcuts, resnet.py:172-199, 276-289) cannot use the forward-conv trick of plan.dgrad_weights.
+//     dX[b, yi, xi, ci] = sum_{o in group(ci), r, s : (yi + pad - r) % stride == 0, ...} dY[b, yo, xo, o] * W[o, r, s, c]
+struct DgradArgs {
+    int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad, groups;
+    const float* dy;    // (B, Ho, Wo, Cout)
+    const float* w;     // (Cout, k, k, Cin/groups)
+    float* dx;          // (B, H, W, Cin)
+};
+
+WG_HD void conv_dgrad_element(const DgradArgs& a, long long idx) {     // idx over B*H*W*Cin
+    const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
+    const int ci = (int)(idx % a.Cin);
+    long long t = idx / a.Cin;
+    const int xi = (int)(t % a.W); t /= a.W;
+    const int yi = (int)(t % a.H);
+    const int b = (int)(t / a.H);
+    const int g = ci / cin_g, c = ci % cin_g;
+    float acc = 0.f;
+    for (int r = 0; r < a.k; ++r) {
+        const int ty = yi + a.pad - r;
+        if (ty < 0 || ty % a.stride) continue;
+        const int yo = ty / a.stride;
+        if (yo >= a.Ho) continue;
+        for (int s = 0; s < a.k; ++s) {
+            const int tx = xi + a.pad - s;
+            if (tx < 0 || tx % a.stride) continue;
+            const int xo = tx / a.stride;
+            if (xo >= a.Wo) continue;
+            const float* dyp = a.dy + (((size_t)b * a.Ho + yo) * a.Wo + xo) * a.Cout + (size_t)g * cout_g;
+            for (int o = 0; o < cout_g; ++o)
+                acc = fmaf(dyp[o], a.w[(((size_t)(g * cout_g + o) * a.k + r) * a.k + s) * cin_g + c], acc);
+        }
+    }
+    a.dx[idx] = acc;
+}
+
 #ifdef __CUDACC__
+__global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
+    const long long n = (long long)a.B * a.H * a.W * a.Cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) conv_dgrad_element(a, i);
+}
+
 // grid (ceil(elements / 256), k_splits)
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
     const long long elems = (long long)a.Cout * a.k * a.k * (a.Cin / a.groups);

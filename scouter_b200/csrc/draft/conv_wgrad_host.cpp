@@ -12,3 +12,8 @@ extern "C" void conv_wgrad_host(const scouter_draft::WgradArgs* a, int splits) {
         if (a->db) for (int o = 0; o < a->Cout; ++o) scouter_draft::conv_bgrad_element(*a, o, m0, m1);
     }
 }
+
+extern "C" void conv_dgrad_host(const scouter_draft::DgradArgs* a) {
+    const long long n = (long long)a->B * a->H * a->W * a->Cin;
+    for (long long i = 0; i < n; ++i) scouter_draft::conv_dgrad_element(*a, i);
+}

@@ -19,6 +19,11 @@ class Args(C.Structure):            # scouter_draft::WgradArgs
                [("x", _f), ("dy", _f), ("dw", _f), ("db", _f)]
 
 
+class DArgs(C.Structure):           # scouter_draft::DgradArgs
+    _fields_ = [(k, C.c_int) for k in ("B", "H", "W", "Cin", "Ho", "Wo", "Cout", "k", "stride", "pad", "groups")] + \
+               [("dy", _f), ("w", _f), ("dx", _f)]
+
+
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     if not shutil.which("g++"):
@@ -29,6 +34,8 @@ def emu(tmp_path_factory):
     lib = C.CDLL(so)
     lib.conv_wgrad_host.argtypes = [C.POINTER(Args), C.c_int]
     lib.conv_wgrad_host.restype = None
+    lib.conv_dgrad_host.argtypes = [C.POINTER(DArgs)]
+    lib.conv_dgrad_host.restype = None
     return lib
 
 
@@ -61,3 +68,23 @@ def test_conv_wgrad_draft_matches_autograd(emu, case):
     assert float((torch.from_numpy(dw) - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
     if bias:
         assert float((torch.from_numpy(db) - grads[1]).abs().max()) <= 1e-5 * max(1.0, float(grads[1].abs().max()))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_dgrad_draft_matches_autograd(emu, case):
+    b, cin, cout, h, w, k, stride, pad, groups, _, _ = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn(b, cin, h, w, generator=g, requires_grad=True)
+    wt = torch.randn(cout, cin // groups, k, k, generator=g)
+    y = F.conv2d(x, wt, None, stride, pad, 1, groups)
+    dy = torch.randn(y.shape, generator=g)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    dys = np.ascontiguousarray(dy.permute(0, 2, 3, 1).numpy())
+    ws = np.ascontiguousarray(wt.permute(0, 2, 3, 1).numpy())
+    dxs = np.full((b, h, w, cin), np.nan, np.float32)
+    p = lambda a_: a_.ctypes.data_as(_f)
+    a = DArgs(B=b, H=h, W=w, Cin=cin, Ho=y.shape[2], Wo=y.shape[3], Cout=cout, k=k, stride=stride, pad=pad, groups=groups,
+              dy=p(dys), w=p(ws), dx=p(dxs))
+    emu.conv_dgrad_host(C.byref(a))
+    got = torch.from_numpy(dxs).permute(0, 3, 1, 2)
+    assert float((got - dx).abs().max()) <= 1e-5 * max(1.0, float(dx.abs().max()))
