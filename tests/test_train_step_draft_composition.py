@@ -1,4 +1,4 @@
-"""CPU: the row-f1 DRAFT kernels composed into one full training-step backward (resnest14d + xSlot, tiny images) and
+"""CPU: the row-f1 DRAFT kernels composed into one full training-step backward (resnest14d / resnest26d + xSlot, tiny images) and
 compared with the train-mode oracle (oracle/train.py = the reference's ``loss.backward()``).
 
 The forward runs in torch (it is not under test); every backward op -- BatchNorm (train statistics), conv data / weight
@@ -85,7 +85,7 @@ def conv_bn(t, x, ckey, bkey, stride=1, pad=0, groups=1, relu=True, residual=Non
     return y, back
 
 
-def resnest_block(t, x, p, avd, down_pool):
+def resnest_block(t, x, p, avd, down_pool, has_down=True):
     o1, b1 = conv_bn(t, x, p + ".conv1", p + ".bn1")
     x2, b2 = conv_bn(t, o1, p + ".conv2.conv", p + ".conv2.bn0", pad=1, groups=2)
     bsz, h, w, c2 = x2.shape
@@ -97,7 +97,10 @@ def resnest_block(t, x, p, avd, down_pool):
     o2 = x2[..., :c] * att[:, None, None, 0] + x2[..., c:] * att[:, None, None, 1]
     pooled = to_nhwc(F.avg_pool2d(to_nchw(o2), 3, 2, 1)) if avd else o2
     res_in = to_nhwc(F.avg_pool2d(to_nchw(x), 2, 2, ceil_mode=True, count_include_pad=False)) if down_pool else x
-    res, bd = conv_bn(t, res_in, p + ".downsample.1", p + ".downsample.2", relu=False)
+    if has_down:
+        res, bd = conv_bn(t, res_in, p + ".downsample.1", p + ".downsample.2", relu=False)
+    else:                                                                                          # identity shortcut
+        res, bd = x, (lambda d_res: (d_res, None))
     out, b3 = conv_bn(t, pooled, p + ".conv3", p + ".bn3", relu=True, residual=res)
 
     def back(d_out):
@@ -114,18 +117,19 @@ def resnest_block(t, x, p, avd, down_pool):
     return out, back
 
 
-@pytest.mark.timeout(600)
-def test_full_backward_composed_from_draft_kernels_matches_train_oracle():
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("model,per_layer", [("resnest14d", 1), ("resnest26d", 2)])
+def test_full_backward_composed_from_draft_kernels_matches_train_oracle(model, per_layer):
     if E.lib() is None:
         pytest.skip("g++ not available")
-    args = dict(model="resnest14d", num_classes=10, slots_per_class=1, power=2, to_k_layer=3, loss_status=1, lambda_value=1.0)
+    args = dict(model=model, num_classes=10, slots_per_class=1, power=2, to_k_layer=3, loss_status=1, lambda_value=1.0)
     m = sb.SlotModel(make_args(**args))
     sd = fill_state_dict(m.state_dict(), seed=0)
     B, size = 3, 64
     x = synth_images(B, 3, size, size)
     tgt = synth_labels(B, 10)
-    ref = train_step("resnest14d", sd, x, tgt, num_classes=10, slots_per_class=1, loss_status=1, power=2, lambda_value=1.0)
-    ref64 = train_step("resnest14d", sd, x, tgt, num_classes=10, slots_per_class=1, loss_status=1, power=2, lambda_value=1.0,
+    ref = train_step(model, sd, x, tgt, num_classes=10, slots_per_class=1, loss_status=1, power=2, lambda_value=1.0)
+    ref64 = train_step(model, sd, x, tgt, num_classes=10, slots_per_class=1, loss_status=1, power=2, lambda_value=1.0,
                        dtype=torch.float64)
 
     # ---- forward with a tape -------------------------------------------------------------------------------------------
@@ -138,8 +142,10 @@ def test_full_backward_composed_from_draft_kernels_matches_train_oracle():
     h = to_nhwc(F.max_pool2d(to_nchw(h), 3, 2, 1))
     blocks = []
     for li in range(1, 5):
-        h, bk = resnest_block(t, h, f"backbone.layer{li}.0", avd=li > 1, down_pool=li > 1)
-        blocks.append(bk)
+        for bi in range(per_layer):
+            first = bi == 0
+            h, bk = resnest_block(t, h, f"backbone.layer{li}.{bi}", avd=first and li > 1, down_pool=first and li > 1, has_down=first)
+            blocks.append(bk)
     bsz, fh, fw, ch = h.shape
     feat_tokens = h.reshape(bsz, fh * fw, ch)
     with torch.no_grad():
@@ -170,10 +176,15 @@ def test_full_backward_composed_from_draft_kernels_matches_train_oracle():
         if g_ref is None:
             assert k.startswith("slot.to_q.") and k not in t.grads
             continue
+        if k.endswith(".conv2.fc1.bias"):
+            # a bias in front of a train-mode BatchNorm has an exactly zero gradient; both sides hold rounding noise only
+            assert float(t.grads[k].abs().max()) < 1e-3 * scale and float(g_ref.abs().max()) < 1e-3 * scale, k
+            checked += 1
+            continue
         den = max(float(g_ref.abs().max()), 1e-4 * scale)
         floor = float((g_ref.double() - ref64["grads"][k]).abs().max()) / den          # the oracle's own fp32 noise on this tensor
         err = float((t.grads[k] - g_ref).abs().max()) / den
-        assert err < max(5e-4, 8 * floor), (k, err, floor)      # measured: <= 2e-4; fc1.bias (zero in exact arithmetic) sits at its floor
+        assert err < max(5e-4, 8 * floor), (k, err, floor)      # measured: <= 2e-4
         checked += 1
     assert checked == len(t.grads) == sum(g is not None for g in ref["grads"].values())
     for k, v in ref["bn_updates"].items():
