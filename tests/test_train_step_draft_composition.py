@@ -14,6 +14,7 @@ import draft_emu as E
 import scouter_b200 as sb
 from oracle import head as oh
 from oracle.train import train_step
+from scouter_b200.plan import dgrad_weights
 from scouter_b200.synth import fill_state_dict, make_args, synth_images, synth_labels
 
 
@@ -46,6 +47,12 @@ class Tape:
 
         def back(dy):
             dx, dw, db = E.conv_backward(x, dy, w_ohwi, stride, pad, groups, bias=bias is not None, need_dx=need_dx)
+            if need_dx and stride == 1:
+                # the library's route for stride-1 convs: the data gradient as a FORWARD conv with plan.dgrad_weights
+                k = w_ohwi.shape[1]
+                wd = dgrad_weights(torch.from_numpy(w_ohwi), groups)                       # (Cin, k, k, Cout/g)
+                via_fwd = to_nhwc(F.conv2d(to_nchw(dy), wd.permute(0, 3, 1, 2).contiguous(), None, 1, k - 1 - pad, 1, groups))
+                assert np.abs(via_fwd - dx).max() <= 1e-5 * max(1.0, np.abs(dx).max()), key
             self._acc(key + ".weight", np.ascontiguousarray(dw.transpose(0, 3, 1, 2)))
             if bias is not None:
                 self._acc(key + ".bias", db)
@@ -187,5 +194,78 @@ def test_full_backward_composed_from_draft_kernels_matches_train_oracle(model, p
         assert err < max(5e-4, 8 * floor), (k, err, floor)      # measured: <= 2e-4
         checked += 1
     assert checked == len(t.grads) == sum(g is not None for g in ref["grads"].values())
+    for k, v in ref["bn_updates"].items():
+        assert np.allclose(t.bn_after[k], v.numpy(), rtol=1e-4, atol=1e-5), k
+
+
+def basic_block(t, x, p, stride, has_down):
+    o1, b1 = conv_bn(t, x, p + ".conv1", p + ".bn1", stride=stride, pad=1)
+    if has_down:                                                                                   # 1x1 stride-s conv + BN shortcut
+        res, bd = conv_bn(t, x, p + ".downsample.0", p + ".downsample.1", stride=stride, relu=False)
+    else:
+        res, bd = x, (lambda d_res: (d_res, None))
+    out, b2 = conv_bn(t, o1, p + ".conv2", p + ".bn2", pad=1, relu=True, residual=res)
+
+    def back(d_out):
+        d_o1, d_res = b2(d_out)
+        d_x, _ = b1(d_o1)
+        d_sc, _ = bd(d_res)
+        return d_x + d_sc
+    return out, back
+
+
+@pytest.mark.timeout(900)
+def test_full_backward_resnet18_mnist_from_draft_kernels_matches_train_oracle():
+    """cfg 1 (MNIST resnet18 + xSlot, 1-channel 3x3 s2 stem, slot_model.py:23-24): strided 3x3 convs and conv shortcuts go
+    through the general-stride data-gradient gather."""
+    if E.lib() is None:
+        pytest.skip("g++ not available")
+    args = dict(model="resnet18", dataset="MNIST", channel=512, num_classes=10, slots_per_class=1, power=1, to_k_layer=1,
+                loss_status=1, lambda_value=1.0)
+    m = sb.SlotModel(make_args(**args))
+    sd = fill_state_dict(m.state_dict(), seed=0)
+    B, size = 3, 64
+    x = synth_images(B, 1, size, size)
+    tgt = synth_labels(B, 10)
+    kw = dict(num_classes=10, slots_per_class=1, loss_status=1, power=1, lambda_value=1.0)
+    ref = train_step("resnet18", sd, x, tgt, **kw)
+    ref64 = train_step("resnet18", sd, x, tgt, dtype=torch.float64, **kw)
+    t = Tape(sd)
+    h, stem_back = conv_bn(t, to_nhwc(x), "backbone.conv1", "backbone.bn1", stride=2, pad=1, need_dx=False)
+    pool_in = h
+    h = to_nhwc(F.max_pool2d(to_nchw(h), 3, 2, 1))
+    blocks = []
+    for li in range(1, 5):
+        for bi in range(2):
+            first = bi == 0 and li > 1
+            h, bk = basic_block(t, h, f"backbone.layer{li}.{bi}", 2 if first else 1, first)
+            blocks.append(bk)
+    bsz, fh, fw, ch = h.shape
+    n, S = fh * fw, 10
+    with torch.no_grad():
+        ho = oh.head_forward(sd, to_nchw(h), num_classes=10, slots_per_class=1, loss_status=1, power=1, return_attn=True)
+    g_logits = (ho["log_probs"].exp() - F.one_hot(tgt, 10)) / bsz
+    coef = 1.0 * 1 / (bsz * S * n)                                                                 # power 1: lambda / (B S n)
+    pe = oh.sine_pe(64, fh, fw).reshape(64, n).t().numpy()
+    d_feat, head_grads = E.head_backward(h.reshape(bsz, n, ch), {k: v.numpy() for k, v in sd.items() if not k.startswith("backbone.")},
+                                         pe, g_logits.numpy(), coef, 10, 1, 1, 1)
+    for k, v in head_grads.items():
+        t._acc(k, v)
+    d = d_feat.reshape(bsz, fh, fw, ch)
+    for bk in reversed(blocks):
+        d = bk(d)
+    d = E.pool_backward(0, pool_in, d)
+    stem_back(d)
+    scale = max(float(g.abs().max()) for g in ref["grads"].values() if g is not None)
+    checked = 0
+    for k, g_ref in ref["grads"].items():
+        if g_ref is None:
+            continue
+        den = max(float(g_ref.abs().max()), 1e-4 * scale)
+        floor = float((g_ref.double() - ref64["grads"][k]).abs().max()) / den
+        err = float((t.grads[k] - g_ref).abs().max()) / den
+        assert err < max(5e-4, 8 * floor), (k, err, floor)
+        checked += 1
+    assert checked == len(t.grads)
     for k, v in ref["bn_updates"].items():
         assert np.allclose(t.bn_after[k], v.numpy(), rtol=1e-4, atol=1e-5), k
