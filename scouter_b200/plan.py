@@ -167,6 +167,110 @@ def lower_backbone(net, math: int = L.MATH_FP32):
     return p, x
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Row f1 groundwork: the TRAINING step as an op program (host side only -- the C++ executor does not run these kinds yet;
+# tests/test_train_program.py interprets the program with the host emulations of the draft kernels in csrc/draft/ and
+# compares every gradient with the train-mode oracle).  In train mode BatchNorm uses batch statistics and cannot be
+# folded into the conv, so conv and BatchNorm(+residual, ReLU) are separate ops and every buffer that the backward needs
+# (conv inputs, BatchNorm inputs and outputs, pool inputs) stays live until its backward op has run.
+# ---------------------------------------------------------------------------------------------------------------------
+def lower_backbone_train(net, prefix: str = "backbone."):
+    """Forward op list of ``ResNet.forward_features`` (resnet.py:491-501) in train mode.  Ops are dicts:
+    ``conv`` {src, dst, key, stride, pad, groups, need_dx}, ``bn`` {src, dst, key, relu, res}, ``maxpool`` /
+    ``avgpool2`` (2,2,ceil,count_include_pad=False) / ``avgpool3`` (3,2,1) {src, dst}, ``splat_gap`` {src, dst} and
+    ``splat_mix`` {src (x2), logits, dst} of split attention (split_attn.py:62-79).  Returns (ops, n_buffers, feature
+    buffer); buffer 0 is the network input, keys are the reference's state_dict prefixes."""
+    from .backbone import BasicBlock, ResNestBottleneck
+    ops, nbuf = [], [1]
+
+    def buf():
+        nbuf[0] += 1
+        return nbuf[0] - 1
+
+    def conv_bn(src, ckey, bkey, conv, relu=True, res=-1, need_dx=True):
+        mid = buf()
+        ops.append(dict(kind="conv", src=src, dst=mid, key=prefix + ckey, stride=conv.stride[0], pad=conv.padding[0],
+                        groups=conv.groups, need_dx=need_dx))
+        dst = buf()
+        ops.append(dict(kind="bn", src=mid, dst=dst, key=prefix + bkey, relu=relu, res=res))
+        return dst
+
+    if isinstance(net.conv1, nn.Sequential):
+        x = conv_bn(0, "conv1.0", "conv1.1", net.conv1[0], need_dx=False)
+        x = conv_bn(x, "conv1.3", "conv1.4", net.conv1[3])
+        x = conv_bn(x, "conv1.6", "bn1", net.conv1[6])
+    else:
+        x = conv_bn(0, "conv1", "bn1", net.conv1, need_dx=False)
+    dst = buf()
+    ops.append(dict(kind="maxpool", src=x, dst=dst))
+    x = dst
+    for li in range(1, 5):
+        for bi, blk in enumerate(getattr(net, f"layer{li}")):
+            p = f"layer{li}.{bi}."
+            if isinstance(blk, ResNestBottleneck):
+                sa = blk.conv2
+                o1 = conv_bn(x, p + "conv1", p + "bn1", blk.conv1)
+                x2 = conv_bn(o1, p + "conv2.conv", p + "conv2.bn0", sa.conv)
+                gap = buf()
+                ops.append(dict(kind="splat_gap", src=x2, dst=gap))
+                a1 = conv_bn(gap, p + "conv2.fc1", p + "conv2.bn1", sa.fc1)
+                logits = buf()
+                ops.append(dict(kind="conv", src=a1, dst=logits, key=prefix + p + "conv2.fc2", stride=1, pad=0, groups=1, need_dx=True))
+                o2 = buf()
+                ops.append(dict(kind="splat_mix", src=x2, logits=logits, dst=o2, gap=gap))
+                if blk.avd_last is not None:
+                    d2 = buf()
+                    ops.append(dict(kind="avgpool3", src=o2, dst=d2))
+                    o2 = d2
+                res = x
+                if blk.downsample is not None:
+                    if isinstance(blk.downsample[0], nn.AvgPool2d):
+                        r = buf()
+                        ops.append(dict(kind="avgpool2", src=x, dst=r))
+                        res = conv_bn(r, p + "downsample.1", p + "downsample.2", blk.downsample[1], relu=False)
+                    else:
+                        res = conv_bn(x, p + "downsample.1", p + "downsample.2", blk.downsample[1], relu=False)
+                x = conv_bn(o2, p + "conv3", p + "bn3", blk.conv3, relu=True, res=res)
+            elif isinstance(blk, BasicBlock):
+                o1 = conv_bn(x, p + "conv1", p + "bn1", blk.conv1)
+                res = x
+                if blk.downsample is not None:
+                    res = conv_bn(x, p + "downsample.0", p + "downsample.1", blk.downsample[0], relu=False)
+                x = conv_bn(o1, p + "conv2", p + "bn2", blk.conv2, relu=True, res=res)
+            else:
+                raise L.ScouterError(f"cannot lower block type {type(blk).__name__}")
+    return ops, nbuf[0], x
+
+
+def backward_schedule(ops, feature_buffer: int):
+    """Reverse-mode schedule of a ``lower_backbone_train`` program.  Gradient buffer ids equal forward buffer ids; an
+    entry's ``acc`` says whether its gradient output must be ADDED to a buffer some later consumer already wrote (a
+    block input feeds both the main path and the shortcut) or may overwrite it.  ``splat_gap``'s backward is the
+    split-attention *apply* stage: it needs the gradient of the mixed output (``d_mix``) and of the pooled descriptor."""
+    written = {feature_buffer}                    # the head's backward delivers d(features)
+    sched = []
+    mix_of_gap = {op["gap"]: op for op in ops if op["kind"] == "splat_mix"}
+    for op in reversed(ops):
+        e = dict(op)
+        outs = []
+        if op["kind"] == "conv":
+            outs = [op["src"]] if op["need_dx"] else []
+        elif op["kind"] == "bn":
+            outs = [op["src"]] + ([op["res"]] if op["res"] >= 0 else [])
+        elif op["kind"] == "splat_mix":
+            outs = [op["logits"]]
+        elif op["kind"] == "splat_gap":
+            mix = mix_of_gap[op["dst"]]
+            e.update(d_mix=mix["dst"], logits=mix["logits"])
+            outs = [op["src"]]
+        else:
+            outs = [op["src"]]
+        e["acc"] = {o: (o in written) for o in outs}
+        written.update(outs)
+        sched.append(e)
+    return sched
+
+
 class CompiledProgram:
     """A ``scouter_plan_t`` plus its bound arena for one input shape."""
 
