@@ -98,23 +98,12 @@ def run_backward(ops, sched, sd, buf, saved, d_feat, feat):
     return grads
 
 
-@pytest.mark.timeout(900)
-@pytest.mark.parametrize("model,extra", [("resnest26d", dict()), ("resnet18", dict(dataset="MNIST", channel=512, to_k_layer=1, power=1))])
-def test_train_program_interpreted_matches_train_oracle(model, extra):
-    if E.lib() is None:
-        pytest.skip("g++ not available")
-    a = dict(model=model, num_classes=10, slots_per_class=1, power=2, to_k_layer=3, loss_status=1, lambda_value=1.0)
-    a.update(extra)
-    m = sb.SlotModel(make_args(**a))
-    sd = fill_state_dict(m.state_dict(), seed=0)
+def program_gradients(m, a, sd, x, tgt):
+    """One training-step forward + backward of SlotModel ``m`` through the op program and the emulated draft kernels.
+    -> ({state_dict key: gradient tensor}, {running-statistic key: value after the step})"""
     ops, nbuf, feat = lower_backbone_train(m.backbone)
     sched = backward_schedule(ops, feat)
     assert len(sched) == len(ops) and sorted(o["dst"] for o in ops) == list(range(1, nbuf))
-    B, size, cin = 3, 64, (1 if model == "resnet18" else 3)
-    x, tgt = synth_images(B, cin, size, size), synth_labels(B, 10)
-    kw = dict(num_classes=10, slots_per_class=1, loss_status=1, power=a["power"], lambda_value=1.0)
-    ref, ref64 = train_step(model, sd, x, tgt, **kw), train_step(model, sd, x, tgt, dtype=torch.float64, **kw)
-
     buf, saved, bn_after = run_forward(ops, sd, to_nhwc(x))
     h = buf[feat]
     bsz, fh, fw, ch = h.shape
@@ -129,6 +118,23 @@ def test_train_program_interpreted_matches_train_oracle(model, extra):
                                     g_logits.numpy(), coef, 10, 1, 1, L)
     grads = {k: torch.from_numpy(np.ascontiguousarray(v)).reshape(sd[k].shape) for k, v in grads.items()}
     grads.update(run_backward(ops, sched, sd, buf, saved, d_feat.reshape(bsz, fh, fw, ch), feat))
+    return grads, bn_after
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("model,extra", [("resnest26d", dict()), ("resnet18", dict(dataset="MNIST", channel=512, to_k_layer=1, power=1))])
+def test_train_program_interpreted_matches_train_oracle(model, extra):
+    if E.lib() is None:
+        pytest.skip("g++ not available")
+    a = dict(model=model, num_classes=10, slots_per_class=1, power=2, to_k_layer=3, loss_status=1, lambda_value=1.0)
+    a.update(extra)
+    m = sb.SlotModel(make_args(**a))
+    sd = fill_state_dict(m.state_dict(), seed=0)
+    B, size, cin = 3, 64, (1 if model == "resnet18" else 3)
+    x, tgt = synth_images(B, cin, size, size), synth_labels(B, 10)
+    kw = dict(num_classes=10, slots_per_class=1, loss_status=1, power=a["power"], lambda_value=1.0)
+    ref, ref64 = train_step(model, sd, x, tgt, **kw), train_step(model, sd, x, tgt, dtype=torch.float64, **kw)
+    grads, bn_after = program_gradients(m, a, sd, x, tgt)
 
     scale = max(float(g.abs().max()) for g in ref["grads"].values() if g is not None)
     checked = 0
