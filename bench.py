@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = "images/sec SlotModel forward (resnest26d, 10 slots)"
+METRIC = "images/sec SlotModel forward (resnest26d, 10 slots) @1/2/4/8 B200"     # BASELINE.json's metric string, verbatim
 ARGS = dict(model="resnest26d", dataset="ImageNet", channel=2048, num_classes=10, slots_per_class=1, power=2,
             to_k_layer=3, loss_status=-1, lambda_value=1.0)
 # 2*MACs of the 47 backbone convs per image
