@@ -43,7 +43,7 @@ AW_HD void adamw_element(const AdamWArgs& a, size_t i) {
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(256) adamw_kernel(AdamWArgs a) {
+static __global__ void __launch_bounds__(256) adamw_kernel(AdamWArgs a) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x)
         adamw_element(a, i);
 }

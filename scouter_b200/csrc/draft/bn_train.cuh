@@ -161,21 +161,21 @@ BN_HD void bn_bwd_apply(const BnBwdArgs& a, long long i4) {
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(BnBwdArgs a) { bn_bwd_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
-__global__ void bn_bwd_finalize_kernel(BnBwdArgs a) {
+static __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(BnBwdArgs a) { bn_bwd_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
+static __global__ void bn_bwd_finalize_kernel(BnBwdArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < a.C) bn_bwd_finalize(a, c);
 }
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
+static __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
     const long long n4 = a.M * a.C / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) bn_bwd_apply(a, i);
 }
-__global__ void __launch_bounds__(256) bn_stats_kernel(BnTrainArgs a) { bn_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
-__global__ void bn_finalize_kernel(BnTrainArgs a) {
+static __global__ void __launch_bounds__(256) bn_stats_kernel(BnTrainArgs a) { bn_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
+static __global__ void bn_finalize_kernel(BnTrainArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < a.C) bn_finalize(a, c);
 }
-__global__ void __launch_bounds__(256) bn_apply_kernel(BnTrainArgs a) {
+static __global__ void __launch_bounds__(256) bn_apply_kernel(BnTrainArgs a) {
     const long long n4 = a.M * a.C / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) bn_apply(a, i);
 }

@@ -98,13 +98,13 @@ WG_HD void conv_dgrad_element(const DgradArgs& a, long long idx) {     // idx ov
 }
 
 #ifdef __CUDACC__
-__global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
+static __global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
     const long long n = (long long)a.B * a.H * a.W * a.Cin;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) conv_dgrad_element(a, i);
 }
 
 // grid (ceil(elements / 256), k_splits)
-__global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
+static __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
     const long long elems = (long long)a.Cout * a.k * a.k * (a.Cin / a.groups);
     const long long M = (long long)a.B * a.Ho * a.Wo;
     const long long per = (M + gridDim.y - 1) / gridDim.y;

@@ -131,7 +131,7 @@ PS_HD void splat_bwd_apply(const SplatBwdArgs& a, long long idx) {      // idx o
 
 #ifdef __CUDACC__
 #define PS_KERNEL(name, fn, Args, count)                                                                     \
-    __global__ void __launch_bounds__(256) name(Args a) {                                                   \
+    static __global__ void __launch_bounds__(256) name(Args a) {                                                   \
         const long long n_ = (count);                                                                       \
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_; i += (long long)gridDim.x * blockDim.x) fn(a, i); \
     }

@@ -14,6 +14,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_draft: first GPU run of the row-f1 draft kernels (pytest -m gpu_draft; never part of -m gpu, "
+                                       "skipped without CUDA)")
 
 
 def load_golden(name):

@@ -1,0 +1,71 @@
+"""FIRST GPU RUN of the row-f1 draft kernels (scouter_b200/csrc/draft/): ``pytest -m gpu_draft`` on a B200, ideally once
+under ``compute-sanitizer --tool memcheck`` and once under ``--tool racecheck``.
+
+Deliberately NOT marked ``gpu``: the round-end ``pytest -m gpu`` must only contain tests that have been seen green on
+hardware, and none of this has run on a GPU yet.  Without CUDA everything here is skipped.  The tests re-run the CPU
+checks with ``draft_emu.BACKEND = "gpu"``: the same ctypes argument blocks, pointed at device memory, launched through
+``draft_api.cu`` (built into its own libscouter_draft.so) -- so whatever passes here has run the real kernels."""
+import numpy as np
+import pytest
+import torch
+
+import draft_emu as E
+
+pytestmark = [pytest.mark.gpu_draft, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+
+@pytest.fixture(autouse=True)
+def gpu_backend(monkeypatch):
+    monkeypatch.setattr(E, "BACKEND", "gpu")
+    yield
+    E._dev.clear()
+
+
+def test_each_kernel_group_gpu_equals_host_emulation():
+    """Every wrapper once on random data: GPU result vs the host emulation of the same body (atomics reorder sums: 1e-5)."""
+    rng = np.random.RandomState(0)
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+
+    def both(fn):
+        E.BACKEND = "host"
+        h = fn()
+        E.BACKEND = "gpu"
+        return h, fn()
+
+    def close(a, b, tol=1e-5):
+        for u, v in zip(a, b):
+            if u is None:
+                assert v is None
+                continue
+            assert np.abs(u - v).max() <= tol * max(1.0, np.abs(u).max())
+
+    x, res, g, b = f(4, 5, 6, 64) * 2 + 3, f(4, 5, 6, 64), np.abs(f(64)) + 0.5, f(64)
+    state = lambda: (np.zeros(64, np.float32), np.ones(64, np.float32))
+    close(*both(lambda: E.bn_train_forward(x, g, b, *state(), residual=res, relu=True)))
+    y, mean, rstd = E.bn_train_forward(x, g, b, *state(), residual=res, relu=True)
+    close(*both(lambda: E.bn_train_backward(x, y, f(4, 5, 6, 64), g, mean, rstd, relu=True, want_residual=True)))
+    w = f(32, 3, 3, 32)
+    dy = f(4, 5, 6, 32)
+    rng2 = np.random.RandomState(1)
+    close(*both(lambda: E.conv_backward(x, dy, w, 1, 1, 2)))
+    xin = np.maximum(f(2, 9, 8, 16), 0)
+    for kind, oshape in ((0, (2, 5, 4, 16)), (1, (2, 5, 4, 16)), (2, (2, 5, 4, 16))):
+        d = rng2.standard_normal(oshape).astype(np.float32)
+        close(*both(lambda: (E.pool_backward(kind, xin, d),)))
+    x2, d_out = np.maximum(f(3, 4, 4, 32), 0), f(3, 4, 4, 16)
+    att = np.abs(f(3, 2, 16)); att /= att.sum(1, keepdims=True)
+    close(*both(lambda: (E.splat_backward_logits(x2, d_out, att),)))
+    close(*both(lambda: (E.splat_backward_apply(x2, d_out, att, f(3, 16) * 0 + 0.25),)))
+    pr, gr = f(10007), f(10007)
+    def adam():
+        q, m, v = pr.copy(), np.zeros_like(pr), np.zeros_like(pr)
+        E.adamw_step(q, gr, m, v, 1e-4, 1)
+        return q, m, v
+    close(*both(adam), tol=1e-6)
+
+
+@pytest.mark.parametrize("model,extra", [("resnet18", dict(dataset="MNIST", channel=512, to_k_layer=1, power=1)), ("resnest26d", dict())])
+def test_training_program_on_gpu_matches_train_oracle(model, extra):
+    """tests/test_train_program.py with every backward kernel (head, BatchNorm, convs, pools, split attention) on the GPU."""
+    from test_train_program import test_train_program_interpreted_matches_train_oracle as run
+    run(model, extra)
