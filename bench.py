@@ -2,20 +2,24 @@
 """bench.py -- images/sec of SlotModel.forward (resnest26d, 10 slots) on N B200s (BASELINE.json metric).
 
     python bench.py [--gpus N --steps K --warmup W]          # this repo's CUDA path
-    python bench.py --impl reference [...]                   # the reference algorithm on the host CPU
+    python bench.py --impl reference [...]                   # the reference's own SlotModel.forward on the host CPU
+    python bench.py --config cfg2|cfg3|cfg4|cfg5 [--size 260]   # the other BASELINE configs (default cfg3 @224)
 
-A "step" is one eval-mode forward of one synthetic batch: cfg 3 of BASELINE.json -- ImageNet-10
-resnest26d + negative xSlot (loss_status -1, to_k_layer 3), batch 256 per GPU, 3x224x224 fp32 (the
-batch north_star's roofline target is quoted on; override with --batch/--size).  One JSON line on stdout:
+A "step" is one eval-mode forward of one synthetic batch.  Default workload: cfg 3 of BASELINE.json -- ImageNet-10
+resnest26d + negative xSlot (loss_status -1, to_k_layer 3), batch 256 per GPU, 3x224x224 fp32 (the batch north_star's
+roofline target is quoted on).  One JSON line on stdout:
 
   value        whole-job images/s, inputs resident in HBM, whole forward replayed from a CUDA graph,
                CUDA-event timed, max over ranks (weak scaling: every rank runs its own batch of B)
-  e2e          same metric through the C-ABI host entry (scouter_forward_host): pinned host batch ->
-               H2D -> forward -> D2H of the log-probs, every step
-  roofline     the fused xSlot head (conv1x1 + PE + to_k + 3x attention/GRU + logits): algorithmic
-               bytes (B*ch*n*4 feature read + weights + logits) / its CUDA-event time, vs measured HBM GB/s
-  roofline_backbone   the backbone program: algorithmic conv FLOPs / its time vs the measured tensor peak
-  cpu_baseline the oracle port of the reference forward on the host cores (bounded sample)
+  e2e          same metric through the host-facing API: pinned host batch -> H2D -> forward -> D2H, every step
+  roofline     the xSlot head (conv1x1 + PE + to_k + 3x attention/GRU + logits): algorithmic bytes
+               (B*ch*n*4 feature read + weights + logits) / its CUDA-event time, vs measured HBM GB/s
+  roofline_backbone   the backbone program (its own CUDA graph): algorithmic conv FLOPs / time vs the tf32 tensor peak
+               measured by scripts/probes/unit_peaks_probe.cu (profiles/r02_unit_peaks.json)
+  cpu_baseline the reference forward on the host cores (bounded sample); kind = "reference" when the unmodified
+               reference is present in baseline/_ref (scripts/fetch_ref.sh), else "port" (oracle restatement)
+  gpu_eager_baseline  the unmodified reference module .cuda() on the same GPU: stock PyTorch eager (cuDNN/cuBLAS),
+               default TF32 flags and TF32 off -- the same-box vendor bar (N=1 only)
 """
 from __future__ import annotations
 
@@ -34,18 +38,54 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "images/sec SlotModel forward (resnest26d, 10 slots) @1/2/4/8 B200"     # BASELINE.json's metric string, verbatim
-ARGS = dict(model="resnest26d", dataset="ImageNet", channel=2048, num_classes=10, slots_per_class=1, power=2,
-            to_k_layer=3, loss_status=-1, lambda_value=1.0)
-# 2*MACs of the 47 backbone convs per image
-BACKBONE_GFLOP = {224: 7.24, 260: 10.30}
+# BASELINE.json.configs (SURVEY.md section 8 legend): model args, per-rank batch, native size, ranks the config is quoted on
+CONFIGS = {
+    "cfg1": dict(args=dict(model="resnet18", dataset="MNIST", channel=512, num_classes=10, slots_per_class=1, power=1,
+                           to_k_layer=1, loss_status=1, lambda_value=1.0), batch=64, cin=1, size=260, ranks=1,
+                 name="cfg1: MNIST resnet18 + xSlot (10x1 slots, to_k_layer 1)"),
+    "cfg2": dict(args=dict(model="resnest26d", dataset="ImageNet", channel=2048, num_classes=10, slots_per_class=1, power=2,
+                           to_k_layer=3, loss_status=1, lambda_value=1.0), batch=70, cin=3, size=224, ranks=1,
+                 name="cfg2: ImageNet-10 resnest26d + positive xSlot (to_k_layer 3, 10x1 slots)"),
+    "cfg3": dict(args=dict(model="resnest26d", dataset="ImageNet", channel=2048, num_classes=10, slots_per_class=1, power=2,
+                           to_k_layer=3, loss_status=-1, lambda_value=1.0), batch=256, cin=3, size=224, ranks=1,
+                 name="cfg3: ImageNet-10 resnest26d + negative xSlot (loss_status -1, to_k_layer 3, 10x1 slots)"),
+    "cfg4": dict(args=dict(model="resnest26d", dataset="ConText", channel=2048, num_classes=30, slots_per_class=1, power=2,
+                           to_k_layer=3, loss_status=1, lambda_value=1.0), batch=200, cin=3, size=224, ranks=4,
+                 name="cfg4: ConText-30 resnest26d + xSlot (30x1 slots)"),
+    "cfg5": dict(args=dict(model="resnest26d", dataset="CUB200", channel=2048, num_classes=200, slots_per_class=2, power=2,
+                           to_k_layer=3, loss_status=1, lambda_value=1.0), batch=512, cin=3, size=224, ranks=8,
+                 name="cfg5: CUB200 resnest26d + xSlot (200x2 slots)"),
+}
+# 2*MACs of the backbone convs per image
+BACKBONE_GFLOP = {("resnest26d", 224): 7.24, ("resnest26d", 260): 10.30, ("resnet18", 260): 4.98}
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], src="measured")
-    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+        out = dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], src="measured")
+    else:
+        out = dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+    # tf32 tensor / fp32 FFMA peaks: measured by scripts/probes/unit_peaks_probe.cu on this pool (committed summary)
+    u = os.path.join(ROOT, "profiles", "r02_unit_peaks.json")
+    if os.path.exists(u):
+        d = json.load(open(u))
+        out.update(tf32=d["tf32_umma_tflops_sustained"], tf32_burst=d["tf32_umma_tflops"], ffma=d["fp32_ffma_tflops_sustained"],
+                   tf32_src="measured: scripts/probes/unit_peaks_probe.cu, tcgen05.mma.kind::tf32 M128 N256 K8 on all SMs, "
+                            "sustained (profiles/r02_unit_peaks.json)")
+    else:
+        out.update(tf32=out["bf16_sustained"] / 2, tf32_burst=out["bf16_burst"] / 2, ffma=None,
+                   tf32_src=out["src"] + " bf16 sustained / 2 (tf32 assumed half of bf16; profiles/r02_unit_peaks.json absent)")
+    return out
+
+
+def head_traffic(cfg, batch, size):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the head's kernels for one launch (ncu --set full), or None."""
+    p = os.path.join(ROOT, "profiles", "r02_head_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(f"{cfg}_b{batch}_{size}")
+    return None
 
 
 class ClockSampler:
@@ -93,28 +133,86 @@ class ClockSampler:
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_rate(batch, size, steps, warmup):
-    """The reference algorithm (oracle port: oracle/backbone.py + oracle/head.py) on the host cores."""
+def _reference_forward(cfg, size, device="cpu"):
+    """(callable x -> log-probs, kind): the unmodified reference's SlotModel when baseline/_ref (or /root/reference) is
+    there, else the oracle port (same torch ops; CPU only).  Same deterministic synthetic weights as our arm."""
     import scouter_b200 as sb
+    from scouter_b200.synth import fill_state_dict, make_args
+    c = CONFIGS[cfg]
+    ours = sb.SlotModel(make_args(**c["args"]))
+    sd = fill_state_dict(ours.state_dict(), seed=0)
+    from baseline import refload
+    fs = None
+    try:
+        ref = refload.load_reference_model(state_dict=sd, **c["args"])
+    except Exception as e:          # a broken copy must not take the bench line down: fall back to the port and say so
+        print(f"bench: reference import failed ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+        ref = None
+    if ref is not None:
+        ref = ref.to(device)
+
+        def fwd(x):
+            nonlocal fs
+            if fs is None:                      # feature map side for this input size (SURVEY.md D6: hard-wired 9 in the reference)
+                with torch.no_grad():
+                    f = ref.backbone(x[:1])
+                fs = int(round((f.shape[1] // c["args"]["channel"]) ** 0.5))
+                ref.feature_size = fs
+            return ref(x)
+        return fwd, "reference"
+    if device != "cpu":
+        return None, "unavailable"
     from oracle import backbone as ob
-    from scouter_b200.synth import fill_state_dict, make_args, synth_images
+    a = c["args"]
+    return (lambda x: ob.slot_model_forward(a["model"], sd, x, num_classes=a["num_classes"], slots_per_class=a["slots_per_class"],
+                                            loss_status=a["loss_status"], power=a["power"])), "port"
+
+
+def cpu_reference_rate(cfg, batch, size, steps, warmup):
+    from scouter_b200.synth import synth_images
     torch.set_num_threads(os.cpu_count())
-    m = sb.SlotModel(make_args(**ARGS))
-    sd = fill_state_dict(m.state_dict(), seed=0)
-    x = synth_images(batch, 3, size, size)
-    fwd = lambda: ob.slot_model_forward("resnest26d", sd, x, num_classes=10, slots_per_class=1, loss_status=-1, power=2)
+    fwd, kind = _reference_forward(cfg, size, "cpu")
+    x = synth_images(batch, CONFIGS[cfg]["cin"], size, size)
     with torch.no_grad():
         for _ in range(warmup):
-            fwd()
+            fwd(x)
         t0 = time.perf_counter()
         for _ in range(steps):
-            fwd()
+            fwd(x)
         dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads()
+    return batch * steps / dt, dt / steps, torch.get_num_threads(), kind
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one head_fused_kernel launch at B=256, 224^2 (ncu --set full)
-HEAD_DRAM_TRAFFIC = 104132608 + 4102656
+def gpu_eager_baseline(cfg, x, ours_log_probs, steps=10, warmup=3):
+    """The unmodified reference module on the same GPU (stock eager PyTorch: cuDNN convs, cuBLAS bmm/addmm, ATen
+    pointwise), CUDA-event timed at the same batch -- with torch's default TF32 flags and with TF32 off."""
+    fwd, kind = _reference_forward(cfg, x.shape[-1], x.device)
+    if fwd is None:
+        return {"unavailable": "no reference tree in baseline/_ref (run scripts/fetch_ref.sh in the build container)"}
+    out = {"impl": "unmodified reference SlotModel.forward, eval, no_grad, torch %s eager" % torch.__version__, "batch": x.shape[0]}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, cud, mm in (("default_flags", saved[0], saved[1]), ("tf32_off", False, False)):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = cud, mm
+            with torch.no_grad():
+                for _ in range(warmup):
+                    y = fwd(x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    y = fwd(x)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            ref = y[0] if isinstance(y, (list, tuple)) else y
+            diff = float((ref - ours_log_probs).abs().max() / max(1.0, float(ref.abs().max())))
+            out[name] = {"value": x.shape[0] / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+                         "cudnn_allow_tf32": bool(cud), "matmul_allow_tf32": bool(mm),
+                         "max_log_prob_diff_vs_ours": diff}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return out
 
 
 _REAL_STDOUT = None
@@ -134,12 +232,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: the config's)")
+    ap.add_argument("--size", type=int, default=None, help="input side (default 224; cfg1: 260)")
     ap.add_argument("--math", default=os.environ.get("SCOUTER_MATH", "tc"), choices=["tc", "fp32", "tc_fast"])
-    ap.add_argument("--cpu-sample", type=int, default=32, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="images per step of the cpu_baseline leg of our arm")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    cfg = CONFIGS[a.config]
+    margs = cfg["args"]
+    a.batch = a.batch or cfg["batch"]
+    a.size = a.size or cfg["size"]
     rank = int(os.environ.get("RANK", "0"))
     # stdout carries exactly ONE JSON line: libraries that write banners to file descriptor 1 (NCCL prints its version
     # there at communicator creation) go to stderr until the line is printed
@@ -149,20 +253,24 @@ def main():
     os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = (f"cfg3: ImageNet-10 resnest26d + negative xSlot (loss_status -1, to_k_layer 3, 10x1 slots), "
-                f"batch {a.batch}/GPU, 3x{a.size}x{a.size} fp32, eval forward")
+    workload = f"{cfg['name']}, batch {a.batch}/GPU, {cfg['cin']}x{a.size}x{a.size} fp32, eval forward"
+    C_, S = margs["num_classes"], margs["num_classes"] * margs["slots_per_class"]
 
     if a.impl == "reference":
         if rank != 0:
             return
-        rate, spb, cores = cpu_reference_rate(a.cpu_sample, a.size, a.steps, min(a.warmup, 1))
-        sample = f"{a.cpu_sample} images/step x {a.steps} steps of the same workload (oracle port of the reference, torch CPU ops)"
+        # the reference's own forward on the host cores, same config and batch; a step = one batch (bounded: the whole
+        # --steps/--warmup run stays within minutes at ~70 img/s on a 2-socket host)
+        rate, spb, cores, kind = cpu_reference_rate(a.config, a.batch, a.size, a.steps, a.warmup)
+        what = ("unmodified reference sloter.slot_model.SlotModel from baseline/_ref" if kind == "reference"
+                else "oracle port of the reference (baseline/_ref absent)")
+        sample = f"{a.batch} images/step x {a.steps} steps after {a.warmup} warm-ups ({what}, torch CPU ops, all host threads)"
         emit(json.dumps({
             "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": min(a.warmup, 1), "ms_per_step": spb * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": spb * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "note": "host CPU only; bounded sample per step"},
-            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload, "global_batch": a.batch, "note": "host CPU only (rank 0); one batch per step"},
+            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -178,19 +286,26 @@ def main():
     sdist.init_from_env("nccl", dev)
     L.check(L.lib().scouter_device_check(local))
 
-    m = sb.SlotModel(make_args(**ARGS))
+    m = sb.SlotModel(make_args(**margs))
     m.load_state_dict(fill_state_dict(m.state_dict(), seed=0))
     m = m.to(dev).eval()
     m.math = {"tc": L.MATH_TC, "fp32": L.MATH_FP32, "tc_fast": L.MATH_TC_FAST}[a.math]
     m.use_cuda_graph = True
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.randn(a.batch, 3, a.size, a.size, device=dev, generator=g)
+    x = torch.randn(a.batch, cfg["cin"], a.size, a.size, device=dev, generator=g)
     x_host = x.cpu().pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
 
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -200,12 +315,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms
+        return max_ranks(e0.elapsed_time(e1))
 
     with torch.no_grad():
         # ---- whole forward, inputs resident, CUDA graph ------------------------------------------
@@ -220,6 +330,12 @@ def main():
         t1 = time.time()
         clocks = sampler.stop(t0, t1) if sampler else None
         value = world * a.batch * a.steps / (ms / 1e3)
+        # the drop-in call itself, model(x) with x already on the device (graph replay + the D2D of x into the captured
+        # input + the clone of the result): what a caller of the nn.Module API sees
+        for _ in range(2):
+            m(x)
+        ms_call = timed(lambda: m(x), a.steps)
+        call_value = world * a.batch * a.steps / (ms_call / 1e3)
 
         # ---- end to end from host memory ----------------------------------------------------------------
         # (a) one synchronous C call per step (scouter_forward_host: H2D, forward, D2H, sync);
@@ -232,7 +348,7 @@ def main():
 
         def stream_steps():
             n = 0
-            for out in m.forward_host_stream([x_host] * a.steps, dev):
+            for _out in m.forward_host_stream([x_host] * a.steps, dev):
                 n += 1
             assert n == a.steps
 
@@ -240,23 +356,18 @@ def main():
         t_w0 = time.perf_counter()
         stream_steps()
         torch.cuda.synchronize()
-        ms_e2e = (time.perf_counter() - t_w0) * 1e3
-        if world > 1:
-            t = torch.tensor([ms_e2e], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t)
+        ms_e2e = max_ranks((time.perf_counter() - t_w0) * 1e3)
         e2e_value = world * a.batch * a.steps / (ms_e2e / 1e3)
         e2e_sync_value = world * a.batch * a.steps / (ms_e2e_sync / 1e3)
 
-        # ---- per-kernel: the fused head and the backbone program, CUDA events on the launch stream ---
+        # ---- per-kernel: the head and the backbone program, CUDA events on the launch stream ---
         import ctypes as C
         desc, packed = m._head_params(st, dev)
         lib = L.lib()
         head = lambda: L.check(lib.scouter_head_forward(C.byref(desc), packed.data_ptr(), C.byref(st.io),
                                                         st.ws.data_ptr() + st.ws_off, st.ws_bytes, L.stream_ptr()))
-        bb = lambda: st.cp.run(st.static_in)
         for _ in range(3):
-            head(); bb()
+            head()
         # the head reads 103 MB of features, less than the 126 MB L2: every timed call is preceded by a 256 MB write so
         # that the features come from HBM as they do inside the forward (the flush is outside the events)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -271,16 +382,25 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 tot += e0.elapsed_time(e1)
-            ms = tot / steps
-            if world > 1:
-                t = torch.tensor([ms], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t)
-            return ms
+            return max_ranks(tot / steps)
 
         ms_head = timed_flushed(head, a.steps)
-        ms_bb = timed(bb, a.steps) / a.steps
+        # the backbone op program as its own CUDA graph (kernel time, not ~80 host launches)
+        st.cp.run(st.static_in)
+        torch.cuda.synchronize()
+        gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb):
+            st.cp.run(st.static_in)
+        for _ in range(3):
+            gb.replay()
+        ms_bb = timed(gb.replay, a.steps) / a.steps
         head_launches = lib.scouter_head_launch_count(C.byref(desc), C.byref(st.io))
+        eager = None
+        if world == 1 and not a.no_eager:
+            try:
+                eager = gpu_eager_baseline(a.config, x, out)
+            except Exception as e:      # a reported baseline must not take the line down
+                eager = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if world > 1:
@@ -289,15 +409,18 @@ def main():
 
     pk = peaks()
     n = st.n
-    S, Lk = 10, 3
-    w_bytes = 2048 * 64 * 4 + 64 * 4 + Lk * (64 * 64 + 64) * 4 + S * 64 * 4 + 2 * (192 * 64 + 192) * 4 + 64 * n * 4
-    head_bytes = a.batch * 2048 * n * 4 + a.batch * 10 * 4 + w_bytes
+    Lk, ch = margs["to_k_layer"], margs["channel"]
+    w_bytes = ch * 64 * 4 + 64 * 4 + Lk * (64 * 64 + 64) * 4 + S * 64 * 4 + 2 * (192 * 64 + 192) * 4 + 64 * n * 4
+    head_bytes = a.batch * ch * n * 4 + a.batch * C_ * 4 + w_bytes
     head_gbs = head_bytes / (ms_head / 1e3) / 1e9
-    bb_tflops = BACKBONE_GFLOP.get(a.size, 7.24 * (a.size / 224.0) ** 2) * a.batch / (ms_bb / 1e3) / 1e3
-    tf32_peak = pk["bf16_sustained"] / 2
-    # bounded CPU sample: ~10 s of host work at N=1 (the reported baseline), a token 3 steps on multi-GPU lines
-    cpu_steps = 24 if world == 1 else 3
-    cpu_rate, cpu_spb, cores = cpu_reference_rate(a.cpu_sample, a.size, cpu_steps, 1)
+    gflop = BACKBONE_GFLOP.get((margs["model"], a.size))
+    if gflop is None:
+        gflop = BACKBONE_GFLOP[(margs["model"], 224 if margs["model"] == "resnest26d" else 260)] * \
+            (a.size / (224.0 if margs["model"] == "resnest26d" else 260.0)) ** 2
+    bb_tflops = gflop * a.batch / (ms_bb / 1e3) / 1e3
+    # bounded CPU sample: ~10-30 s of host work at N=1 (the reported baseline), a token 2 steps on multi-GPU lines
+    cpu_steps = 16 if world == 1 else 2
+    cpu_rate, cpu_spb, cores, cpu_kind = cpu_reference_rate(a.config, a.cpu_sample, a.size, cpu_steps, 2)
     launches = m.launches_per_forward(tuple(x.shape), dev)
     emit(json.dumps({
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -305,28 +428,34 @@ def main():
         "dtype": {"tc": "tf32 + 2 bf16 correction products (error-compensated, fp32-class; fp32 accumulate)", "tc_fast": "tf32", "fp32": "f32"}[a.math], "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * a.batch, "parallelism": f"dp{world}",
                    "math": a.math, "timing": "CUDA events, max over ranks; whole forward = one CUDA-graph replay; inputs "
-                   "(154 MB batch + GBs of activations) larger than the 126 MB L2, no explicit flush"},
+                   "(batch + GBs of activations) larger than the 126 MB L2, no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / a.steps,
-                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": a.batch * 10 * 4,
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": a.batch * C_ * 4,
                 "api": "SlotModel.forward_host_stream (pinned host batches in, pinned log-probs out; the H2D of batch i+1 "
                        "overlaps the compute of batch i; wall-clock over all steps incl. first upload and last read-back)",
                 "synchronous_call_value": e2e_sync_value,
                 "synchronous_call": "scouter_forward_host: H2D + forward + D2H + sync in one C call per step"},
+        "module_call": {"value": call_value, "unit": "images/s", "ms_per_step": ms_call / a.steps,
+                        "api": "SlotModel.__call__(x) with x resident on the device (nn.Module drop-in surface)"},
         "gpu_launches": launches * a.steps,
         "roofline": {"kernel": "xSlot head: scouter_head_forward (conv1x1+ReLU+PE+to_k+3x{QK^T,normalise,sigmoid,attn.V,GRU}+logits)",
                      "bound": "hbm", "achieved": head_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": head_gbs / pk["hbm"],
-                     "traffic": HEAD_DRAM_TRAFFIC if (a.batch, a.size) == (256, 224) else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of head_fused_kernel, one ncu --set full capture "
-                                       "(profiles/r01_ncu_head_fused.md)",
+                     "traffic": head_traffic(a.config, a.batch, a.size),
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the head's kernels, one ncu --set full "
+                                       "capture (profiles/r02_head_traffic.json, profiles/r02_ncu_head.md)",
                      "ms": ms_head, "algorithmic_bytes": head_bytes, "peak_source": pk["src"] + " copy bandwidth",
                      "launches": head_launches, "timing": "CUDA events around each call, 256 MB L2 flush before each call"},
-        "roofline_backbone": {"kernel": "backbone op program (47 convs + pools + split attention)", "bound": "tensor",
-                              "achieved": bb_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": bb_tflops / tf32_peak,
-                              "ms": ms_bb, "peak_source": pk["src"] + " bf16 sustained / 2 (tf32 assumed half of bf16)"},
-        "cpu_baseline": {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{a.cpu_sample} images/step x {cpu_steps} steps after 1 warm-up (oracle port of the reference "
-                                   "forward, torch CPU ops, all host threads)"},
+        "roofline_backbone": {"kernel": "backbone op program (convs + pools + split attention), one CUDA graph", "bound": "tensor",
+                              "achieved": bb_tflops, "peak": pk["tf32"], "unit": "TFLOP/s", "frac": bb_tflops / pk["tf32"],
+                              "ms": ms_bb, "peak_source": pk["tf32_src"],
+                              "note": "algorithmic conv FLOPs (2*MACs, SURVEY App. B); the error-compensated product issues 2x the tf32 "
+                                      "tensor time per FLOP by construction"},
+        "cpu_baseline": {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": cpu_kind,
+                         "sample": f"{a.cpu_sample} images/step x {cpu_steps} steps after 2 warm-ups of the same workload "
+                                   f"({'unmodified reference from baseline/_ref' if cpu_kind == 'reference' else 'oracle port of the reference'}"
+                                   ", torch CPU ops, all host threads); `--impl reference` times full batches"},
+        "gpu_eager_baseline": eager,
     }))
     if world > 1:
         dist.destroy_process_group()
