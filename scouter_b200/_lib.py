@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscouter_b200.so")
+# SCOUTER_B200_LIB: load another build of the same library (debug variants built by scripts/, e.g. -DSCOUTER_PROF)
+LIB_PATH = os.environ.get("SCOUTER_B200_LIB") or os.path.join(_HERE, "libscouter_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "head_fused.cu", "stem_ts.cu", "vis.cu", "umma_conv.cu", "umma_halo.cu"]
 

@@ -43,7 +43,8 @@ def test_each_kernel_group_gpu_equals_host_emulation():
     state = lambda: (np.zeros(64, np.float32), np.ones(64, np.float32))
     close(*both(lambda: E.bn_train_forward(x, g, b, *state(), residual=res, relu=True)))
     y, mean, rstd = E.bn_train_forward(x, g, b, *state(), residual=res, relu=True)
-    close(*both(lambda: E.bn_train_backward(x, y, f(4, 5, 6, 64), g, mean, rstd, relu=True, want_residual=True)))
+    d_y = f(4, 5, 6, 64)              # drawn ONCE: both backends must see the same upstream gradient
+    close(*both(lambda: E.bn_train_backward(x, y, d_y, g, mean, rstd, relu=True, want_residual=True)))
     w = f(32, 3, 3, 32)
     dy = f(4, 5, 6, 32)
     rng2 = np.random.RandomState(1)
