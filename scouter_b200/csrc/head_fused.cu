@@ -137,6 +137,10 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmT,
                   const __grid_constant__ CUtensorMap tmT2, const FusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
+#ifdef SCOUTER_PROF
+    const long long prof_entry = clock64();
+    if (threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_prof_head[blockIdx.x * 32 + 28] = gt; }
+#endif
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int n = a.n, S = a.S;
     const int R = G * n;            // token rows of this unit; rows R .. R+G-1 of the key tile hold ksum per image
@@ -167,7 +171,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // loop views (alias the phase-A rings; see layout())
     const int ksteps = (n + 7) >> 3;                // K = 8 steps of the update MMAs
     constexpr int SS = G == 2 ? 16 : 0;             // slot row of (image g, slot i) = g * SS + i
-    constexpr int SPP = G == 2 ? 16 : 32;           // row stride of the plain attention
+    constexpr int SPP = G == 2 ? 17 : 33;           // row stride of the plain attention (odd: conflict-free column reads)
     uint8_t* const xt = smem + a.off_xt;
     uint8_t* const xl = smem + a.off_xl;
     uint8_t* const atb = smem + a.off_atb;
@@ -223,9 +227,21 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     PROF_DECL(phaseA); PROF_DECL(mlp); PROF_DECL(loop); PROF_BEGIN(phaseA);
+#ifdef SCOUTER_PROF
+    if (threadIdx.x == 0) g_prof_head[blockIdx.x * 32 + 26] = (unsigned long long)(prof_begin_phaseA - prof_entry);
+#endif
 
     const int kblocks = a.kblocks;
     uint8_t* const w_ring = smem + a.off_w;
+    // small parameters that the serial tail reads once (PE rows, GRU matrices and biases): pull them into L2 now, while the
+    // feature stream runs -- inside a forward they were evicted by gigabytes of activations since the last call
+    if (warp >= 4 && warp < 8) {
+        const int t = tid - 128;
+        auto pf = [](const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+        for (int i = t; i < (n * XD * 4 + 127) / 128; i += 128) pf(reinterpret_cast<const char*>(a.pe) + i * 128);
+        for (int i = t; i < XG * XD * 4 / 128; i += 128) { pf(reinterpret_cast<const char*>(a.gru_w_ih) + i * 128); pf(reinterpret_cast<const char*>(a.gru_w_hh) + i * 128); }
+        if (t < 6) { pf(a.gru_b_ih + 32 * t); pf(a.gru_b_hh + 32 * t); }
+    }
 
     // =========================================== phase A ===========================================================
     if (warp == 0) {
@@ -943,15 +959,26 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (tid == 0) LT(15);
     }
 
+#ifdef SCOUTER_PROF
+#define ET(slot) do { if (tid == 0) g_prof_head[blockIdx.x * 32 + (slot)] = (unsigned long long)(clock64() - prof_begin_loop); } while (0)
+#else
+#define ET(slot)
+#endif
+    ET(12);
     // ---- logits_i = loss_status / d * sum_j attn_ij * rowsum(X_j): one warp per (image, slot), fixed shuffle tree -------
-    for (int sl = warp; sl < G * S; sl += HW_) {
-        const int g = sl / S, i = sl - g * S;
+    {   // half-warp per (image, slot): all pairs at once
+        const int sl = tid >> 4, hl = lane & 15;
+        const int g = (G == 2 && sl >= S) ? 1 : 0, i = sl - g * S;
         float s_ = 0.f;
-        for (int jj = lane; jj < n; jj += 32) s_ = fmaf(attnP[(g * n + jj) * SPP + i], xsum[g * n + jj], s_);
-        s_ = warp_sum(s_);
-        if (lane == 0) usum[sl] = s_ * (1.0f / XD);
+        if (sl < G * S)
+            for (int jj = hl; jj < n; jj += 16) s_ = fmaf(attnP[(g * n + jj) * SPP + i], xsum[g * n + jj], s_);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s_ += __shfl_xor_sync(0xffffffffu, s_, o);
+        if (hl == 0 && sl < G * S) usum[sl] = s_ * (1.0f / XD);
     }
+    ET(13);
     __syncthreads();
+    ET(14);
     for (int idx = tid; idx < nimg * a.C; idx += HT) {
         const int img = idx / a.C, c = idx - img * a.C;
         float s = 0.f;
@@ -967,12 +994,20 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) a.attn_sum[b0 + img] = s;
         }
     }
+    ET(15);
     PROF_END(loop);
     if (tid == 0) { PROF_STORE(g_prof_head, 0, phaseA); PROF_STORE(g_prof_head, 1, mlp); PROF_STORE(g_prof_head, 2, loop); }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
     cluster_wait();       // the peer may still be arriving on this CTA's barriers until it has left phase A
+#ifdef SCOUTER_PROF
+    if (tid == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_prof_head[blockIdx.x * 32 + 29] = gt;
+        g_prof_head[blockIdx.x * 32 + 27] = (unsigned long long)(clock64() - prof_entry);
+    }
+#endif
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -998,7 +1033,7 @@ EncodeTiledFn encode_fn() {
 size_t layout(int G, int n, int S, int L, FusedArgs* out) {
     const int R = G * n;
     const int R8 = (R + 7) & ~7;
-    const int kbt = (n + 31) / 32, SPP = G == 2 ? 16 : 32;
+    const int kbt = (n + 31) / 32, SPP = G == 2 ? 17 : 33;
     const size_t a_stage = (size_t)R8 * 128;
     const size_t xt_kb = (size_t)G * 64 * 128;                               // k-block of the X^T tile: (64 G) rows x 32 tokens
     const size_t off_xt = 0, off_xl = off_xt + kbt * xt_kb + (G == 1 ? 8192 : 0);     // G = 1: the M = 128 MMAs read 64 rows past the tile

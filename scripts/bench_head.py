@@ -105,8 +105,11 @@ if a.prof:
     arr = np.array(buf[:], dtype=np.float64).reshape(256, 32)[:min(units, 256)]
     names = {0: "phaseA", 1: "mlp", 2: "loop", 3: "prodA.wait_empty", 4: "prodW.wait_done", 5: "iss0.wait_cempty", 6: "iss0.wait_opfull",
              7: "split0.wait_fullA", 8: "split0.wait_done", 9: "split0.wait_fullW", 10: "split0.tmem_st",
-             19: "own.stream_end", 24: "own.ho_regs", 25: "own.ho_xt", 20: "own.handover", 21: "own.to_tmem", 22: "own.mlp_done", 23: "own.keys_done", 12: "loop.dots_mma", 13: "loop.normalise", 14: "loop.update_mma", 15: "loop.update_operand", 16: "loop.gates_mma", 17: "loop.readout+cell"}
-    print("per-CTA clocks (mean / max):", {names.get(i, i): (int(arr[:, i].mean()), int(arr[:, i].max())) for i in range(27) if arr[:, i].any()})
+             19: "own.stream_end", 24: "own.ho_regs", 25: "own.ho_xt", 20: "own.handover", 21: "own.to_tmem", 22: "own.mlp_done", 23: "own.keys_done", 12: "end.loop_exit", 13: "end.logit_dots", 14: "end.sync", 15: "end.stores"}
+    act = arr[arr[:, 28] > 0]
+    print(f"globaltimer: first CTA entry -> last CTA exit {(act[:, 29].max() - act[:, 28].min()) / 1e3:.1f} us; entry skew {(act[:, 28].max() - act[:, 28].min()) / 1e3:.1f} us; "
+          f"exit skew {(act[:, 29].max() - act[:, 29].min()) / 1e3:.1f} us; per-CTA entry->exit clocks mean {act[:, 27].mean():.0f} max {act[:, 27].max():.0f}; entry->phaseA {act[:, 26].mean():.0f}")
+    print("per-CTA clocks (mean / max):", {names.get(i, i): (int(arr[:, i].mean()), int(arr[:, i].max())) for i in range(26) if arr[:, i].any()})
     tb = (C.c_ulonglong * (128 * 8))()
     lib.scouter_trace_read_head(tb, 128 * 8)
     full = np.array(tb[:], dtype=np.int64).reshape(128, 8)
