@@ -54,6 +54,10 @@ MODEL_CASES = {
     "cfg5_cub200x2_224": dict(args=dict(model="resnest26d", dataset="CUB200", channel=2048, num_classes=200,
                                         slots_per_class=2, power=2, to_k_layer=3, loss_status=1, lambda_value=1.0),
                               batch=2, cin=3, size=224),
+    # the README's resnest50d runs (README.md:189-228), dumped from the reference's own resnest50d
+    "f4_resnest50d_224": dict(args=dict(model="resnest50d", dataset="ImageNet", channel=2048, num_classes=10,
+                                        slots_per_class=1, power=2, to_k_layer=3, loss_status=1, lambda_value=1.0),
+                              batch=2, cin=3, size=224),
 }
 
 # Head-only cases (SlotAttention.forward on synthetic (B,n,64) features): shapes / edge cases.
@@ -106,8 +110,12 @@ def run_model_case(name, case, check):
     ref64 = refshim.reference_slot_model(**case["args"]).double()
     ref64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()})
     ref64.feature_size = fs
-    with torch.no_grad():
+    hs64 = ref64.slot.register_forward_hook(lambda m, i, o: feats.__setitem__("slot64", o[0].detach().clone()))
+    with torch.no_grad(), refshim.capture_sigmoid() as cap64:
         out64 = ref64(x.double())
+    hs64.remove()
+    attn64 = [o for o in cap64.outs if o.dim() == 3 and o.shape[1] == S][-1]      # the reference's own fp32-vs-fp64 attention floor
+    logits64 = feats["slot64"]
 
     a = case["args"]
     o = ob.slot_model_forward(a["model"], sd, x, num_classes=a["num_classes"], slots_per_class=a["slots_per_class"],
@@ -116,7 +124,7 @@ def run_model_case(name, case, check):
     ofeat = ob.backbone_features(a["model"], sd, x)
     diffs = dict(feat=rel_err(ofeat, feat), logits=rel_err(o["logits"], logits), log_probs=rel_err(o["log_probs"], out),
                  attn=float((o["attn"] - attn).abs().max()), loss=abs(float(o["loss"] - loss)),
-                 noise_floor_log_probs=rel_err(out, out64))
+                 noise_floor_log_probs=rel_err(out, out64), noise_floor_attn=float((attn.double() - attn64).abs().max()))
     print(f"[{name}] oracle-vs-reference {json.dumps(diffs)}")
     if check:
         assert diffs["feat"] < 1e-5 and diffs["logits"] < 1e-4 and diffs["attn"] < 1e-3, diffs
@@ -124,7 +132,8 @@ def run_model_case(name, case, check):
         os.path.join(GOLDEN_DIR, name + ".npz"),
         meta=json.dumps(dict(kind="model", args=a, batch=case["batch"], cin=case["cin"], size=case["size"], fs=fs,
                              oracle_vs_reference=diffs)),
-        log_probs=out.numpy(), log_probs64=out64.numpy(), logits=logits.numpy(), attn=attn.numpy(),
+        log_probs=out.numpy(), log_probs64=out64.numpy(), logits=logits.numpy(), logits64=logits64.numpy(), attn=attn.numpy(),
+        attn64=attn64.numpy(),
         losses=np.array([float(loss), float(nll), float(attn_loss)], dtype=np.float32),
         feat_sample=feat[:, ::64].numpy(), feat_abs_mean=np.float32(feat.abs().mean()),
         target=tgt.numpy())

@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) vis_maps_kernel(const float* __restrict__
     auto val = [&](int idx) {
         int c = idx / n, j = idx - c * n;
         float s = 0.f;
-        for (int m = 0; m < spc; ++m) s += attn[(long long)(c * spc + m) * n + j];
+        for (int m = 0; m < spc; ++m) s = __fadd_rn(s, attn[(long long)(c * spc + m) * n + j]);
         return s;
     };
     float mn = INFINITY, mx = -INFINITY;
@@ -481,7 +481,8 @@ __global__ void __launch_bounds__(256) vis_maps_kernel(const float* __restrict__
     mn = rmin[0]; mx = rmax[0];
     for (int i = 1; i < 8; ++i) { mn = fminf(mn, rmin[i]); mx = fmaxf(mx, rmax[i]); }
     for (int idx = tid; idx < C * n; idx += 256) {
-        float v = (val(idx) - mn) / (mx - mn) * 255.0f;
+        // byte work is held to bit-exactness: IEEE sub / div / mul in the reference's order, nothing contracted
+        const float v = __fmul_rn(__fdiv_rn(__fsub_rn(val(idx), mn), __fsub_rn(mx, mn)), 255.0f);
         maps[idx] = (uint8_t)v;  // numpy astype(uint8) truncates
     }
 }

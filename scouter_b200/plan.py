@@ -31,9 +31,12 @@ def _require_cuda(x: torch.Tensor, what: str):
 
 
 def _version_signature(module: nn.Module):
+    """Changes when a parameter / buffer is re-assigned or modified in place through autograd-visible ops.  In-place
+    writes through ``.data`` (``p.data.copy_()``, ``bn.running_mean.data...``) do NOT bump ``_version``: after those, call
+    ``SlotModel.invalidate()`` / ``BackboneRunner.invalidate()``."""
     sig = 0
     for t in list(module.parameters()) + list(module.buffers()):
-        sig = (sig * 1000003 + t._version + (t.data_ptr() & 0xFFFF)) & 0xFFFFFFFFFFFF
+        sig = (sig * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
     return sig
 
 
@@ -278,6 +281,10 @@ class CompiledProgram:
         self.program = program
         arr = (L.Op * len(program.ops))(*program.ops)
         h = C.c_void_p()
+        # plan_create reads the small stem filter banks back with a synchronous copy on the legacy stream: make sure the
+        # fold kernels that produced them (torch's current stream, possibly a non-blocking one) have finished
+        if torch.cuda.is_available() and any(t.is_cuda for t in program.keep):
+            torch.cuda.current_stream().synchronize()
         L.check(L.lib().scouter_plan_create(arr, len(program.ops), program.nbuf, math, C.byref(h)), "scouter_plan_create")
         self.handle = h
         self.shape = None
@@ -340,6 +347,11 @@ class BackboneRunner:
         self.math = math
         self.sig = None
         self.cp = None
+
+    def invalidate(self):
+        """Drop the folded / packed weights (rebuilt on the next call).  Needed after in-place parameter writes that
+        bypass the version counter (``.data``); ordinary assignments and in-place ops are detected automatically."""
+        self.cp, self.sig = None, None
 
     def _compile(self):
         from .backbone import Identical

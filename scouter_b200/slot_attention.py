@@ -56,6 +56,11 @@ class SlotAttention(nn.Module):
         self._desc = None
 
     # -- parameter pack -----------------------------------------------------------------------
+    def invalidate(self):
+        """Drop the packed parameter block (re-packed on the next forward); required after ``.data`` writes, which do not
+        bump the version counter that ``desc_and_pack`` watches."""
+        self._packed, self._packed_sig, self._desc = None, None, None
+
     def _linears(self):
         return [m for m in self.to_k if isinstance(m, nn.Linear)]
 

@@ -75,6 +75,7 @@ class SlotModel(nn.Module):
         self.num_classes = args.num_classes
         self.math = None              # None -> scouter_b200.default_math()
         self.use_cuda_graph = False
+        self.check_targets = True     # validate labels like F.nll_loss does (one device sync per call with targets)
         self.keep_attn = False        # retain the final attention maps in .last_attn (first-class output)
         self.last_attn = None
         self.last_logits = None
@@ -104,6 +105,25 @@ class SlotModel(nn.Module):
             self.dfs_freeze_bnorm(child)
 
     # -- compiled state -------------------------------------------------------------------------
+    def invalidate(self):
+        """Forget every derived copy of the parameters -- BN-folded / packed conv weights, the bf16 split of
+        ``conv1x1.weight``, the packed xSlot block, captured CUDA graphs -- so that the next forward rebuilds them from
+        the live tensors.  Parameter re-assignment and autograd-visible in-place ops are detected automatically
+        (``_version`` + ``data_ptr``); writes through ``.data`` (``p.data.mul_()``, ``bn.running_mean.data.copy_()``) are
+        not, and REQUIRE this call: without it the model keeps running on stale folded weights."""
+        self._prog, self._sig = None, None
+        self._states.clear()
+        self._conv_w_split_key = None
+        if self.use_slot:
+            self.slot.invalidate()
+
+    refresh_weights = invalidate
+
+    def release_states(self):
+        """Free the per-input-shape device state (plan arenas of ~10 MB per image at 224^2, head workspaces, captured
+        graphs).  States are otherwise kept for the 4 most recent (shape, device) pairs."""
+        self._states.clear()
+
     def _math(self):
         from . import default_math
         return default_math() if self.math is None else self.math
@@ -230,6 +250,9 @@ class SlotModel(nn.Module):
             self._last_fhw = (st.fh, st.fw)
             if target is not None:
                 target = target.to(device=x.device, dtype=torch.int64).contiguous()
+                if self.check_targets and target.numel() and (int(target.min()) < 0 or int(target.max()) >= self.num_classes):
+                    # F.nll_loss (slot_model.py:122) raises for a label outside [0, C); the finalize kernel would drop it
+                    raise IndexError(f"SlotModel: target {int(target.min())}..{int(target.max())} is out of bounds for {self.num_classes} classes")
             if self.use_cuda_graph and target is None:
                 self._replay(st, x)
             else:

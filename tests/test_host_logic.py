@@ -152,3 +152,29 @@ def test_dgrad_weights_turn_the_data_gradient_into_a_forward_conv(cin, cout, k, 
     assert wd.shape == (cin, k, k, cout // groups)
     got = torch.nn.functional.conv2d(dy, wd.permute(0, 3, 1, 2), None, 1, k - 1 - pad, 1, groups)
     assert got.shape == dx.shape and torch.allclose(got, dx, rtol=1e-12, atol=1e-12)
+
+
+def test_invalidate_covers_data_writes():
+    """in-place writes through ``.data`` do not bump ``_version`` -- the signature cannot see them, so an explicit
+    ``invalidate()`` must drop every derived copy (program, per-shape states, packed head block, bf16 weight split)."""
+    import torch
+    import scouter_b200 as sb
+    from scouter_b200.plan import _version_signature
+    from scouter_b200.synth import make_args
+    m = sb.SlotModel(make_args())
+    s0 = _version_signature(m.backbone)
+    with torch.no_grad():
+        m.backbone.layer1[0].conv1.weight.data.mul_(2.0)
+    assert _version_signature(m.backbone) == s0              # the documented blind spot
+    with torch.no_grad():
+        m.backbone.layer1[0].conv1.weight.mul_(2.0)
+    assert _version_signature(m.backbone) != s0              # ordinary in-place ops are seen
+    m._prog, m._sig, m._conv_w_split_key = ("stale",), 123, ("stale",)
+    m._states["k"] = object()
+    m.slot._packed, m.slot._packed_sig = object(), ("stale",)
+    m.invalidate()
+    assert m._prog is None and m._sig is None and not m._states and m._conv_w_split_key is None
+    assert m.slot._packed is None and m.slot._packed_sig is None
+    m._states["k"] = object()
+    m.release_states()
+    assert not m._states
