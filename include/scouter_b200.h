@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SCOUTER_ABI_VERSION 2
+#define SCOUTER_ABI_VERSION 3
 
 #define SCOUTER_OK 0
 #define SCOUTER_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, ...) */
@@ -241,6 +241,10 @@ int scouter_plan_launch_count(const scouter_plan_t* plan);
 int scouter_conv_forward(const scouter_op_t* op, const float* in, const float* res, float* out, int batch, int h, int w,
                          int math, scouter_stream_t stream);
 int scouter_conv_path(const scouter_op_t* op, int batch, int h, int w, int math);
+/* The network's first conv (SCOUTER_OP_STEM_CONV geometry: NCHW input with 1..4 channels -> NHWC) outside a plan; used
+ * by the train-mode forward, where BatchNorm is not folded (resnet.py:401, slot_model.py:23-24). */
+int scouter_stem_conv_forward(const scouter_op_t* op, const float* in_nchw, float* out, int batch, int h, int w,
+                              scouter_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * f2  input pipeline boundary (engine.py:25, dataset/transform_func.py:52-67 ToTensor, :87-94 Normalize,
@@ -251,6 +255,112 @@ int scouter_conv_path(const scouter_op_t* op, int batch, int h, int w, int math)
  * ---------------------------------------------------------------------------------------------- */
 int scouter_preprocess_u8(const uint8_t* img_nhwc, int batch, int h, int w, int c, const double* mean_host,
                           const double* std_host, float* out_nchw, scouter_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * f1  the training step (engine.py:28-35 `loss.backward(); optimizer.step()`, train.py:140-148): train-mode
+ *     BatchNorm, the backward of every op on the path, AdamW.  Each entry is one stream-ordered launch group over
+ *     caller-owned NHWC fp32 buffers; the step itself (op order, buffer lifetimes, gradient accumulation flags) is host
+ *     logic in scouter_b200/train.py, driven by the same op program as the forward.  These are the correctness-first
+ *     CUDA-core kernels of csrc/draft/ (validated on B200 against the reference's loss.backward(), memcheck + racecheck
+ *     clean); the tensor-core versions of the conv gradients replace them behind the same entries.
+ *     Gradient outputs marked "accumulated" must be zeroed (or hold a running sum) on entry.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct scouter_bn_train_args {   /* nn.BatchNorm2d in train mode (eps 1e-5, momentum 0.1): timm/models/resnet.py:401-420 */
+    long long M; int C;                  /* x viewed as (M = B*H*W, C); C % 4 == 0 */
+    const float* x;
+    double* sums;                        /* (C, 2) workspace, zeroed by the call */
+    const float *gamma, *beta;
+    float *running_mean, *running_var;   /* updated in place (unbiased variance, momentum) */
+    float *scale, *shift;                /* (C) workspace */
+    float *save_mean, *save_rstd;        /* (C) batch statistics kept for the backward, or NULL */
+    float eps, momentum;
+    const float* residual;               /* (M, C) added before the ReLU, or NULL */
+    float* y;                            /* (M, C); may alias x */
+    int relu;
+} scouter_bn_train_args_t;
+int scouter_train_bn_forward(const scouter_bn_train_args_t* a, scouter_stream_t stream);
+
+typedef struct scouter_bn_bwd_args {     /* backward of out = [relu](bn(x) [+ residual]) */
+    long long M; int C;
+    const float *x, *out, *d_out;        /* conv output, block output (ReLU mask; may be NULL when !relu), its gradient */
+    const float *gamma, *save_mean, *save_rstd;
+    double* sums;                        /* (C, 2) workspace, zeroed by the call */
+    float *d_gamma, *d_beta;             /* (C) accumulated */
+    float* coef;                         /* (C, 3) workspace */
+    float* dx;                           /* (M, C); may alias d_out */
+    float* d_residual;                   /* (M, C) or NULL: receives the masked gradient */
+    int relu;
+} scouter_bn_bwd_args_t;
+int scouter_train_bn_backward(const scouter_bn_bwd_args_t* a, scouter_stream_t stream);
+
+typedef struct scouter_wgrad_args {      /* nn.Conv2d weight / bias gradient; dW in this library's OHWI layout */
+    int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad, groups;
+    const float *x, *dy;                 /* (B,H,W,Cin), (B,Ho,Wo,Cout) */
+    float* dw;                           /* (Cout,k,k,Cin/groups) accumulated */
+    float* db;                           /* (Cout) accumulated, or NULL */
+} scouter_wgrad_args_t;
+int scouter_train_conv_wgrad(const scouter_wgrad_args_t* a, scouter_stream_t stream);
+
+typedef struct scouter_dgrad_args {      /* nn.Conv2d data gradient, any stride (gather form) */
+    int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad, groups;
+    const float *dy, *w;                 /* (B,Ho,Wo,Cout), (Cout,k,k,Cin/groups) */
+    float* dx;                           /* (B,H,W,Cin) overwritten */
+} scouter_dgrad_args_t;
+int scouter_train_conv_dgrad(const scouter_dgrad_args_t* a, scouter_stream_t stream);
+
+typedef struct scouter_pool_bwd_args {   /* kind 0: MaxPool2d(3,2,1) resnet.py:420; 1: AvgPool2d(2,2,ceil,count_include_pad=False) */
+    int B, H, W, C, Ho, Wo;              /*      resnet.py:300; 2: AvgPool2d(3,2,1) resnest.py:101 */
+    const float* x;                      /* forward input (kind 0 only) */
+    const float* dy; float* dx;
+} scouter_pool_bwd_args_t;
+int scouter_train_pool_backward(const scouter_pool_bwd_args_t* a, int kind, scouter_stream_t stream);
+/* forward of the same three pools outside a plan (the train-mode forward keeps every buffer alive for the backward) */
+int scouter_pool_forward(int kind, const float* in, float* out, int batch, int h, int w, int c, scouter_stream_t stream);
+
+typedef struct scouter_splat_bwd_args {  /* split attention, split_attn.py:62-79 (radix 2) */
+    int B, HW, C;
+    const float *x2, *d_out, *att;       /* (B,HW,2C), (B,HW,C), softmax over the radix (B,2,C) */
+    float *d_att, *d_logit;              /* stage 0 outputs (B,2,C) */
+    const float* d_gap;                  /* stage 1 input (B,C) */
+    float* d_x2;                         /* stage 1 output (B,HW,2C) */
+} scouter_splat_bwd_args_t;
+int scouter_train_splat_backward(const scouter_splat_bwd_args_t* a, int stage, scouter_stream_t stream);
+/* forward halves outside a plan: gap = mean_hw(x_0 + x_1) (scratch: scouter_splat_gap_scratch_floats floats);
+ * out = x_0 * a_0 + x_1 * a_1 with a = softmax over the radix pair of `logits` (B, 2C) */
+size_t scouter_splat_gap_scratch_floats(int batch, int hw, int c);
+int scouter_splat_gap_forward(const float* in, float* scratch, float* gap, int batch, int hw, int c, scouter_stream_t stream);
+int scouter_splat_apply_forward(const float* in, const float* logits, float* out, int batch, int h, int w, int c,
+                                scouter_stream_t stream);
+
+typedef struct scouter_head_bwd_args {   /* backward of slot_model.py:108-116 + slot_attention.py:44-96 (recomputes the forward) */
+    int B, n, ch, S, C, spc, L, iters, loss_status;
+    const float* feat;                   /* (B, n, ch) token-major backbone output */
+    const float *conv_w, *conv_b, *pe;   /* (64, ch), (64), (n, 64) */
+    const float *to_k_w[SCOUTER_MAX_TO_K_LAYERS], *to_k_b[SCOUTER_MAX_TO_K_LAYERS];
+    const float *w_ih, *w_hh, *b_ih, *b_hh;
+    const float* slots0;                 /* (S, 64) */
+    const float* g_logits;               /* (B, C) gradient at the logits */
+    const float* attn_coef;              /* device scalar: g_attn_loss * power * mean(attn)^(power-1) / (B*S*n) */
+    float* d_feat;                       /* (B, n, ch) or NULL */
+    float* d_pre;                        /* (B, n, 64) or NULL */
+    float *g_conv_w, *g_conv_b, *g_to_k_w[SCOUTER_MAX_TO_K_LAYERS], *g_to_k_b[SCOUTER_MAX_TO_K_LAYERS];
+    float *g_w_ih, *g_w_hh, *g_b_ih, *g_b_hh, *g_slots0;     /* accumulated */
+    float* scratch;                      /* B * scouter_train_head_backward_scratch_floats(...) floats */
+    size_t scratch_per_image;
+} scouter_head_bwd_args_t;
+size_t scouter_train_head_backward_scratch_floats(int n, int s, int to_k_layers, int iters);
+int scouter_train_head_backward(const scouter_head_bwd_args_t* a, scouter_stream_t stream);
+
+typedef struct scouter_adamw_args {      /* torch.optim.AdamW single-tensor step (train.py:146, engine.py:34); scalars from the host */
+    float decay;                         /* 1 - lr * weight_decay */
+    float one_minus_beta1, beta2, one_minus_beta2, eps;
+    float step_size;                     /* lr / (1 - beta1^t) */
+    float bias_correction2_sqrt;         /* sqrt(1 - beta2^t) */
+    size_t n;
+    float* p; const float* g; float *m, *v;
+} scouter_adamw_args_t;
+int scouter_train_adamw_step(const scouter_adamw_args_t* a, scouter_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a1  SlotModel.forward from HOST buffers in one call (sloter/slot_model.py:105-127 as driven by

@@ -13,7 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SCOUTER_B200_LIB: load another build of the same library (debug variants built by scripts/, e.g. -DSCOUTER_PROF)
 LIB_PATH = os.environ.get("SCOUTER_B200_LIB") or os.path.join(_HERE, "libscouter_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "head_fused.cu", "stem_ts.cu", "vis.cu", "umma_conv.cu", "umma_halo.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "aux_kernels.cu", "xslot.cu", "xslot_fast.cu", "head_fused.cu", "stem_ts.cu", "vis.cu", "umma_conv.cu", "umma_halo.cu",
+           # row f1 (training step): C-ABI glue + the kernel bodies of csrc/draft/
+           "train.cu", "draft/head_backward.cu", "draft/adamw.cu", "draft/bn_train.cu", "draft/pool_splat_bwd.cu", "draft/conv_wgrad.cu"]
 
 OK = 0
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
@@ -108,7 +110,75 @@ SIGNATURES = {
     "scouter_plan_launch_count": (C.c_int, [C.c_void_p]),
     "scouter_preprocess_u8": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _fp, _fp]),
     "scouter_forward_host": (C.c_int, [C.POINTER(ForwardHostArgs)]),
+    "scouter_stem_conv_forward": (C.c_int, [C.POINTER(Op), _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    # row f1
+    "scouter_train_bn_forward": (C.c_int, [C.c_void_p, _fp]),
+    "scouter_train_bn_backward": (C.c_int, [C.c_void_p, _fp]),
+    "scouter_train_conv_wgrad": (C.c_int, [C.c_void_p, _fp]),
+    "scouter_train_conv_dgrad": (C.c_int, [C.c_void_p, _fp]),
+    "scouter_train_pool_backward": (C.c_int, [C.c_void_p, C.c_int, _fp]),
+    "scouter_pool_forward": (C.c_int, [C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "scouter_train_splat_backward": (C.c_int, [C.c_void_p, C.c_int, _fp]),
+    "scouter_splat_gap_scratch_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "scouter_splat_gap_forward": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    "scouter_splat_apply_forward": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "scouter_train_head_backward_scratch_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "scouter_train_head_backward": (C.c_int, [C.c_void_p, _fp]),
+    "scouter_train_adamw_step": (C.c_int, [C.c_void_p, _fp]),
 }
+
+
+# ---- row f1: argument blocks of the training entries (mirror include/scouter_b200.h field by field) -----------------
+_f32p, _f64p = C.c_void_p, C.c_void_p
+
+
+class BnTrainArgs(C.Structure):
+    _fields_ = [("M", C.c_longlong), ("C", C.c_int), ("x", _fp), ("sums", _fp), ("gamma", _fp), ("beta", _fp),
+                ("running_mean", _fp), ("running_var", _fp), ("scale", _fp), ("shift", _fp), ("save_mean", _fp), ("save_rstd", _fp),
+                ("eps", C.c_float), ("momentum", C.c_float), ("residual", _fp), ("y", _fp), ("relu", C.c_int)]
+
+
+class BnBwdArgs(C.Structure):
+    _fields_ = [("M", C.c_longlong), ("C", C.c_int), ("x", _fp), ("out", _fp), ("d_out", _fp), ("gamma", _fp), ("save_mean", _fp),
+                ("save_rstd", _fp), ("sums", _fp), ("d_gamma", _fp), ("d_beta", _fp), ("coef", _fp), ("dx", _fp), ("d_residual", _fp),
+                ("relu", C.c_int)]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("B", "H", "W", "Cin", "Ho", "Wo", "Cout", "k", "stride", "pad", "groups")] + \
+               [("x", _fp), ("dy", _fp), ("dw", _fp), ("db", _fp)]
+
+
+class DgradArgs(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("B", "H", "W", "Cin", "Ho", "Wo", "Cout", "k", "stride", "pad", "groups")] + \
+               [("dy", _fp), ("w", _fp), ("dx", _fp)]
+
+
+class PoolBwdArgs(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("B", "H", "W", "C", "Ho", "Wo")] + [("x", _fp), ("dy", _fp), ("dx", _fp)]
+
+
+class SplatBwdArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("HW", C.c_int), ("C", C.c_int), ("x2", _fp), ("d_out", _fp), ("att", _fp), ("d_att", _fp),
+                ("d_logit", _fp), ("d_gap", _fp), ("d_x2", _fp)]
+
+
+class HeadBwdArgs(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("B", "n", "ch", "S", "C", "spc", "L", "iters", "loss_status")] + \
+               [("feat", _fp), ("conv_w", _fp), ("conv_b", _fp), ("pe", _fp),
+                ("to_k_w", _fp * MAX_TO_K_LAYERS), ("to_k_b", _fp * MAX_TO_K_LAYERS),
+                ("w_ih", _fp), ("w_hh", _fp), ("b_ih", _fp), ("b_hh", _fp), ("slots0", _fp), ("g_logits", _fp), ("attn_coef", _fp),
+                ("d_feat", _fp), ("d_pre", _fp), ("g_conv_w", _fp), ("g_conv_b", _fp),
+                ("g_to_k_w", _fp * MAX_TO_K_LAYERS), ("g_to_k_b", _fp * MAX_TO_K_LAYERS),
+                ("g_w_ih", _fp), ("g_w_hh", _fp), ("g_b_ih", _fp), ("g_b_hh", _fp), ("g_slots0", _fp),
+                ("scratch", _fp), ("scratch_per_image", C.c_size_t)]
+
+
+class AdamWArgs(C.Structure):
+    _fields_ = [("decay", C.c_float), ("one_minus_beta1", C.c_float), ("beta2", C.c_float), ("one_minus_beta2", C.c_float),
+                ("eps", C.c_float), ("step_size", C.c_float), ("bias_correction2_sqrt", C.c_float), ("n", C.c_size_t),
+                ("p", _fp), ("g", _fp), ("m", _fp), ("v", _fp)]
+
 
 _lib = None
 

@@ -469,6 +469,19 @@ extern "C" int scouter_conv_forward(const scouter_op_t* op, const float* in, con
     return launch_conv_simt(a, (cudaStream_t)stream);
 }
 
+// The network's first conv outside a plan: NCHW input (1..4 channels) -> NHWC output, CUDA-core kernel (the train-mode
+// forward of scouter_b200/train.py; in train mode BatchNorm is a separate op, so no bias / ReLU is fused here).
+extern "C" int scouter_stem_conv_forward(const scouter_op_t* op, const float* in_nchw, float* out, int batch, int h, int w,
+                                         scouter_stream_t stream) {
+    SC_CHECK_ARG(op && in_nchw && out && op->w && batch > 0 && h > 0 && w > 0, SCOUTER_E_INVALID, "stem_conv_forward: bad arguments");
+    SC_CHECK_ARG(op->kh == op->kw && op->groups == 1 && op->stride >= 1, SCOUTER_E_UNSUPPORTED, "stem_conv_forward: square, ungrouped kernels only");
+    const int Ho = (h + 2 * op->pad - op->kh) / op->stride + 1, Wo = (w + 2 * op->pad - op->kw) / op->stride + 1;
+    SC_CHECK_ARG(Ho > 0 && Wo > 0, SCOUTER_E_INVALID, "stem_conv_forward: empty output");
+    StemArgs a{in_nchw, op->w, op->b, out, batch, h, w, op->cin, Ho, Wo, op->cout, op->kh, op->stride, op->pad,
+               (op->flags & SCOUTER_F_RELU) ? 1 : 0, 0, nullptr, nullptr, 0};
+    return launch_stem_conv(a, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // f2: input pipeline boundary
 // ------------------------------------------------------------------------------------------------

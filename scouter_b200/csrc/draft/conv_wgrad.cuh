@@ -41,7 +41,7 @@ WG_HD void conv_wgrad_element(const WgradArgs& a, long long e, long long m0, lon
     const int r = (int)(t % a.k);
     const int o = (int)(t / a.k);
     const int ci = (o / cout_g) * cin_g + c;
-    float acc = 0.f;
+    double acc = 0.0;      // K = B*Ho*Wo reaches 10^5..10^6 terms: a sequential fp32 sum would carry ~1e-3 of rounding noise
     for (long long m = m0; m < m1; ++m) {
         const int xo = (int)(m % a.Wo);
         const long long q = m / a.Wo;
@@ -49,15 +49,15 @@ WG_HD void conv_wgrad_element(const WgradArgs& a, long long e, long long m0, lon
         const int b = (int)(q / a.Ho);
         const int yi = yo * a.stride + r - a.pad, xi = xo * a.stride + s - a.pad;
         if (yi < 0 || yi >= a.H || xi < 0 || xi >= a.W) continue;
-        acc = fmaf(a.dy[(size_t)m * a.Cout + o], a.x[(((size_t)b * a.H + yi) * a.W + xi) * a.Cin + ci], acc);
+        acc += (double)a.dy[(size_t)m * a.Cout + o] * (double)a.x[(((size_t)b * a.H + yi) * a.W + xi) * a.Cin + ci];
     }
-    WG_ATOMIC_ADD(a.dw + e, acc);
+    WG_ATOMIC_ADD(a.dw + e, (float)acc);
 }
 
 WG_HD void conv_bgrad_element(const WgradArgs& a, int o, long long m0, long long m1) {
-    float acc = 0.f;
-    for (long long m = m0; m < m1; ++m) acc += a.dy[(size_t)m * a.Cout + o];
-    WG_ATOMIC_ADD(a.db + o, acc);
+    double acc = 0.0;
+    for (long long m = m0; m < m1; ++m) acc += (double)a.dy[(size_t)m * a.Cout + o];
+    WG_ATOMIC_ADD(a.db + o, (float)acc);
 }
 
 // Data gradient for ANY stride as a gather (thread = one input element): the strided convs of resnet18 (3x3 s2 and the

@@ -9,7 +9,9 @@ lambda_value``), same ``state_dict`` keys and the same return
 Differences, all deliberate:
 * ``feature_size`` is derived from the real feature map instead of being hard-wired to 9 (the reference
   crashes on anything but 260x260 inputs); the attribute is updated after each forward.
-* eval-mode forward only (train-mode BatchNorm / backward = SURVEY.md row f1).
+* ``.train()`` mode runs the training step of ``scouter_b200/train.py`` (train-mode BatchNorm, backward through the C ABI,
+  exposed to autograd as one Function: ``loss.backward()`` / DDP / ``torch.optim`` work on top); the no-slot stage-1
+  classifier cannot be trained here.
 * ``pre_trained=True`` is refused (it downloads weights); ``use_pre`` loads the stage-1 checkpoint exactly
   like the reference (:26-33).
 """
@@ -240,8 +242,16 @@ class SlotModel(nn.Module):
     # -- forward --------------------------------------------------------------------------------
     def forward(self, x, target=None):
         _require_cuda(x, "SlotModel")
-        _check_inference(self, "SlotModel")
         x = x.contiguous()
+        if self.training:
+            # row f1: train-mode BatchNorm + backward through the C ABI (scouter_b200/train.py); engine.py:28-35
+            from .train import train_forward
+            if target is not None:
+                target = target.to(device=x.device, dtype=torch.int64).contiguous()
+                if self.check_targets and target.numel() and (int(target.min()) < 0 or int(target.max()) >= self.num_classes):
+                    raise IndexError(f"SlotModel: target {int(target.min())}..{int(target.max())} is out of bounds for {self.num_classes} classes")
+            with torch.cuda.device(x.device):
+                return train_forward(self, x, target)
         if not self.use_slot:
             return self._forward_no_slot(x, target)
         with torch.cuda.device(x.device):

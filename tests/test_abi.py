@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = L.lib()
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.scouter_abi_version() == 2
+    assert lib.scouter_abi_version() == 3
 
 
 def test_argument_errors_without_gpu():

@@ -266,10 +266,11 @@ def test_cuda_graph_follows_head_parameter_updates(dev):
     assert torch.equal(g1, e1)
 
 
-def test_training_mode_raises_not_falls_back(dev):
-    m = sb.SlotModel(make_args()).to(dev).train()
+def test_training_without_slot_head_raises_not_falls_back(dev):
+    """The xSlot model trains on the device (tests/test_gpu_train.py); the no-slot stage-1 classifier does not -- and says so."""
+    m = sb.SlotModel(make_args(use_slot=False)).to(dev).train()
     with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 3, 224, 224, device=dev))
+        m(torch.zeros(2, 3, 224, 224, device=dev), torch.zeros(2, dtype=torch.int64, device=dev))
 
 
 @pytest.mark.parametrize("name,batch", [("cfg2_resnest26d_pos_224", 70), ("cfg3_resnest26d_neg_224", 256),
