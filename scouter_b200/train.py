@@ -28,7 +28,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as L
-from .plan import backward_schedule, lower_backbone_train, split_weights_bf16
+from .plan import backward_schedule, dgrad_weights, lower_backbone_train, split_weights_bf16
 
 POOL_KIND = {"maxpool": 0, "avgpool2": 1, "avgpool3": 2}
 
@@ -231,9 +231,20 @@ class TrainEngine:
                     grads[e["key"] + ".bias"] = db
                 if e["need_dx"]:
                     dx = torch.empty_like(x)
-                    da = L.DgradArgs(B=B, H=H, W=W, Cin=Cin, Ho=Ho, Wo=Wo, Cout=Cout, k=w.shape[1], stride=e["stride"], pad=e["pad"],
-                                     groups=e["groups"], dy=dy.data_ptr(), w=w.data_ptr(), dx=dx.data_ptr())
-                    L.check(lib.scouter_train_conv_dgrad(C.byref(da), st), "scouter_train_conv_dgrad")
+                    kk = w.shape[1]
+                    if e["stride"] == 1 and (Cout // e["groups"]) % 16 == 0:
+                        # the data gradient of a stride-1 conv IS a conv (taps flipped, channels swapped inside each group,
+                        # padding k-1-pad): it runs on the forward kernels -- tcgen05 in the tensor-core mode
+                        math_mode = m._math()
+                        wt = dgrad_weights(w, e["groups"])
+                        wt2 = split_weights_bf16(wt) if math_mode == L.MATH_TC else None
+                        o = L.Op(kind=L.OP_CONV, src=0, src2=-1, dst=1, cin=Cout, cout=Cin, kh=kk, kw=kk, stride=1, pad=kk - 1 - e["pad"],
+                                 groups=e["groups"], flags=0, mid=0, reserved=0, w=wt.data_ptr(), b=0, w2=_p(wt2), b2=0)
+                        L.check(lib.scouter_conv_forward(C.byref(o), dy.data_ptr(), 0, dx.data_ptr(), B, Ho, Wo, math_mode, st), "scouter_conv_forward (dgrad)")
+                    else:
+                        da = L.DgradArgs(B=B, H=H, W=W, Cin=Cin, Ho=Ho, Wo=Wo, Cout=Cout, k=kk, stride=e["stride"], pad=e["pad"],
+                                         groups=e["groups"], dy=dy.data_ptr(), w=w.data_ptr(), dx=dx.data_ptr())
+                        L.check(lib.scouter_train_conv_dgrad(C.byref(da), st), "scouter_train_conv_dgrad")
                     put(e, e["src"], dx)
             elif k == "bn":
                 bn = self._mod(e["key"])
