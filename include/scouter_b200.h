@@ -194,6 +194,9 @@ enum scouter_op_kind {
 #define SCOUTER_F_CEIL_MODE 4
 #define SCOUTER_F_COUNT_INCLUDE_PAD 8
 #define SCOUTER_F_AVD_POOL 16         /* SPLAT_APPLY: follow with AvgPool2d(3, 2, padding=1) */
+#define SCOUTER_F_TF32_1PASS 32      /* per-stage precision policy: in a SCOUTER_MATH_TC plan run THIS op as SCOUTER_MATH_TC_FAST
+                                        would (single tf32 pass, tf32-rounded output; the caller passes tf32-rounded weights and
+                                        no w2).  Ignored by the other math modes. */
 
 typedef struct scouter_op {
     int32_t kind;

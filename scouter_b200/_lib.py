@@ -24,7 +24,7 @@ MAX_TO_K_LAYERS = 8
 
 OP_STEM_CONV, OP_CONV, OP_MAXPOOL, OP_AVGPOOL = 1, 2, 3, 4
 OP_SPLAT_GAP, OP_SPLAT_APPLY, OP_GAP, OP_TO_NCHW = 5, 7, 8, 9
-F_RELU, F_RESIDUAL, F_CEIL_MODE, F_COUNT_INCLUDE_PAD, F_AVD_POOL = 1, 2, 4, 8, 16
+F_RELU, F_RESIDUAL, F_CEIL_MODE, F_COUNT_INCLUDE_PAD, F_AVD_POOL, F_TF32_1PASS = 1, 2, 4, 8, 16, 32
 
 _fp = C.c_void_p  # device pointers travel as integers
 

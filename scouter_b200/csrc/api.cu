@@ -249,8 +249,6 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
     SC_CHECK_ARG(arena_bytes >= plan->arena_bytes, SCOUTER_E_INVALID, "plan_run: arena of %zu bytes, need %zu", arena_bytes, plan->arena_bytes);
     SC_CHECK_ARG(((uintptr_t)arena & 1023) == 0, SCOUTER_E_INVALID, "plan_run: arena is not 1024-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    const int rnd = plan->math == SCOUTER_MATH_TC_FAST ? 1 : 0;  // tf32-representable activations for the 1-pass tcgen05 convs
-    const int split = plan->math == SCOUTER_MATH_TC ? 1 : 0;     // error-compensated 3xTF32
     char* base = (char*)arena;
     auto ptr = [&](int id) -> float* { return id == 0 ? const_cast<float*>(input_nchw) : (float*)(base + plan->bufs[id].offset); };
     for (size_t i = 0; i < plan->ops.size(); ++i) {
@@ -258,6 +256,10 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
         const Buf& sb = plan->bufs[o.src];
         const Buf& db = plan->bufs[o.dst];
         int rc = 0;
+        // per-op precision: SCOUTER_F_TF32_1PASS turns one op of a compensated plan into its single-pass form
+        const bool fast = plan->math == SCOUTER_MATH_TC_FAST || (plan->math == SCOUTER_MATH_TC && (o.flags & SCOUTER_F_TF32_1PASS));
+        const int rnd = fast ? 1 : 0;                                       // tf32-representable activations for the 1-pass tcgen05 convs
+        const int split = (plan->math == SCOUTER_MATH_TC && !fast) ? 1 : 0; // error-compensated 3xTF32
         switch (o.kind) {
             case SCOUTER_OP_STEM_CONV: {
                 SC_CHECK_ARG(o.kh == o.kw && o.groups == 1, SCOUTER_E_UNSUPPORTED, "stem conv: square, ungrouped kernels only");

@@ -41,26 +41,46 @@ struct BnTrainArgs {
     int relu;
 };
 
+// On the GPU the lanes of a CTA that hold the same channel quad are merged in shared memory first (fixed order), so a CTA
+// issues ONE fp64 atomic pair per channel instead of one per thread (592 CTAs x 256 threads x 8 atomics on 2*C addresses
+// was 140 us per launch).  `red` = (nthreads, 8) doubles of shared memory, NULL in the host emulation (no merge needed).
+// Returns whether this thread adds `v` to the global sums.  All threads of the CTA must call it (it synchronises).
+BN_HD bool bn_cta_merge(double (*red)[8], int tid, int qpr, int lanes, double v[8]) {
+#ifdef __CUDACC__
+    if (red && lanes > 1) {
+        for (int k = 0; k < 8; ++k) red[tid][k] = v[k];
+        __syncthreads();
+        if (tid < qpr)
+            for (int l = 1; l < lanes; ++l)
+                for (int k = 0; k < 8; ++k) v[k] += red[tid + l * qpr][k];
+        __syncthreads();
+        return tid < qpr;
+    }
+#endif
+    (void)red; (void)tid; (void)qpr; (void)lanes; (void)v;
+    return true;
+}
+
 // CTA `cta` of `n_ctas` owns a contiguous slab of rows; inside it thread `tid` owns channel quad tid % qpr and the rows
 // r0 + tid / qpr, + lanes, + 2*lanes ... (qpr = quads per row handled at once = min(C/4, nthreads)).
-BN_HD void bn_stats_partial(const BnTrainArgs& a, int cta, int n_ctas, int tid, int nthreads) {
+BN_HD void bn_stats_partial(const BnTrainArgs& a, int cta, int n_ctas, int tid, int nthreads, double (*red)[8] = nullptr) {
     const int quads = a.C / 4;
     const int qpr = quads < nthreads ? quads : nthreads;
     const int lanes = nthreads / qpr;
-    if (tid >= lanes * qpr) return;
     const long long per = (a.M + n_ctas - 1) / n_ctas;
     const long long r0 = (long long)cta * per, r1 = r0 + per < a.M ? r0 + per : a.M;
     const int lane = tid / qpr;
-    for (int q = tid % qpr; q < quads; q += qpr) {       // more than nthreads quads per row: loop
-        double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-        for (long long r = r0 + lane; r < r1; r += lanes) {
-            const float* p = a.x + r * a.C + 4 * q;
-            for (int k = 0; k < 4; ++k) { const double v = p[k]; s[k] += v; ss[k] += v * v; }
-        }
-        for (int k = 0; k < 4; ++k) {
-            BN_ATOMIC_ADD(a.sums + 2 * (4 * q + k), s[k]);
-            BN_ATOMIC_ADD(a.sums + 2 * (4 * q + k) + 1, ss[k]);
-        }
+    for (int q0 = 0; q0 < quads; q0 += qpr) {            // more than nthreads quads per row: loop (uniform trip count)
+        const int q = q0 + tid % qpr;
+        const bool active = tid < lanes * qpr && q < quads;
+        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // [sum, sum of squares] x 4 channels
+        if (active)
+            for (long long r = r0 + lane; r < r1; r += lanes) {
+                const float* p = a.x + r * a.C + 4 * q;
+                for (int k = 0; k < 4; ++k) { const double x = p[k]; v[2 * k] += x; v[2 * k + 1] += x * x; }
+            }
+        if (bn_cta_merge(red, tid, qpr, lanes, v) && active)
+            for (int k = 0; k < 8; ++k) BN_ATOMIC_ADD(a.sums + 2 * (4 * q) + k, v[k]);
     }
 }
 
@@ -113,29 +133,29 @@ BN_HD float bn_bwd_dy(const BnBwdArgs& a, long long i) {
     return (a.relu && !(a.out[i] > 0.f)) ? 0.f : g;
 }
 
-BN_HD void bn_bwd_stats_partial(const BnBwdArgs& a, int cta, int n_ctas, int tid, int nthreads) {
+BN_HD void bn_bwd_stats_partial(const BnBwdArgs& a, int cta, int n_ctas, int tid, int nthreads, double (*red)[8] = nullptr) {
     const int quads = a.C / 4;
     const int qpr = quads < nthreads ? quads : nthreads;
     const int lanes = nthreads / qpr;
-    if (tid >= lanes * qpr) return;
     const long long per = (a.M + n_ctas - 1) / n_ctas;
     const long long r0 = (long long)cta * per, r1 = r0 + per < a.M ? r0 + per : a.M;
     const int lane = tid / qpr;
-    for (int q = tid % qpr; q < quads; q += qpr) {
-        double s[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0};
-        for (long long r = r0 + lane; r < r1; r += lanes) {
-            for (int k = 0; k < 4; ++k) {
-                const int c = 4 * q + k;
-                const long long i = r * a.C + c;
-                const double dy = bn_bwd_dy(a, i);
-                s[k] += dy;
-                sx[k] += dy * (((double)a.x[i] - a.save_mean[c]) * a.save_rstd[c]);
+    for (int q0 = 0; q0 < quads; q0 += qpr) {
+        const int q = q0 + tid % qpr;
+        const bool active = tid < lanes * qpr && q < quads;
+        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // [sum dy, sum dy * xhat] x 4 channels
+        if (active)
+            for (long long r = r0 + lane; r < r1; r += lanes) {
+                for (int k = 0; k < 4; ++k) {
+                    const int c = 4 * q + k;
+                    const long long i = r * a.C + c;
+                    const double dy = bn_bwd_dy(a, i);
+                    v[2 * k] += dy;
+                    v[2 * k + 1] += dy * (((double)a.x[i] - a.save_mean[c]) * a.save_rstd[c]);
+                }
             }
-        }
-        for (int k = 0; k < 4; ++k) {
-            BN_ATOMIC_ADD(a.sums + 2 * (4 * q + k), s[k]);
-            BN_ATOMIC_ADD(a.sums + 2 * (4 * q + k) + 1, sx[k]);
-        }
+        if (bn_cta_merge(red, tid, qpr, lanes, v) && active)
+            for (int k = 0; k < 8; ++k) BN_ATOMIC_ADD(a.sums + 2 * (4 * q) + k, v[k]);
     }
 }
 
@@ -161,7 +181,10 @@ BN_HD void bn_bwd_apply(const BnBwdArgs& a, long long i4) {
 }
 
 #ifdef __CUDACC__
-static __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(BnBwdArgs a) { bn_bwd_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
+static __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(BnBwdArgs a) {
+    __shared__ double red[256][8];
+    bn_bwd_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x, red);
+}
 static __global__ void bn_bwd_finalize_kernel(BnBwdArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < a.C) bn_bwd_finalize(a, c);
@@ -170,7 +193,10 @@ static __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
     const long long n4 = a.M * a.C / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) bn_bwd_apply(a, i);
 }
-static __global__ void __launch_bounds__(256) bn_stats_kernel(BnTrainArgs a) { bn_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x); }
+static __global__ void __launch_bounds__(256) bn_stats_kernel(BnTrainArgs a) {
+    __shared__ double red[256][8];
+    bn_stats_partial(a, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x, red);
+}
 static __global__ void bn_finalize_kernel(BnTrainArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < a.C) bn_finalize(a, c);

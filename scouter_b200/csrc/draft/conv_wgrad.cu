@@ -7,12 +7,12 @@ namespace scouter_draft {
 
 // Tiled CUDA-core weight gradient (the naive thread-per-weight kernel of conv_wgrad.cuh spends 95 % of a training step):
 // dW[o, (r,s), c] = sum_m dY[m, o] * X[m shifted by tap (r,s), c] is a GEMM whose K dimension is the pixel index m, and in
-// NHWC both operands are K-major rows of contiguous channels.  CTA = 64 output channels x BC input channels of one tap,
-// 256 threads with 4 x (BC/16) register tiles, 32 pixels per shared-memory stage, the pixel range split over gridDim.z
+// NHWC both operands are K-major rows of contiguous channels.  CTA = BO output channels x BC input channels of one tap,
+// 256 threads with (BO/16) x (BC/16) register tiles, 32 pixels per shared-memory stage, the pixel range split over gridDim.z
 // and merged with fp32 atomics (like the naive kernel).
-template <int BC>
+template <int BO, int BC>
 __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(WgradArgs a) {
-    constexpr int BO = 64, KP = 32, TC = BC / 16;
+    constexpr int KP = 32, TO = BO / 16, TC = BC / 16;
     __shared__ float dy_s[KP][BO + 4];
     __shared__ float x_s[KP][BC + 4];
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
@@ -27,9 +27,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(WgradArgs a) {
     const long long per = ((M + gridDim.z - 1) / gridDim.z + KP - 1) / KP * KP;
     const long long m0 = (long long)blockIdx.z * per, m1 = m0 + per < M ? m0 + per : M;
     const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
-    float acc[4][TC];
+    float acc[TO][TC];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TO; ++i)
 #pragma unroll
         for (int j = 0; j < TC; ++j) acc[i][j] = 0.f;
     for (long long mb = m0; mb < m1; mb += KP) {
@@ -58,23 +58,23 @@ __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(WgradArgs a) {
         __syncthreads();
 #pragma unroll 8
         for (int k = 0; k < KP; ++k) {
-            const float4 d4 = *reinterpret_cast<const float4*>(&dy_s[k][4 * ty]);
-            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-            float xv[TC];
+            float dv[TO], xv[TC];
+#pragma unroll
+            for (int i = 0; i < TO; ++i) dv[i] = dy_s[k][ty * TO + i];
 #pragma unroll
             for (int j = 0; j < TC; ++j) xv[j] = x_s[k][tx * TC + j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TO; ++i)
 #pragma unroll
                 for (int j = 0; j < TC; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TO; ++i)
 #pragma unroll
         for (int j = 0; j < TC; ++j) {
-            const int o = o0 + 4 * ty + i, c = ct * BC + tx * TC + j;             // c inside the group
+            const int o = o0 + TO * ty + i, c = ct * BC + tx * TC + j;             // c inside the group
             atomicAdd(a.dw + (((size_t)o * a.k + r) * a.k + sx) * cin_g + c, acc[i][j]);
         }
 }
@@ -84,17 +84,19 @@ int conv_wgrad_launch(const WgradArgs& a, int sms, cudaStream_t stream) {
         const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
         const long long M = (long long)a.B * a.Ho * a.Wo;
         // big maps without a bias: the tiled GEMM form (fc convs on (B,1,1,C) maps and the 1..4-channel stem stay on the naive kernel)
-        if (!a.db && cout_g % 64 == 0 && cin_g % 32 == 0 && M >= 1024 && ((a.Cin | a.Cout) & 3) == 0) {
-            const int bc = cin_g % 64 == 0 ? 64 : 32;
-            const int ctas = a.groups * (cout_g / 64) * (cin_g / bc) * a.k * a.k;
+        if (!a.db && cout_g % 32 == 0 && cin_g % 32 == 0 && M >= 1024 && ((a.Cin | a.Cout) & 3) == 0) {
+            const int bc = cin_g % 64 == 0 ? 64 : 32, bo = cout_g % 64 == 0 ? 64 : 32;
+            const int ctas = a.groups * (cout_g / bo) * (cin_g / bc) * a.k * a.k;
             int splits = (6 * sms + ctas - 1) / ctas;
             const int max_splits = (int)((M + 255) / 256);            // at least 256 pixels per CTA
             if (splits > max_splits) splits = max_splits;
             if (splits < 1) splits = 1;
             if (splits > 65535) splits = 65535;
-            dim3 grid(a.groups * (cout_g / 64) * (cin_g / bc), a.k * a.k, splits);
-            if (bc == 64) conv_wgrad_tiled_kernel<64><<<grid, 256, 0, stream>>>(a);
-            else conv_wgrad_tiled_kernel<32><<<grid, 256, 0, stream>>>(a);
+            dim3 grid(a.groups * (cout_g / bo) * (cin_g / bc), a.k * a.k, splits);
+            if (bo == 64 && bc == 64) conv_wgrad_tiled_kernel<64, 64><<<grid, 256, 0, stream>>>(a);
+            else if (bo == 64) conv_wgrad_tiled_kernel<64, 32><<<grid, 256, 0, stream>>>(a);
+            else if (bc == 64) conv_wgrad_tiled_kernel<32, 64><<<grid, 256, 0, stream>>>(a);
+            else conv_wgrad_tiled_kernel<32, 32><<<grid, 256, 0, stream>>>(a);
             return (int)cudaGetLastError();
         }
     }

@@ -16,6 +16,7 @@ library only sees raw pointers.  Weight packs are rebuilt when any parameter/buf
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -83,8 +84,10 @@ def dgrad_weights(w_ohwi: torch.Tensor, groups: int = 1) -> torch.Tensor:
 class Program:
     """Accumulates ops; keeps every packed tensor alive."""
 
-    def __init__(self, math: int = L.MATH_FP32):
+    def __init__(self, math: int = L.MATH_FP32, fast_stages=()):
         self.math = math
+        self.fast_stages = frozenset(fast_stages)   # per-stage precision policy (MATH_TC only): stages run as single-pass tf32
+        self.fast = False                           # set by stage(): ops emitted now carry F_TF32_1PASS
         self.ops: list[L.Op] = []
         self.keep: list[torch.Tensor] = []
         self.nbuf = 1  # buffer 0 = network input
@@ -92,6 +95,9 @@ class Program:
     def buf(self) -> int:
         self.nbuf += 1
         return self.nbuf - 1
+
+    def stage(self, name: str):
+        self.fast = self.math == L.MATH_TC and name in self.fast_stages
 
     def _t(self, t):
         if t is None:
@@ -101,6 +107,8 @@ class Program:
 
     def emit(self, kind, src, dst, *, src2=-1, cin=0, cout=0, k=1, stride=1, pad=0, groups=1, flags=0, mid=0,
              w=None, b=None, w2=None, b2=None):
+        if self.fast:
+            flags |= L.F_TF32_1PASS
         self.ops.append(L.Op(kind=kind, src=src, src2=src2, dst=dst, cin=cin, cout=cout, kh=k, kw=k, stride=stride,
                              pad=pad, groups=groups, flags=flags, mid=mid, reserved=0,
                              w=self._t(w), b=self._t(b), w2=self._t(w2), b2=self._t(b2)))
@@ -108,10 +116,10 @@ class Program:
 
     def conv(self, src, conv: nn.Conv2d, bn, *, relu, residual=-1, stem=False):
         w, b = fold_conv_bn(conv, bn)
-        if self.math == L.MATH_TC_FAST and not stem:
+        if (self.math == L.MATH_TC_FAST or self.fast) and not stem:
             w = round_tf32(w)        # 1-pass kind::tf32 reads the top 19 bits: make that a rounding, not a truncation
         w2 = None
-        if self.math == L.MATH_TC and not stem:
+        if self.math == L.MATH_TC and not self.fast and not stem:
             # correction operands for the error-compensated kernels: bf16 [W ; W - trunc19(W)]
             w2 = split_weights_bf16(w)
         flags = (L.F_RELU if relu else 0) | (L.F_RESIDUAL if residual >= 0 else 0)
@@ -148,10 +156,26 @@ def _lower_basic_block(p: Program, blk, x: int) -> int:
     return p.conv(t, blk.conv2, blk.bn2, relu=True, residual=res)
 
 
-def lower_backbone(net, math: int = L.MATH_FP32):
+STAGES = ("stem", "layer1", "layer2", "layer3", "layer4")
+
+
+def default_fast_stages():
+    """SCOUTER_TC_FAST_STAGES=stem,layer1,...: the stages of a SCOUTER_MATH_TC backbone that run as ONE tf32 pass on rounded
+    operands instead of the error-compensated product (the precision-policy experiment of profiles/r02_precision_policy.txt).
+    Default: none -- no policy passes the parity bars of all configurations with margin."""
+    v = os.environ.get("SCOUTER_TC_FAST_STAGES", "").strip().lower()
+    st = tuple(t for t in (x.strip() for x in v.split(",")) if t)
+    bad = [t for t in st if t not in STAGES]
+    if bad:
+        raise L.ScouterError(f"SCOUTER_TC_FAST_STAGES: unknown stage(s) {bad}; expected a subset of {list(STAGES)}")
+    return st
+
+
+def lower_backbone(net, math: int = L.MATH_FP32, fast_stages=()):
     """Returns (program, feature_buffer_id) for ``forward_features`` (resnet.py:491-501)."""
     from .backbone import BasicBlock, ResNestBottleneck
-    p = Program(math)
+    p = Program(math, fast_stages)
+    p.stage("stem")
     if isinstance(net.conv1, nn.Sequential):                                    # deep stem
         x = p.conv(0, net.conv1[0], net.conv1[1], relu=True, stem=True)
         x = p.conv(x, net.conv1[3], net.conv1[4], relu=True)
@@ -160,6 +184,7 @@ def lower_backbone(net, math: int = L.MATH_FP32):
         x = p.conv(0, net.conv1, net.bn1, relu=True, stem=True)
     x = p.emit(L.OP_MAXPOOL, x, p.buf(), k=3, stride=2, pad=1)
     for li in range(1, 5):
+        p.stage(f"layer{li}")
         for blk in getattr(net, f"layer{li}"):
             if isinstance(blk, ResNestBottleneck):
                 x = _lower_resnest_block(p, blk, x)
@@ -167,6 +192,7 @@ def lower_backbone(net, math: int = L.MATH_FP32):
                 x = _lower_basic_block(p, blk, x)
             else:
                 raise L.ScouterError(f"cannot lower block type {type(blk).__name__}")
+    p.stage("")
     return p, x
 
 
@@ -342,9 +368,10 @@ def _check_inference(module: nn.Module, what: str):
 class BackboneRunner:
     """``ResNet.forward`` (resnet.py:503-509) on the CUDA library."""
 
-    def __init__(self, net, math: int | None = None):
+    def __init__(self, net, math: int | None = None, fast_stages=None):
         self.net = net
         self.math = math
+        self.fast_stages = fast_stages       # None: SCOUTER_TC_FAST_STAGES (default: none)
         self.sig = None
         self.cp = None
 
@@ -358,7 +385,7 @@ class BackboneRunner:
         from . import default_math
         net = self.net
         math = default_math() if self.math is None else self.math
-        p, feat = lower_backbone(net, math)
+        p, feat = lower_backbone(net, math, default_fast_stages() if self.fast_stages is None else self.fast_stages)
         self.flatten_nchw = isinstance(net.global_pool, Identical)
         if self.flatten_nchw:
             out = p.emit(L.OP_TO_NCHW, feat, p.buf())

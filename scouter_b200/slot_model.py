@@ -76,6 +76,7 @@ class SlotModel(nn.Module):
                 self.dfs_freeze(self.backbone, args.freeze_layers)
         self.num_classes = args.num_classes
         self.math = None              # None -> scouter_b200.default_math()
+        self.fast_stages = None       # None -> SCOUTER_TC_FAST_STAGES (default none): stages of a MATH_TC backbone run as one tf32 pass
         self.use_cuda_graph = False
         self.check_targets = True     # validate labels like F.nll_loss does (one device sync per call with targets)
         self.keep_attn = False        # retain the final attention maps in .last_attn (first-class output)
@@ -130,10 +131,14 @@ class SlotModel(nn.Module):
         from . import default_math
         return default_math() if self.math is None else self.math
 
+    def _fast_stages(self):
+        from .plan import default_fast_stages
+        return tuple(default_fast_stages() if self.fast_stages is None else self.fast_stages)
+
     def _program(self):
-        sig = (_version_signature(self.backbone), self._math())
+        sig = (_version_signature(self.backbone), self._math(), self._fast_stages())
         if self._prog is None or sig != self._sig:
-            prog, feat = lower_backbone(self.backbone, self._math())
+            prog, feat = lower_backbone(self.backbone, self._math(), self._fast_stages())
             self._prog = (prog, feat)
             self._sig = sig
             self._states.clear()

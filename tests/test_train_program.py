@@ -123,7 +123,7 @@ def program_gradients(m, a, sd, x, tgt):
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("model,extra", [("resnest26d", dict()), ("resnet18", dict(dataset="MNIST", channel=512, to_k_layer=1, power=1))])
-def test_train_program_interpreted_matches_train_oracle(model, extra):
+def test_train_program_interpreted_matches_train_oracle(model, extra, min_bar=5e-4):
     if E.lib() is None:
         pytest.skip("g++ not available")
     a = dict(model=model, num_classes=10, slots_per_class=1, power=2, to_k_layer=3, loss_status=1, lambda_value=1.0)
@@ -137,7 +137,7 @@ def test_train_program_interpreted_matches_train_oracle(model, extra):
     grads, bn_after = program_gradients(m, a, sd, x, tgt)
 
     scale = max(float(g.abs().max()) for g in ref["grads"].values() if g is not None)
-    checked = 0
+    checked, bad = 0, []
     for k, g_ref in ref["grads"].items():
         if g_ref is None:
             continue
@@ -148,8 +148,10 @@ def test_train_program_interpreted_matches_train_oracle(model, extra):
             den = max(float(g_ref.abs().max()), 1e-4 * scale)
             floor = float((g_ref.double() - ref64["grads"][k]).abs().max()) / den
             err = float((got - g_ref).abs().max()) / den
-            assert err < max(5e-4, 8 * floor), (k, err, floor)
+            if not err < max(min_bar, 8 * floor):
+                bad.append((k, err, floor))
         checked += 1
+    assert not bad, sorted(bad, key=lambda t: -t[1])[:12]
     assert checked == len(grads)
     for k, v in ref["bn_updates"].items():
         assert np.allclose(bn_after[k], v.numpy(), rtol=1e-4, atol=1e-5), k
