@@ -233,6 +233,12 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
            | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
+// Instruction descriptor, kind::f16 with fp16 operands, fp32 accumulator, both operands K-major.  (The descriptor has one format
+// field per operand, but a kind::f16 MMA whose A and B formats differ is an illegal instruction on sm_100a -- measured.)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // a_format = b_format = 0 (F16)
+}
+
 // Instruction descriptor, kind::tf32, fp32 accumulator, both operands K-major (mma_sm100_desc.hpp InstrDescriptor).
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4)                      // c_format  = F32
@@ -271,24 +277,30 @@ constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc_make(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
-// Operand split of one 8-float group for the error-compensated product: x = trunc19(x) + r.  Returns bf16x8 of x
-// (in `xb`) and of r (in `rb`), each packed as 4 x bf16x2 -- the two correction products use 8-bit-mantissa operands,
-// which costs 2^-9 on terms that are themselves 2^-11 of the main product.
-__device__ __forceinline__ void split8_bf16(const float4& a, const float4& b, uint4& xb, uint4& rb) {
-    auto pack = [](float lo, float hi) {
-        uint32_t r;
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-        return r;
-    };
-    auto rem = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
-    xb = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(b.x, b.y), pack(b.z, b.w));
-    rb = make_uint4(pack(rem(a.x), rem(a.y)), pack(rem(a.z), rem(a.w)), pack(rem(b.x), rem(b.y)), pack(rem(b.z), rem(b.w)));
+// Operand split of one 8-float group for the error-compensated product: x = h + r with h = fp16(x) (round to nearest, 11-bit
+// significand, saturating at +-65504) and r = x - h, which is EXACT in fp32 (the low 13 bits of x; below fp16's normal range
+// h is a multiple of 2^-24 and r still exact) and ~2^-12 |x|.  Three 16-bit forms, each packed as 4 x 16-bit pairs: fp16x8 of
+// h (`xh`, the main product's operand) and bf16x8 of x (`xb`) and of r (`rb`) for the two correction products -- bf16 keeps
+// fp32's exponent range, so neither tiny nor saturated values lose their correction; its 8-bit significand costs 2^-9 on
+// terms that are 2^-12 of the product.
+__device__ __forceinline__ void split2_hbr(float lo, float hi, uint32_t& h2, uint32_t& b2, uint32_t& r2) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(hi), "f"(lo));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b2) : "f"(hi), "f"(lo));
+    float fl, fh;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(fl), "=f"(fh) : "r"(h2));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r2) : "f"(hi - fh), "f"(lo - fl));
+}
+__device__ __forceinline__ void split8_hbr(const float4& a, const float4& b, uint4& xh, uint4& xb, uint4& rb) {
+    split2_hbr(a.x, a.y, xh.x, xb.x, rb.x);
+    split2_hbr(a.z, a.w, xh.y, xb.y, rb.y);
+    split2_hbr(b.x, b.y, xh.z, xb.z, rb.z);
+    split2_hbr(b.z, b.w, xh.w, xb.w, rb.w);
 }
 
-// Converts rows of a SWIZZLE_128B fp32 tile (128-byte rows) into two SWIZZLE_64B bf16 tiles (64-byte rows): bf16(x) and
-// bf16(x - trunc19(x)).  128 threads; thread `tid` owns the 8-float group p = tid % 4 of rows tid/4 + 32*i, so its
-// swizzled source / destination offsets are the same for every i up to a multiple of 4096 / 2048 bytes (row % 8 and
-// (row / 2) % 4 do not change when the row advances by 32): three offsets per thread, computed once per kernel.
+// Converts rows of a SWIZZLE_128B fp32 tile (128-byte rows) into three SWIZZLE_64B 16-bit tiles (64-byte rows) `tile` bytes
+// apart: fp16(x), bf16(x), bf16(x - fp16(x)).  128 threads; thread `tid` owns the 8-float group p = tid % 4 of rows
+// tid/4 + 32*i, so its swizzled source / destination offsets are the same for every i up to a multiple of 4096 / 2048 bytes
+// (row % 8 and (row / 2) % 4 do not change when the row advances by 32): three offsets per thread, computed once per kernel.
 struct SplitLane {
     uint32_t src0, src1, dst;
     int row;
@@ -305,7 +317,7 @@ __device__ __forceinline__ SplitLane split_lane(int tid) {
 // U groups of 32 rows starting at row group `g0`; all loads are issued before the first conversion so that their
 // shared-memory latency overlaps.  Rows >= rows are skipped (halo patches are not a multiple of 32 rows).
 template <int U, bool GUARD>
-__device__ __forceinline__ void split_groups(const uint8_t* src, uint8_t* dst_x, uint8_t* dst_r, const SplitLane& l, int g0, int rows) {
+__device__ __forceinline__ void split_groups(const uint8_t* src, uint8_t* dst, uint32_t tile, const SplitLane& l, int g0, int rows) {
     float4 a[U], b[U];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
@@ -317,25 +329,27 @@ __device__ __forceinline__ void split_groups(const uint8_t* src, uint8_t* dst_x,
 #pragma unroll
     for (int i = 0; i < U; ++i) {
         if (!GUARD || l.row + 32 * (g0 + i) < rows) {
-            uint4 xb, rb;
-            split8_bf16(a[i], b[i], xb, rb);
-            *reinterpret_cast<uint4*>(dst_x + l.dst + 2048 * (g0 + i)) = xb;
-            *reinterpret_cast<uint4*>(dst_r + l.dst + 2048 * (g0 + i)) = rb;
+            uint4 xh, xb, rb;
+            split8_hbr(a[i], b[i], xh, xb, rb);
+            uint8_t* d = dst + l.dst + 2048 * (g0 + i);
+            *reinterpret_cast<uint4*>(d) = xh;
+            *reinterpret_cast<uint4*>(d + tile) = xb;
+            *reinterpret_cast<uint4*>(d + 2 * tile) = rb;
         }
     }
 }
 // Whole tile of ROWS rows (a multiple of 32).
 template <int ROWS>
-__device__ __forceinline__ void split_tile_bf16(const uint8_t* src, uint8_t* dst_x, uint8_t* dst_r, const SplitLane& l) {
-    static_assert(ROWS % 32 == 0, "split_tile_bf16: whole 32-row groups");
-    split_groups<ROWS / 32, false>(src, dst_x, dst_r, l, 0, ROWS);
+__device__ __forceinline__ void split_tile_hbr(const uint8_t* src, uint8_t* dst, uint32_t tile, const SplitLane& l) {
+    static_assert(ROWS % 32 == 0, "split_tile_hbr: whole 32-row groups");
+    split_groups<ROWS / 32, false>(src, dst, tile, l, 0, ROWS);
 }
 // Any number of rows (halo patches).
-__device__ __forceinline__ void split_rows_bf16(const uint8_t* src, uint8_t* dst_x, uint8_t* dst_r, const SplitLane& l, int rows) {
+__device__ __forceinline__ void split_rows_hbr(const uint8_t* src, uint8_t* dst, uint32_t tile, const SplitLane& l, int rows) {
     const int groups = (rows + 31) >> 5;
     int g = 0;
-    for (; g + 4 <= groups; g += 4) split_groups<4, true>(src, dst_x, dst_r, l, g, rows);
-    for (; g < groups; ++g) split_groups<1, true>(src, dst_x, dst_r, l, g, rows);
+    for (; g + 4 <= groups; g += 4) split_groups<4, true>(src, dst, tile, l, g, rows);
+    for (; g < groups; ++g) split_groups<1, true>(src, dst, tile, l, g, rows);
 }
 
 // 32 lanes x 32 columns of fp32 from TMEM: thread i of the warp gets lane (base_lane + i), columns [col, col+32).

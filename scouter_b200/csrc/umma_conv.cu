@@ -3,14 +3,13 @@
 //   D[M = B*H*W, N = Cout/groups] = A[M, K = kh*kw*Cin/groups] * W[N, K]^T     (stride 1, 1x1 or 3x3 pad 1)
 //
 // * Two precisions of the same kernel (template SPLIT):
-//     SPLIT=true  (SCOUTER_MATH_TC, default): error-compensated "3xTF32".  kind::tf32 reads the top 19 bits of an
-//       fp32 word, i.e. x_t = trunc19(x) EXACTLY; the remainder x_r = x - x_t is exact in fp32 and ~2^-11 |x|.  The
-//       issuer accumulates, in the fp32 TMEM accumulator,  A_t*W_t (4 tf32 MMAs per 32-channel k-block) plus the two
-//       correction products A*W_r and A_r*W with bf16 operands (2 + 2 kind::f16 MMAs, K = 16 each: half the tensor
-//       time and half the shared-memory operand bytes of tf32; their 2^-9 operand rounding sits on terms that are
-//       2^-11 of the result).  Four splitter warps derive the bf16 tiles from the TMA-written fp32 tile in shared
-//       memory; weights come pre-split from the host.  Operands stay plain fp32 in HBM; measured error 1.5e-6
-//       (fp32 FMA: 5e-7, one-pass tf32: 7e-4).
+//     SPLIT=true  (SCOUTER_MATH_TC, default): error-compensated 16-bit product.  x = h + r with h = fp16(x) (rounded,
+//       11-bit significand, saturating) and r = x - h, exact in fp32 and ~2^-12 |x|.  The issuer accumulates, in the fp32
+//       TMEM accumulator,  A_h*W_h (fp16 x fp16) + A_b*W_r + A_r*W_b (bf16 x bf16: bf16 keeps fp32's exponent range for the
+//       small terms) as 2 + 2 + 2 kind::f16 MMAs (K = 16) per 32-channel k-block.  Four splitter warps derive A_h / A_b /
+//       A_r from the TMA-written fp32 tile; weights come pre-split from the host ([fp16 W_h ; bf16 W ; bf16 W_r]) or are
+//       split in the kernel.  Operands stay plain fp32 in HBM.  Round 1 ran the main product as kind::tf32 on trunc19(x)
+//       (4 MMAs of K = 8 + 2 + 2 bf16 corrections): 8 MMA times per k-block against 6 now.
 //     SPLIT=false (SCOUTER_MATH_TC_FAST): one tf32 MMA; producers round stored activations with cvt.rna and
 //       weights are pre-rounded on the host, so the MMA multiplies exactly the stored values (cuDNN-TF32 class).
 // * No im2col buffer: for a 3x3 conv the K loop walks the 9 taps and each tap is ONE 4-D TMA box load
@@ -59,19 +58,20 @@ struct UmmaArgs {
 // (M128 x N128 x K8: 4 KB + 4 KB = 64 clk at 128 B/clk, exactly its tensor-pipe floor), so together with the TMA writes and
 // the split tiles a BN=128 k-block moves 160 KB through the shared-memory pipe: 1250 clk for 512 clk of MMAs (measured:
 // 1200 clk per k-block on the layer-4 1x1 convs).  With TS the splitter threads (thread = row) read their row of the TMA
-// tile once, derive the bf16 forms in registers and tcgen05.st [fp32 | bf16 | bf16 remainder] into the 64-column TMEM
-// operand buffer of the stage; the MMAs read only the weight tiles from shared memory (96 KB per k-block).
+// tile once, derive the three 16-bit forms in registers and tcgen05.st [fp16 | bf16 | bf16 remainder] into the 48-column TMEM
+// operand buffer of the stage; the MMAs read only the weight tiles from shared memory.
 template <int BN, bool SPLIT, bool RES = false, bool TS = false>
 struct Cfg {
     static_assert(!TS || SPLIT, "TS is a variant of the error-compensated kernel");
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
-    // SPLIT: [A | W | bf16 A | bf16 A_r | bf16 W | bf16 W_r];  TS: [A | W | bf16 W | bf16 W_r]
-    static constexpr int STAGE = TS ? RAW + B_BYTES : (SPLIT ? 2 * RAW : RAW);
-    static constexpr int OFF_AB = RAW, OFF_ARB = RAW + A_BYTES / 2;
-    static constexpr int OFF_WB = TS ? RAW : RAW + A_BYTES, OFF_WRB = OFF_WB + B_BYTES / 2;
-    static constexpr int OP_COL0 = 2 * BN;                   // TS: operand buffer b = 64 columns at OP_COL0 + 64*b
+    // SPLIT: [A fp32 | W fp32 (only when split in the kernel) | fp16 A_h | bf16 A_b | bf16 A_r | fp16 W_h | bf16 W_b | bf16 W_r]
+    static constexpr int A_TILE = A_BYTES / 2, B_TILE = B_BYTES / 2;   // 16-bit tiles: 64-byte rows
+    static constexpr int STAGE = SPLIT ? RAW + 3 * A_TILE + 3 * B_TILE : RAW;
+    static constexpr int OFF_A16 = RAW, OFF_W16 = RAW + 3 * A_TILE;
+    static constexpr int OP_COL0 = 2 * BN;                   // TS: operand buffer b = 48 columns at OP_COL0 + 48*b
+    static constexpr int OP_COLS = 48;                       //     [fp16 A_h | bf16 A_b | bf16 A_r], 16 columns each
 
     static constexpr int TMEM_COLS = TS ? 512 : (2 * BN < 32 ? 32 : 2 * BN);
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
@@ -88,9 +88,9 @@ struct Cfg {
     // TS: two rings instead of stages.  The activation tile is dead as soon as the splitters hold it in registers, so its
     // ring (NA x 16 KB, fed from HBM) runs far ahead; the weight tiles (fp32 + bf16 pair, from L2) need NW slots; NO TMEM
     // operand buffers sit between the splitters and the MMAs.
-    static constexpr int W_SLOT = 2 * B_BYTES;               // [W fp32 | bf16 W | bf16 W_r]
+    static constexpr int W_SLOT = 3 * B_TILE;                // [fp16 W_h | bf16 W_b | bf16 W_r], BN x 64 bytes each
     static constexpr int BUDGET = 224 * 1024 - OUT_BYTES;
-    static constexpr int NW = (BUDGET - 3 * W_SLOT) / A_BYTES >= 4 ? 3 : 2;
+    static constexpr int NW = (BUDGET - 4 * W_SLOT) / A_BYTES >= 5 ? 4 : 3;
     static constexpr int NA_FIT = (BUDGET - NW * W_SLOT) / A_BYTES;
     static constexpr int NA = NA_FIT > 8 ? 8 : NA_FIT;
     static constexpr int NO = 4;
@@ -216,7 +216,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (TS && warp == 3) {
         if (elect_one()) {
-            // ===== weight producer (TS): fp32 tile + pre-split bf16 [W ; W_r] tiles, NW slots =====
+            // ===== weight producer (TS): pre-split [fp16 W_h ; bf16 W ; bf16 W_r] tiles, NW slots =====
             int ws = 0, gk = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const int sp = t % p.ksplit;
@@ -231,9 +231,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint8_t* sw = w_ring + ws * C::W_SLOT;
                     mbar_arrive_expect_tx(&fullW[ws], (uint32_t)C::W_SLOT);
                     const int kbg = sp * p.kblocks + kb;
-                    tma_load_2d(sw, &tmB, &fullW[ws], kbg * 32, g * p.cout_g + nt * BN);
-                    tma_load_2d(sw + C::B_BYTES, &tmB2, &fullW[ws], kbg * 32, g * p.cout_g + nt * BN);
-                    tma_load_2d(sw + C::B_BYTES + C::B_BYTES / 2, &tmB2, &fullW[ws], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        tma_load_2d(sw + j * C::B_TILE, &tmB2, &fullW[ws], kbg * 32, j * p.rem_rows + g * p.cout_g + nt * BN);
                     if (++ws == C::NW) ws = 0;
                 }
             }
@@ -241,8 +241,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (TS && warp == 1) {
         if (elect_one()) {
             // ===== MMA issuer (TS): A operands from the TMEM operand buffers, weights from the weight ring =====
-            constexpr uint32_t idesc = idesc_tf32(128, BN);
-            constexpr uint32_t idesc_b = idesc_bf16(128, BN);
+            constexpr uint32_t id_h = idesc_f16(128, BN), id_b = idesc_bf16(128, BN);
             const uint32_t w_lo0 = desc_lo(smem_u32(w_ring));
             const uint32_t opfull_a = smem_u32(opfull), fullw_a = smem_u32(fullW), done_a = smem_u32(done), cfull_a = smem_u32(cfull),
                            cempty_a = smem_u32(cempty);
@@ -258,17 +257,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     const uint32_t acc = in_chunk != 0;
-                    const uint32_t a_tm = tmem_base + C::OP_COL0 + 64u * ob;        // [fp32 A | bf16 A | bf16 A_r]
-                    const uint32_t w_lo = w_lo0 + (uint32_t)ws * (C::W_SLOT >> 4);   // [W fp32 | bf16 W | bf16 W_r]
+                    const uint32_t a_tm = tmem_base + C::OP_COL0 + (uint32_t)C::OP_COLS * ob;   // [fp16 A_h | bf16 A_b | bf16 A_r]
+                    const uint32_t w_lo = w_lo0 + (uint32_t)ws * (C::W_SLOT >> 4);              // [fp16 W_h | bf16 W_b | bf16 W_r]
 #pragma unroll
-                    for (uint32_t k = 0; k < 2; ++k)   // A * W_r
-                        umma_bf16_ts(d_tmem, a_tm + 32 + 8 * k, desc_make(DESC_HI_SW64, w_lo + ((C::B_BYTES + C::B_BYTES / 2) >> 4) + 2 * k), idesc_b, acc | k);
+                    for (uint32_t k = 0; k < 2; ++k)   // A_b * W_r   (bf16)
+                        umma_bf16_ts(d_tmem, a_tm + 16 + 8 * k, desc_make(DESC_HI_SW64, w_lo + ((2 * C::B_TILE) >> 4) + 2 * k), id_b, acc | k);
 #pragma unroll
-                    for (uint32_t k = 0; k < 2; ++k)   // A_r * W
-                        umma_bf16_ts(d_tmem, a_tm + 48 + 8 * k, desc_make(DESC_HI_SW64, w_lo + (C::B_BYTES >> 4) + 2 * k), idesc_b, 1);
+                    for (uint32_t k = 0; k < 2; ++k)   // A_r * W_b   (bf16)
+                        umma_bf16_ts(d_tmem, a_tm + 32 + 8 * k, desc_make(DESC_HI_SW64, w_lo + (C::B_TILE >> 4) + 2 * k), id_b, 1);
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
-                        umma_tf32_ts(d_tmem, a_tm + 8 * k, desc_make(DESC_HI_SW128, w_lo + 2 * k), idesc, 1);
+                    for (uint32_t k = 0; k < 2; ++k)   // A_h * W_h   (fp16)
+                        umma_bf16_ts(d_tmem, a_tm + 8 * k, desc_make(DESC_HI_SW64, w_lo + 2 * k), id_h, 1);
                     umma_commit_a(done_a + 8 * ob);    // frees the weight slot and the operand buffer
                     if (++ws == C::NW) { ws = 0; wphase ^= 1; }
                     if (++in_chunk == chunk || kb + 1 == kblocks) {
@@ -314,7 +313,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     PROF_T(empty, mbar_wait(&empty[stage], phase ^ 1));
                     uint8_t* sa = smem + stage * C::STAGE;
                     uint8_t* sb = sa + C::A_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + C::B_BYTES + (SPLIT && p.rem_rows ? C::B_BYTES : 0)));
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + (SPLIT && p.rem_rows ? 3 * C::B_TILE : C::B_BYTES)));
                     const int kbg = sp * p.kblocks + kb;   // k-block index in the full K
                     const int tap = kbg / p.cblocks;
                     const int c0 = p.cin_g * g + (kbg - tap * p.cblocks) * 32;
@@ -324,10 +323,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     } else {
                         tma_load_2d(sa, &tmA, &full[stage], c0, mt * 128);
                     }
-                    tma_load_2d(sb, &tmB, &full[stage], kbg * 32, g * p.cout_g + nt * BN);
-                    if (SPLIT && p.rem_rows) {  // host-pre-split weights: bf16 W and bf16 W_r tiles
-                        tma_load_2d(sa + C::OFF_WB, &tmB2, &full[stage], kbg * 32, g * p.cout_g + nt * BN);
-                        tma_load_2d(sa + C::OFF_WRB, &tmB2, &full[stage], kbg * 32, p.rem_rows + g * p.cout_g + nt * BN);
+                    if (SPLIT && p.rem_rows) {  // host-pre-split weights: fp16 W_h, bf16 W and bf16 W_r tiles
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            tma_load_2d(sa + C::OFF_W16 + j * C::B_TILE, &tmB2, &full[stage], kbg * 32, j * p.rem_rows + g * p.cout_g + nt * BN);
+                    } else {
+                        tma_load_2d(sb, &tmB, &full[stage], kbg * 32, g * p.cout_g + nt * BN);
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -365,21 +366,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     const uint32_t acc = in_chunk != 0;
-                    // UMMA_K = 8 tf32 / 16 bf16 = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
+                    // UMMA_K = 8 tf32 / 16 halves = 32 bytes: advance the start address inside the swizzle atom (+2 x 16 B)
                     if constexpr (SPLIT) {
-                        constexpr uint32_t idesc_b = idesc_bf16(128, BN);
+                        constexpr uint32_t id_h = idesc_f16(128, BN), id_b = idesc_bf16(128, BN);
+                        constexpr uint32_t AH = C::OFF_A16 >> 4, AB = (C::OFF_A16 + C::A_TILE) >> 4, AR = (C::OFF_A16 + 2 * C::A_TILE) >> 4;
+                        constexpr uint32_t WH = C::OFF_W16 >> 4, WB = (C::OFF_W16 + C::B_TILE) >> 4, WR = (C::OFF_W16 + 2 * C::B_TILE) >> 4;
 #pragma unroll
-                        for (uint32_t k = 0; k < 2; ++k)   // A * W_r
-                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + (C::OFF_AB >> 4) + 2 * k),
-                                      desc_make(DESC_HI_SW64, s_lo + (C::OFF_WRB >> 4) + 2 * k), idesc_b, acc | k);
+                        for (uint32_t k = 0; k < 2; ++k)   // A_b * W_r   (bf16)
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + AB + 2 * k), desc_make(DESC_HI_SW64, s_lo + WR + 2 * k), id_b, acc | k);
 #pragma unroll
-                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W
-                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + (C::OFF_ARB >> 4) + 2 * k),
-                                      desc_make(DESC_HI_SW64, s_lo + (C::OFF_WB >> 4) + 2 * k), idesc_b, 1);
+                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W_b   (bf16)
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + AR + 2 * k), desc_make(DESC_HI_SW64, s_lo + WB + 2 * k), id_b, 1);
 #pragma unroll
-                        for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
-                            umma_tf32(d_tmem, desc_make(DESC_HI_SW128, s_lo + 2 * k),
-                                      desc_make(DESC_HI_SW128, s_lo + (C::A_BYTES >> 4) + 2 * k), idesc, 1);
+                        for (uint32_t k = 0; k < 2; ++k)   // A_h * W_h   (fp16)
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + AH + 2 * k), desc_make(DESC_HI_SW64, s_lo + WH + 2 * k), id_h, 1);
                     } else {
 #pragma unroll
                         for (uint32_t k = 0; k < 4; ++k)
@@ -620,11 +620,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             PROF_STORE(g_prof_flat, 18, e_math); PROF_STORE(g_prof_flat, 19, e_fence); PROF_STORE(g_prof_flat, 20, e_bar2); PROF_STORE(g_prof_flat, 21, e_tma);
         }
     } else if (SPLIT && warp >= 8 && warp < 12) {
-        // ===== operand splitters: bf16(x) and bf16(x - trunc19(x)) tiles of the activation (and, unless pre-split, weight) tile =====
+        // ===== operand splitters: fp16(x), bf16(x), bf16(x - fp16(x)) tiles of the activation (and, unless pre-split, weight) tile =====
         const int tid = threadIdx.x - 256;  // 0..127
         PROF_DECL(pfull); PROF_DECL(spl); PROF_BEGIN(spl);
         if constexpr (TS) {
-            // thread = row of the tile: fp32 | bf16 | bf16 remainder of its 32 channels -> TMEM operand buffer gk & 3
+            // thread = row of the tile: fp16 | bf16 | bf16 remainder of its 32 channels -> TMEM operand buffer gk & 3
             const uint32_t sw = (uint32_t)(tid & 7);
             const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::OP_COL0;
             int sa_i = 0;
@@ -633,19 +633,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = 0; kb < p.kblocks; ++kb, ++gk) {
                     PROF_T(pfull, mbar_wait(&fullA[sa_i], aphase));
                     const uint8_t* src = smem + sa_i * C::A_BYTES + tid * 128;
-                    uint32_t f[32], xb[16], rb[16];
+                    uint32_t f[32], xh[16], xb[16], rb[16];
 #pragma unroll
                     for (uint32_t c = 0; c < 8; ++c) {
                         const uint4 v = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));   // SWIZZLE_128B
                         f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float x0 = __uint_as_float(f[2 * i]), x1 = __uint_as_float(f[2 * i + 1]);
-                        const float r0 = x0 - __uint_as_float(f[2 * i] & 0xFFFFE000u), r1 = x1 - __uint_as_float(f[2 * i + 1] & 0xFFFFE000u);
-                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xb[i]) : "f"(x1), "f"(x0));
-                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rb[i]) : "f"(r1), "f"(r0));
-                    }
+                    for (int i = 0; i < 16; ++i) split2_hbr(__uint_as_float(f[2 * i]), __uint_as_float(f[2 * i + 1]), xh[i], xb[i], rb[i]);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&emptyA[sa_i]);          // the tile lives in registers now
                     if (gk >= (uint32_t)C::NO) {
@@ -653,10 +648,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         mbar_wait(&done[j & 3], (j >> 2) & 1u);         // the MMAs that read this operand buffer have retired
                     }
                     tc_fence_after();
-                    const uint32_t t0 = t_lane + 64u * (gk & 3);
-                    tmem_st_32x32(t0, f);
-                    tmem_st_32x16(t0 + 32, xb);
-                    tmem_st_32x16(t0 + 48, rb);
+                    const uint32_t t0 = t_lane + (uint32_t)C::OP_COLS * (gk & 3);
+                    tmem_st_32x16(t0, xh);
+                    tmem_st_32x16(t0 + 16, xb);
+                    tmem_st_32x16(t0 + 32, rb);
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -672,8 +667,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     PROF_T(pfull, mbar_wait(&full[stage], phase));
                     uint8_t* st = smem + stage * C::STAGE;
-                    split_tile_bf16<128>(st, st + C::OFF_AB, st + C::OFF_ARB, sl);
-                    if (!p.rem_rows) split_tile_bf16<BN>(st + C::A_BYTES, st + C::OFF_WB, st + C::OFF_WRB, sl);
+                    split_tile_hbr<128>(st, st + C::OFF_A16, C::A_TILE, sl);
+                    if (!p.rem_rows) split_tile_hbr<BN>(st + C::A_BYTES, st + C::OFF_W16, C::B_TILE, sl);
                     fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&split_done[stage]);
@@ -767,7 +762,7 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     u.cblocks = cin_g / 32;
     u.kblocks = a.kh * a.kw * u.cblocks;
     u.relu = a.relu; u.round_out = a.round_out;
-    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();
+    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
     u.chunk = a.split ? chunk_kb : u.kblocks;
     const bool presplit = a.split && a.w_rem != nullptr;
     u.rem_rows = presplit ? a.Cout : 0;
@@ -804,8 +799,8 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
         r = enc(&plan.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.w, dimsB, stridesB, boxB, esB, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
-        if (presplit) {   // bf16 [W ; W_r]: (2*Cout) rows of Kt bf16
-            cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)2 * a.Cout};
+        if (presplit) {   // 16-bit [fp16 W_h ; bf16 W ; bf16 W_r]: (3*Cout) rows of Kt elements, moved as raw 16-bit words
+            cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)3 * a.Cout};
             cuuint64_t stridesB2[1] = {Kt * 2};
             r = enc(&plan.tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.w_rem, dimsB2, stridesB2, boxB, esB,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

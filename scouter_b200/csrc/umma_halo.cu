@@ -1,4 +1,4 @@
-// 3x3 (stride 1, pad 1) convolution on tcgen05 from ONE halo tile per channel block -- error-compensated 3xTF32.
+// 3x3 (stride 1, pad 1) convolution on tcgen05 from ONE halo tile per channel block -- error-compensated fp16 product.
 //
 // The tap-reload kernel (umma_conv.cu) re-fetches the activation tile from L2 nine times, once per tap.  Here the
 // producer loads the (Hb+2) x (Wb+2) pixel halo patch of 32 channels ONCE (a single 4-D TMA box, out-of-bound
@@ -9,12 +9,15 @@
 // The M dimension then walks 128 CONSECUTIVE patch rows, i.e. "virtual" output rows m' = hb*PW + wb' that include
 // the two halo columns of every line (computed and discarded: Wb/PW of the MMA rows are useful).
 //
-// Per (channel block, tap) the weights arrive as three TMA tiles: W in fp32 (kind::tf32 reads trunc19(W) exactly) and
-// the host-made bf16 copies of W and of W_r = W - trunc19(W).  Four splitter warps turn each fp32 patch into bf16
-// patches of A and A_r = A - trunc19(A) once per patch (not once per tap).  The issuer accumulates
-// A_t*W_t (4 tf32 MMAs) + A*W_r + A_r*W (2 + 2 bf16 MMAs) in TMEM in chunks of `chunk` k-steps; epilogue threads merge
-// the chunks in fp32 registers (the TMEM accumulator truncates on every MMA --
-// profiles/r01_tmem_accumulator_truncation.txt).
+// Precision (round 2): x = h + r with h = fp16(x) and r = x - h exact in fp32 (ptx.cuh split2_hbr).  Per (channel block, tap)
+// the weights arrive as three host-made 16-bit TMA tiles -- fp16 W_h, bf16 W, bf16 W_r -- and four splitter warps turn each
+// fp32 patch into an fp16 patch A_h and bf16 patches A_b, A_r once per patch (not once per tap).  The issuer accumulates
+//     A_h*W_h  (fp16 x fp16)  +  A_b*W_r  +  A_r*W_b  (bf16 x bf16)        = 2 + 2 + 2 kind::f16 MMAs of K = 16
+// in TMEM in chunks of `chunk` k-steps; epilogue threads merge the chunks in fp32 registers (the TMEM accumulator truncates
+// on every MMA -- profiles/r01_tmem_accumulator_truncation.txt).  Against round 1's tf32 main product (4 MMAs of K = 8 +
+// 2 + 2 bf16 corrections) this is 6 instead of 8 MMA times per 32 channels, 3/4 of the weight bytes through shared memory,
+// and a rounded (not truncated) 11-bit main operand.  (fp16 x bf16 in ONE kind::f16 MMA would save the two bf16 copies, but
+// is an illegal instruction on sm_100a -- tried.)
 //
 // Warp roles (512 threads, 1 CTA/SM, persistent): 0 TMA producer | 1 MMA issuer | 2 TMEM alloc | 4-7 and 12-15
 // epilogue (two column halves) | 8-11 splitters.
@@ -43,7 +46,7 @@ struct HaloArgs {
     int cin_g, cout_g, Cout, cblocks;
     int relu;
     int patch_bytes;   // TMA bytes of one raw patch = PH*PW*128
-    int patch_alloc;   // bytes reserved per patch buffer (raw or remainder), multiple of 1024
+    int patch_alloc;   // bytes reserved for the raw fp32 patch (each 16-bit patch takes half of it), multiple of 2048
     int pst, bst;      // ring depths
     int chunk;         // k-steps (cb,tap pairs) per accumulation chunk
     int tma_store;     // epilogue leaves through swizzled staging + 4-D TMA stores (box {16 ch, Wb, Hb, 1})
@@ -52,7 +55,8 @@ struct HaloArgs {
 template <int BN>
 struct HCfg {
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int B_STAGE = 2 * B_BYTES;  // [W fp32 | bf16 W | bf16 W_r]
+    static constexpr int B_TILE = B_BYTES / 2;   // one 16-bit weight tile: BN rows x 64 bytes
+    static constexpr int B_STAGE = 3 * B_TILE;   // [fp16 W_h | bf16 W | bf16 W_r]
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr int EPI_GROUPS = BN == 128 ? 2 : 1;
     static constexpr int NC = BN / EPI_GROUPS;
@@ -63,13 +67,14 @@ struct HCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(512, 1)
-conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO, const HaloArgs p) {
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB2,
+                    const __grid_constant__ CUtensorMap tmO, const HaloArgs p) {
     using C = HCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* patch0 = smem;                                      // pst x [raw | rem]
-    uint8_t* bt0 = smem + p.pst * 2 * p.patch_alloc;            // bst x [W_t | W_r]
+    const int pslot = p.patch_alloc / 2 * 5;                     // one patch stage: [raw fp32 | fp16 A_h | bf16 A_b | bf16 A_r]
+    uint8_t* patch0 = smem;
+    uint8_t* bt0 = smem + p.pst * pslot;                         // bst x [W_h | W_b | W_r]
     uint8_t* out_stage = bt0 + p.bst * C::B_STAGE;               // [EPI_GROUPS][2][OUT_STAGE], 1024-aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + C::OUT_BYTES);
     uint64_t* pfull = bars;                  // [MAX_ST] patch landed (TMA)
@@ -84,7 +89,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&tmA);
-        prefetch_tmap(&tmB);
+        prefetch_tmap(&tmB2);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < C::MAX_ST; ++i) {
@@ -130,7 +135,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tile_coords(t, nt, g, w0, h0, b);
                 PROF_T(pempty, mbar_wait(&pempty[ps], pphase ^ 1));
                 mbar_arrive_expect_tx(&pfull[ps], (uint32_t)p.patch_bytes);
-                tma_load_4d(patch0 + ps * 2 * p.patch_alloc, &tmA, &pfull[ps], g * p.cin_g + cb * 32, w0 - 1, h0 - 1, b);
+                tma_load_4d(patch0 + ps * pslot, &tmA, &pfull[ps], g * p.cin_g + cb * 32, w0 - 1, h0 - 1, b);
                 if (++ps == p.pst) { ps = 0; pphase ^= 1; }
             };
             // patch cursor runs (pst - 1) jobs ahead of the weight-tile cursor
@@ -152,9 +157,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_arrive_expect_tx(&bfull[bs], (uint32_t)C::B_STAGE);
                         const int kcol = tap * p.cin_g + cb * 32;
                         const int nrow = g * p.cout_g + nt * BN;
-                        tma_load_2d(sb, &tmB, &bfull[bs], kcol, nrow);                                   // W fp32
-                        tma_load_2d(sb + C::B_BYTES, &tmB2, &bfull[bs], kcol, nrow);                      // bf16 W
-                        tma_load_2d(sb + C::B_BYTES + C::B_BYTES / 2, &tmB2, &bfull[bs], kcol, p.Cout + nrow);  // bf16 W_r
+                        tma_load_2d(sb, &tmB2, &bfull[bs], kcol, nrow);                                  // fp16 W_h
+                        tma_load_2d(sb + C::B_TILE, &tmB2, &bfull[bs], kcol, p.Cout + nrow);              // bf16 W
+                        tma_load_2d(sb + 2 * C::B_TILE, &tmB2, &bfull[bs], kcol, 2 * p.Cout + nrow);      // bf16 W_r
                         if (++bs == p.bst) { bs = 0; bphase ^= 1; }
                     }
                 }
@@ -168,12 +173,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // One thread, ~4.5 clk per dependent instruction: everything that can be hoisted is.  Descriptors are a
             // constant high word plus a low word advanced by 32-bit adds; barrier addresses are 32-bit shared-window
             // addresses; the nine taps are unrolled so that (r, s) and the k sub-steps are immediates.
-            constexpr uint32_t idesc = idesc_tf32(128, BN), idesc_b = idesc_bf16(128, BN);
-            constexpr uint32_t BSTEP = C::B_STAGE >> 4, WB_OFF = C::B_BYTES >> 4, WRB_OFF = (C::B_BYTES + C::B_BYTES / 2) >> 4;
+            constexpr uint32_t id_h = idesc_f16(128, BN), id_b = idesc_bf16(128, BN);
+            constexpr uint32_t BSTEP = C::B_STAGE >> 4, WB_OFF = C::B_TILE >> 4, WR_OFF = (2 * C::B_TILE) >> 4;
             const uint32_t pa_lo0 = desc_lo(smem_u32(patch0)), b_lo0 = desc_lo(smem_u32(bt0));
-            const uint32_t pstep = (uint32_t)(2 * p.patch_alloc) >> 4;
-            const uint32_t ab_off = (uint32_t)p.patch_alloc >> 4, arb_off = (uint32_t)(p.patch_alloc + p.patch_alloc / 2) >> 4;
-            const uint32_t pw8 = (uint32_t)p.PW * 8u, pw4 = (uint32_t)p.PW * 4u;   // one patch line in 16-byte units (fp32 / bf16 rows)
+            const uint32_t pstep = (uint32_t)pslot >> 4;
+            const uint32_t ah_off = (uint32_t)p.patch_alloc >> 4, half = (uint32_t)(p.patch_alloc / 2) >> 4;
+            const uint32_t pw4 = (uint32_t)p.PW * 4u;   // one patch line of 64-byte rows in 16-byte units
             const uint32_t pready_a = smem_u32(pready), pempty_a = smem_u32(pempty), bfull_a = smem_u32(bfull),
                            bempty_a = smem_u32(bempty), cfull_a = smem_u32(cfull), cempty_a = smem_u32(cempty);
             const int last_cb = p.cblocks - 1, chunk = p.chunk, pst = p.pst, bst = p.bst;
@@ -191,20 +196,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         PROF_T(bfull, mbar_wait_a(bfull_a + 8 * bs, bphase));
                         tc_fence_after();
                         const uint32_t r = tap / 3, sx = tap % 3;              // immediates after unrolling
-                        const uint32_t a32 = pa_lo + r * pw8 + sx * 8u;        // fp32 patch, tap row (r*PW + s) * 128 B
-                        const uint32_t a16 = pa_lo + ab_off + r * pw4 + sx * 4u;
-                        const uint32_t ar16 = pa_lo + arb_off + r * pw4 + sx * 4u;
+                        const uint32_t ah = pa_lo + ah_off + r * pw4 + sx * 4u;   // fp16 patch, tap row (r*PW + s) * 64 B
+                        const uint32_t ab = ah + half, ar = ab + half;            // bf16 patch, bf16 remainder patch
                         const uint32_t d_tmem = tmem_base + buf * BN;
                         const uint32_t acc = in_chunk != 0;
 #pragma unroll
-                        for (uint32_t k = 0; k < 2; ++k)   // A * W_r
-                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, a16 + 2 * k), desc_make(DESC_HI_SW64, b_lo + WRB_OFF + 2 * k), idesc_b, acc | k);
+                        for (uint32_t k = 0; k < 2; ++k)   // A_b * W_r   (bf16)
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ab + 2 * k), desc_make(DESC_HI_SW64, b_lo + WR_OFF + 2 * k), id_b, acc | k);
 #pragma unroll
-                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W
-                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ar16 + 2 * k), desc_make(DESC_HI_SW64, b_lo + WB_OFF + 2 * k), idesc_b, 1);
+                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W_b   (bf16)
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ar + 2 * k), desc_make(DESC_HI_SW64, b_lo + WB_OFF + 2 * k), id_b, 1);
 #pragma unroll
-                        for (uint32_t k = 0; k < 4; ++k)   // A_t * W_t
-                            umma_tf32(d_tmem, desc_make(DESC_HI_SW128, a32 + 2 * k), desc_make(DESC_HI_SW128, b_lo + 2 * k), idesc, 1);
+                        for (uint32_t k = 0; k < 2; ++k)   // A_h * W_h   (fp16)
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ah + 2 * k), desc_make(DESC_HI_SW64, b_lo + 2 * k), id_h, 1);
                         umma_commit_a(bempty_a + 8 * bs);
                         if (++bs == bst) { bs = 0; bphase ^= 1; b_lo = b_lo0; } else { b_lo += BSTEP; }
                         if (++in_chunk == chunk || (tap == 8 && cb == last_cb)) {
@@ -313,7 +317,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         PROF_END(epi);
         if (threadIdx.x == 128) { PROF_STORE(g_prof_halo, 10, epi); PROF_STORE(g_prof_halo, 11, cfull); PROF_STORE(g_prof_halo, 12, store); }
     } else if (warp >= 8 && warp < 12) {
-        // ===== splitters: bf16 patches of A and of A - trunc19(A), once per patch =====
+        // ===== splitters: fp16 / bf16 patches of A and the bf16 patch of A - fp16(A), once per patch =====
         const int tid = threadIdx.x - 256;
         const int prows = p.patch_bytes / 128;
         const SplitLane sl = split_lane(tid);
@@ -323,8 +327,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             for (int cb = 0; cb < p.cblocks; ++cb) {
                 PROF_T(pfull, mbar_wait(&pfull[ps], pphase));
-                uint8_t* raw = patch0 + ps * 2 * p.patch_alloc;
-                split_rows_bf16(raw, raw + p.patch_alloc, raw + p.patch_alloc + p.patch_alloc / 2, sl, prows);
+                uint8_t* raw = patch0 + ps * pslot;
+                split_rows_hbr(raw, raw + p.patch_alloc, (uint32_t)p.patch_alloc / 2, sl, prows);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pready[ps]);
@@ -382,10 +386,10 @@ int halo_bn(int cout_g) {
 }
 
 template <int BN>
-int launch_halo_bn(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tB2, const CUtensorMap& tO, const HaloArgs& u,
+int launch_halo_bn(const CUtensorMap& tA, const CUtensorMap& tB2, const CUtensorMap& tO, const HaloArgs& u,
                    int grid, int smem, cudaStream_t s) {
     SC_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv3x3_halo_kernel<BN><<<grid, 512, smem, s>>>(tA, tB, tB2, tO, u);
+    conv3x3_halo_kernel<BN><<<grid, 512, smem, s>>>(tA, tB2, tO, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -425,22 +429,24 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     u.relu = a.relu;
     u.patch_bytes = PH * u.PW * 128;
     // the last tap starts at row 2*PW+2 and the MMA reads 128 rows from there
-    u.patch_alloc = (int)align_up((size_t)std::max(PH * u.PW, 2 * u.PW + 2 + 128) * 128, 1024);
-    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();
+    // multiple of 2048: a stage is 2.5 patch buffers and the next stage's SWIZZLE_128B patch must start 1024-aligned
+    u.patch_alloc = (int)align_up((size_t)std::max(PH * u.PW, 2 * u.PW + 2 + 128) * 128, 2048);
+    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
     u.chunk = chunk_kb;
-    const int b_stage = 2 * BN * 128;
+    const int b_stage = BN * 192;   // HCfg<BN>::B_STAGE
     static bool no_tma_store = getenv("SCOUTER_NO_TMA_STORE") != nullptr;
     u.tma_store = no_tma_store ? 0 : 1;
     const int scratch = (BN == 128 ? 2 : 1) * 2 * 128 * 64;   // HCfg<BN>::OUT_BYTES
     const int budget = 226 * 1024 - 1536 - scratch;
     // narrow tiles (small BN) do little MMA work per patch and are latency/bandwidth bound: deeper patch prefetch
     const int want_pst = BN == 128 ? 2 : (BN == 64 ? 3 : 4);
+    const int pslot = u.patch_alloc / 2 * 5;    // [raw | fp16 | bf16 | bf16 remainder]
     u.pst = 2;
     for (int pst = want_pst; pst >= 2; --pst)
-        if ((budget - pst * 2 * u.patch_alloc) / b_stage >= 4) { u.pst = pst; break; }
-    u.bst = std::min(8, (budget - u.pst * 2 * u.patch_alloc) / b_stage);
+        if ((budget - pst * pslot) / b_stage >= 4) { u.pst = pst; break; }
+    u.bst = std::min(8, (budget - u.pst * pslot) / b_stage);
     SC_CHECK_ARG(u.bst >= 2, SCOUTER_E_UNSUPPORTED, "conv_halo: patch of %d bytes leaves no room for the weight ring", u.patch_alloc);
-    const int smem = u.pst * 2 * u.patch_alloc + u.bst * b_stage + 1024 + 512 + scratch;
+    const int smem = u.pst * pslot + u.bst * b_stage + 1024 + 512 + scratch;
 
     const bool reuse = plan.valid && plan.halo && plan.in == a.in && plan.w == a.w && plan.B == a.B && plan.H == a.H &&
                        plan.W == a.W && plan.Cin == a.Cin && plan.Cout == a.Cout && plan.groups == a.groups && plan.BN == BN && plan.out == a.out;
@@ -454,15 +460,10 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_halo: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
         const cuuint64_t Kt = (cuuint64_t)9 * cin_g;
-        cuuint64_t dimsB[2] = {Kt, (cuuint64_t)a.Cout};
-        cuuint64_t stridesB[1] = {Kt * 4};
         cuuint32_t boxB[2] = {32, (cuuint32_t)BN};
         cuuint32_t esB[2] = {1, 1};
-        r = enc(&plan.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.w, dimsB, stridesB, boxB, esB, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_halo: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
-        // bf16 [W ; W - trunc19(W)]: (2*Cout) rows of 9*cin_g bf16
-        cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)2 * a.Cout};
+        // 16-bit [fp16 W_h ; bf16 W ; bf16 W_r]: (3*Cout) rows of 9*cin_g elements (moved as raw 16-bit words)
+        cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)3 * a.Cout};
         cuuint64_t stridesB2[1] = {Kt * 2};
         r = enc(&plan.tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.w_rem, dimsB2, stridesB2, boxB, esB,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -489,9 +490,9 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     const long long total = (long long)u.m_tiles * u.n_tiles * u.groups;
     const int grid = (int)std::min<long long>(total, sms);
     switch (BN) {
-        case 32: return launch_halo_bn<32>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, smem, s);
-        case 64: return launch_halo_bn<64>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, smem, s);
-        case 128: return launch_halo_bn<128>(plan.tmA, plan.tmB, plan.tmB2, plan.tmO, u, grid, smem, s);
+        case 32: return launch_halo_bn<32>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s);
+        case 64: return launch_halo_bn<64>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s);
+        case 128: return launch_halo_bn<128>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s);
     }
     return SCOUTER_E_UNSUPPORTED;
 }

@@ -69,6 +69,16 @@ def split_weights_bf16(w: torch.Tensor) -> torch.Tensor:
     return torch.cat([w, trunc19_remainder(w)], dim=0).to(torch.bfloat16).contiguous()
 
 
+def split_weights_f16(w: torch.Tensor) -> torch.Tensor:
+    """(3*Cout, kh, kw, Cin/g) 16-bit words (int16 view): rows [0,Cout) = fp16(W) (round to nearest, saturating at +-65504),
+    rows [Cout,2Cout) = bf16(W), rows [2Cout,3Cout) = bf16(W - fp16(W)) -- the pre-split weight operand of the
+    error-compensated tcgen05 convs (csrc/umma_conv.cu, umma_halo.cu; ``w2`` of ``scouter_op_t``)."""
+    w = w.contiguous()
+    h = w.clamp(-65504.0, 65504.0).to(torch.float16)
+    r = (w - h.float()).to(torch.bfloat16)
+    return torch.cat([h.view(torch.int16), w.to(torch.bfloat16).view(torch.int16), r.view(torch.int16)], dim=0).contiguous()
+
+
 def dgrad_weights(w_ohwi: torch.Tensor, groups: int = 1) -> torch.Tensor:
     """Row f1 groundwork (host side; no backward program exists yet): the data gradient of a stride-1 convolution is
     itself a convolution -- ``dX = conv(dY, W')`` with the taps flipped, input/output channels swapped inside each
@@ -120,8 +130,8 @@ class Program:
             w = round_tf32(w)        # 1-pass kind::tf32 reads the top 19 bits: make that a rounding, not a truncation
         w2 = None
         if self.math == L.MATH_TC and not self.fast and not stem:
-            # correction operands for the error-compensated kernels: bf16 [W ; W - trunc19(W)]
-            w2 = split_weights_bf16(w)
+            # pre-split operand of the error-compensated kernels: [fp16 W ; bf16 W ; bf16 (W - fp16 W)]
+            w2 = split_weights_f16(w)
         flags = (L.F_RELU if relu else 0) | (L.F_RESIDUAL if residual >= 0 else 0)
         return self.emit(L.OP_STEM_CONV if stem else L.OP_CONV, src, self.buf(), src2=residual,
                          cin=conv.in_channels, cout=conv.out_channels, k=conv.kernel_size[0], stride=conv.stride[0],

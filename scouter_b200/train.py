@@ -28,7 +28,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as L
-from .plan import backward_schedule, dgrad_weights, lower_backbone_train, split_weights_bf16
+from .plan import backward_schedule, dgrad_weights, lower_backbone_train, split_weights_f16
 
 POOL_KIND = {"maxpool": 0, "avgpool2": 1, "avgpool3": 2}
 
@@ -74,7 +74,7 @@ class TrainEngine:
             if k == "conv":
                 conv = self._mod(op["key"])
                 w = conv.weight.detach().permute(0, 2, 3, 1).contiguous()           # OHWI
-                w2 = split_weights_bf16(w) if math_mode == L.MATH_TC else None
+                w2 = split_weights_f16(w) if math_mode == L.MATH_TC else None
                 kh = conv.kernel_size[0]
                 Ho = (H + 2 * op["pad"] - kh) // op["stride"] + 1
                 Wo = (W + 2 * op["pad"] - kh) // op["stride"] + 1
@@ -237,7 +237,7 @@ class TrainEngine:
                         # padding k-1-pad): it runs on the forward kernels -- tcgen05 in the tensor-core mode
                         math_mode = m._math()
                         wt = dgrad_weights(w, e["groups"])
-                        wt2 = split_weights_bf16(wt) if math_mode == L.MATH_TC else None
+                        wt2 = split_weights_f16(wt) if math_mode == L.MATH_TC else None
                         o = L.Op(kind=L.OP_CONV, src=0, src2=-1, dst=1, cin=Cout, cout=Cin, kh=kk, kw=kk, stride=1, pad=kk - 1 - e["pad"],
                                  groups=e["groups"], flags=0, mid=0, reserved=0, w=wt.data_ptr(), b=0, w2=_p(wt2), b2=0)
                         L.check(lib.scouter_conv_forward(C.byref(o), dy.data_ptr(), 0, dx.data_ptr(), B, Ho, Wo, math_mode, st), "scouter_conv_forward (dgrad)")

@@ -31,7 +31,7 @@ if a.build_only:
     sys.exit(0)
 
 import torch  # noqa: E402
-from scouter_b200.plan import split_weights_bf16  # noqa: E402
+from scouter_b200.plan import split_weights_f16  # noqa: E402
 
 L.LIB_PATH = PROF_LIB
 lib = L.lib()
@@ -59,7 +59,7 @@ B = a.batch
 for name, H, W, Cin, Cout, k, g, use_res in CASES:
     x = torch.randn(B, H, W, Cin, device=dev)
     w = torch.randn(Cout, k, k, Cin // g, device=dev) * (2.0 / (Cin // g * k * k)) ** 0.5
-    w2 = split_weights_bf16(w)
+    w2 = split_weights_f16(w)
     bias = torch.randn(Cout, device=dev) * 0.1
     res = torch.randn(B, H, W, Cout, device=dev) if use_res else None
     out = torch.empty(B, H, W, Cout, device=dev)

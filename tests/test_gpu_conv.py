@@ -43,14 +43,14 @@ CASES = [
 
 def run_conv(dev, x, w, b, res, k, groups, relu, math, presplit=False):
     """x NCHW cpu, w (Cout,Cin/g,k,k) cpu -> out NCHW cpu via the library."""
-    from scouter_b200.plan import split_weights_bf16
+    from scouter_b200.plan import split_weights_f16
     Bn, Cin, H, W = x.shape
     Cout = w.shape[0]
     xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
     wd = w.permute(0, 2, 3, 1).contiguous().to(dev)
     w2 = 0
-    if presplit:                                      # bf16 [W ; W - trunc19(W)], like plan.py
-        keep = split_weights_bf16(wd)
+    if presplit:                                      # [fp16 W ; bf16 W ; bf16 (W - fp16 W)], like plan.py
+        keep = split_weights_f16(wd)
         w2 = keep.data_ptr()
     bd = b.to(dev)
     rd = res.permute(0, 2, 3, 1).contiguous().to(dev) if res is not None else None
