@@ -19,6 +19,14 @@
 // and a rounded (not truncated) 11-bit main operand.  (fp16 x bf16 in ONE kind::f16 MMA would save the two bf16 copies, but
 // is an illegal instruction on sm_100a -- tried.)
 //
+// FOLD (narrow outputs, cout/groups <= 64): every MMA re-reads its 128 x 32-byte A slice from shared memory whatever N is,
+// so nine taps x three products x two K halves of N = 32 cost 216 KB of operand reads per 128-row tile -- these layers
+// (deep-stem 3x3s, layer-1 split-attention convs) ran at 1.5-1.9 TB/s of their HBM traffic.  The folded form puts the
+// three taps s = 0,1,2 of one kernel row r into N:  D[m, s*Cout + co] = sum_{r,c} patch[m + r*PW, c] * W[co, r, s, c]  (three
+// A start rows instead of nine, N = 3*Cout), and the epilogue finishes  out[m] = sum_s D[m + s, block s]  with warp shuffles
+// -- patch lines are PW = 16 rows, so a line never straddles a warp's 32 TMEM lanes and the lanes that would read across
+// the line end are the two discarded halo columns.  A reads and MMA issues drop 3x.
+//
 // Warp roles (512 threads, 1 CTA/SM, persistent): 0 TMA producer | 1 MMA issuer | 2 TMEM alloc | 4-7 and 12-15
 // epilogue (two column halves) | 8-11 splitters.
 //
@@ -50,26 +58,32 @@ struct HaloArgs {
     int pst, bst;      // ring depths
     int chunk;         // k-steps (cb,tap pairs) per accumulation chunk
     int tma_store;     // epilogue leaves through swizzled staging + 4-D TMA stores (box {16 ch, Wb, Hb, 1})
+    int wres;          // FOLD: the weights of one (group, n-tile) stay RESIDENT in shared memory (bst = cblocks*3 stages, loaded
+                       // when the key changes) -- streamed per tile they are 108 KB from L2 against a 20 KB patch (L2-bound)
 };
 
-template <int BN>
+template <int BN, bool FOLD = false>
 struct HCfg {
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int B_TILE = B_BYTES / 2;   // one 16-bit weight tile: BN rows x 64 bytes
-    static constexpr int B_STAGE = 3 * B_TILE;   // [fp16 W_h | bf16 W | bf16 W_r]
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int EPI_GROUPS = BN == 128 ? 2 : 1;
+    static_assert(!FOLD || BN <= 64, "the folded form needs N = 3*BN <= 256");
+    static constexpr int NB = FOLD ? 3 * BN : BN;   // N of one MMA = columns of one TMEM accumulator buffer
+    static constexpr int STEPS = FOLD ? 3 : 9;      // k-steps (weight stages) per channel block: kernel rows / taps
+    static constexpr int B_TILE = NB * 64;          // one 16-bit weight tile: NB rows x 64 bytes
+    static constexpr int B_STAGE = 3 * B_TILE;      // [fp16 W_h | bf16 W | bf16 W_r]
+    static constexpr int TMEM_COLS = 2 * NB <= 32 ? 32 : (2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512)));
+    static constexpr int BUF_COLS = TMEM_COLS / 2;  // column stride of the two accumulator buffers (a power of two >= NB)
+    static constexpr int EPI_GROUPS = (BN == 128 || FOLD) ? 2 : 1;   // FOLD: 3*BN accumulator columns + shuffles per output row
     static constexpr int NC = BN / EPI_GROUPS;
     static constexpr int MAX_ST = 8;
     static constexpr int OUT_STAGE = 128 * 64;   // staging of 16 columns x <=128 compact tile rows, SWIZZLE_64B
-    static constexpr int OUT_BYTES = EPI_GROUPS * 2 * OUT_STAGE;
+    static constexpr int OUT_BUFS = FOLD ? 1 : 2;   // staging buffers per epilogue group (FOLD: shared memory holds the weights)
+    static constexpr int OUT_BYTES = EPI_GROUPS * OUT_BUFS * OUT_STAGE;
 };
 
-template <int BN>
+template <int BN, bool FOLD>
 __global__ void __launch_bounds__(512, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB2,
                     const __grid_constant__ CUtensorMap tmO, const HaloArgs p) {
-    using C = HCfg<BN>;
+    using C = HCfg<BN, FOLD>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int pslot = p.patch_alloc / 2 * 5;                     // one patch stage: [raw fp32 | fp16 A_h | bf16 A_b | bf16 A_r]
@@ -84,7 +98,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* bempty = bfull + C::MAX_ST;    // [MAX_ST]
     uint64_t* cfull = bempty + C::MAX_ST;    // [2]
     uint64_t* cempty = cfull + 2;            // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(cempty + 2);
+    uint64_t* wfull = cempty + 2;            // resident weights landed
+    uint64_t* wempty = wfull + 1;            // every MMA that read the resident weights retired (before a reload)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wempty + 1);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (warp == 0 && elect_one()) {
@@ -103,6 +119,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(&cfull[i], 1);
             mbar_init(&cempty[i], 128 * C::EPI_GROUPS);
         }
+        mbar_init(wfull, 1);
+        mbar_init(wempty, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -112,7 +130,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_base = *tmem_ptr;
 
     const int total = p.m_tiles * p.n_tiles * p.groups;
-    const int ksteps = p.cblocks * 9;
+    const int ksteps = p.cblocks * C::STEPS;
     const int nchunks = (ksteps + p.chunk - 1) / p.chunk;
 
     auto tile_coords = [&](int t, int& nt, int& g, int& w0, int& h0, int& b) {
@@ -146,20 +164,45 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (++pcb == p.cblocks) { pcb = 0; pt += gridDim.x; }
             };
             for (int i = 0; i < p.pst - 1; ++i) issue_next_patch();
+            int wkey = -1;
+            uint32_t wephase = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 int nt, g, w0, h0, b;
                 tile_coords(t, nt, g, w0, h0, b);
+                if (FOLD && p.wres) {
+                    const int key = g * p.n_tiles + nt;
+                    if (key != wkey) {     // (re)load the resident weights: all channel blocks x kernel rows of this (group, n-tile)
+                        if (wkey >= 0) { mbar_wait(wempty, wephase); wephase ^= 1; }
+                        mbar_arrive_expect_tx(wfull, (uint32_t)(p.cblocks * 3 * C::B_STAGE));
+                        const int nrow = g * p.cout_g + nt * BN;
+                        for (int st = 0; st < p.cblocks * 3; ++st)
+                            for (int s3 = 0; s3 < 3; ++s3) {
+                                const int kcol = ((st % 3) * 3 + s3) * p.cin_g + (st / 3) * 32;
+                                uint8_t* d = bt0 + st * C::B_STAGE + s3 * BN * 64;
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) tma_load_2d(d + j * C::B_TILE, &tmB2, wfull, kcol, j * p.Cout + nrow);
+                            }
+                        wkey = key;
+                    }
+                    for (int cb = 0; cb < p.cblocks; ++cb) issue_next_patch();
+                    continue;
+                }
                 for (int cb = 0; cb < p.cblocks; ++cb) {
-                    for (int tap = 0; tap < 9; ++tap) {
-                        if (tap == 3) issue_next_patch();  // the issuer is inside this job: the oldest patch stage is (about to be) free
+                    for (int st = 0; st < C::STEPS; ++st) {
+                        if (st == C::STEPS / 3) issue_next_patch();  // the issuer is inside this job: the oldest patch stage is (about to be) free
                         PROF_T(bempty, mbar_wait(&bempty[bs], bphase ^ 1));
                         uint8_t* sb = bt0 + bs * C::B_STAGE;
                         mbar_arrive_expect_tx(&bfull[bs], (uint32_t)C::B_STAGE);
-                        const int kcol = tap * p.cin_g + cb * 32;
                         const int nrow = g * p.cout_g + nt * BN;
-                        tma_load_2d(sb, &tmB2, &bfull[bs], kcol, nrow);                                  // fp16 W_h
-                        tma_load_2d(sb + C::B_TILE, &tmB2, &bfull[bs], kcol, p.Cout + nrow);              // bf16 W
-                        tma_load_2d(sb + 2 * C::B_TILE, &tmB2, &bfull[bs], kcol, 2 * p.Cout + nrow);      // bf16 W_r
+#pragma unroll
+                        for (int s3 = 0; s3 < (FOLD ? 3 : 1); ++s3) {     // FOLD: taps (st, 0..2) stacked along N
+                            const int tap = FOLD ? st * 3 + s3 : st;
+                            const int kcol = tap * p.cin_g + cb * 32;
+                            uint8_t* d = sb + s3 * BN * 64;
+                            tma_load_2d(d, &tmB2, &bfull[bs], kcol, nrow);                                  // fp16 W_h
+                            tma_load_2d(d + C::B_TILE, &tmB2, &bfull[bs], kcol, p.Cout + nrow);              // bf16 W
+                            tma_load_2d(d + 2 * C::B_TILE, &tmB2, &bfull[bs], kcol, 2 * p.Cout + nrow);      // bf16 W_r
+                        }
                         if (++bs == p.bst) { bs = 0; bphase ^= 1; }
                     }
                 }
@@ -173,7 +216,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // One thread, ~4.5 clk per dependent instruction: everything that can be hoisted is.  Descriptors are a
             // constant high word plus a low word advanced by 32-bit adds; barrier addresses are 32-bit shared-window
             // addresses; the nine taps are unrolled so that (r, s) and the k sub-steps are immediates.
-            constexpr uint32_t id_h = idesc_f16(128, BN), id_b = idesc_bf16(128, BN);
+            constexpr uint32_t id_h = idesc_f16(128, C::NB), id_b = idesc_bf16(128, C::NB);
             constexpr uint32_t BSTEP = C::B_STAGE >> 4, WB_OFF = C::B_TILE >> 4, WR_OFF = (2 * C::B_TILE) >> 4;
             const uint32_t pa_lo0 = desc_lo(smem_u32(patch0)), b_lo0 = desc_lo(smem_u32(bt0));
             const uint32_t pstep = (uint32_t)pslot >> 4;
@@ -185,20 +228,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int ps = 0, bs = 0, in_chunk = 0;
             uint32_t pphase = 0, bphase = 0, cc = 0;
             uint32_t pa_lo = pa_lo0, b_lo = b_lo0;
+            const bool wres = FOLD && p.wres;
+            int wkey = -1;
+            uint32_t wfphase = 0;
+            auto tile_key = [&](int t) { return (t / (p.n_tiles * p.m_tiles)) * p.n_tiles + t % p.n_tiles; };
             PROF_DECL(pready); PROF_DECL(cempty); PROF_DECL(bfull); PROF_DECL(iss); PROF_DECL(ntaps); PROF_BEGIN(iss);
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                if (wres && tile_key(t) != wkey) {
+                    mbar_wait(wfull, wfphase);
+                    wfphase ^= 1;
+                    wkey = tile_key(t);
+                }
                 for (int cb = 0; cb <= last_cb; ++cb) {
+                    if (wres) b_lo = b_lo0 + (uint32_t)(cb * 3) * BSTEP;
                     PROF_T(pready, mbar_wait_a(pready_a + 8 * ps, pphase));
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < C::STEPS; ++tap) {
                         const uint32_t buf = cc & 1;
                         if (in_chunk == 0) PROF_T(cempty, mbar_wait_a(cempty_a + 8 * buf, ((cc >> 1) & 1) ^ 1));
-                        PROF_T(bfull, mbar_wait_a(bfull_a + 8 * bs, bphase));
+                        if (!wres) PROF_T(bfull, mbar_wait_a(bfull_a + 8 * bs, bphase));
                         tc_fence_after();
-                        const uint32_t r = tap / 3, sx = tap % 3;              // immediates after unrolling
+                        const uint32_t r = FOLD ? tap : tap / 3, sx = FOLD ? 0 : tap % 3;   // immediates after unrolling
                         const uint32_t ah = pa_lo + ah_off + r * pw4 + sx * 4u;   // fp16 patch, tap row (r*PW + s) * 64 B
                         const uint32_t ab = ah + half, ar = ab + half;            // bf16 patch, bf16 remainder patch
-                        const uint32_t d_tmem = tmem_base + buf * BN;
+                        const uint32_t d_tmem = tmem_base + buf * C::BUF_COLS;
                         const uint32_t acc = in_chunk != 0;
 #pragma unroll
                         for (uint32_t k = 0; k < 2; ++k)   // A_b * W_r   (bf16)
@@ -209,9 +262,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (uint32_t k = 0; k < 2; ++k)   // A_h * W_h   (fp16)
                             umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ah + 2 * k), desc_make(DESC_HI_SW64, b_lo + 2 * k), id_h, 1);
-                        umma_commit_a(bempty_a + 8 * bs);
-                        if (++bs == bst) { bs = 0; bphase ^= 1; b_lo = b_lo0; } else { b_lo += BSTEP; }
-                        if (++in_chunk == chunk || (tap == 8 && cb == last_cb)) {
+                        if (wres) {
+                            b_lo += BSTEP;
+                        } else {
+                            umma_commit_a(bempty_a + 8 * bs);
+                            if (++bs == bst) { bs = 0; bphase ^= 1; b_lo = b_lo0; } else { b_lo += BSTEP; }
+                        }
+                        if (++in_chunk == chunk || (tap == C::STEPS - 1 && cb == last_cb)) {
                             umma_commit_a(cfull_a + 8 * buf);
                             ++cc;
                             in_chunk = 0;
@@ -220,9 +277,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     umma_commit_a(pempty_a + 8 * ps);
                     if (++ps == pst) { ps = 0; pphase ^= 1; pa_lo = pa_lo0; } else { pa_lo += pstep; }
 #ifdef SCOUTER_PROF
-                    prof_ntaps += 9;
+                    prof_ntaps += C::STEPS;
 #endif
                 }
+                if (wres && t + (int)gridDim.x < total && tile_key(t + gridDim.x) != wkey) umma_commit_a(smem_u32(wempty));
             }
             PROF_END(iss);
             PROF_STORE(g_prof_halo, 4, iss); PROF_STORE(g_prof_halo, 5, pready); PROF_STORE(g_prof_halo, 6, cempty);
@@ -261,13 +319,40 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int buf = cc & 1;
                 PROF_T(cfull, mbar_wait(&cfull[buf], (cc >> 1) & 1));
                 tc_fence_after();
+                if constexpr (FOLD) {
+                    // out[m] = sum_s D[m + s, block s]: lane m takes block s from lane m + s of its own warp (a patch line is 16
+                    // lanes; the lanes that would wrap are the discarded halo columns wb >= Wb)
 #pragma unroll
-                for (int c = 0; c < C::NC / 32; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + col0 + c * 32, r);
-                    tmem_ld_wait();
+                    for (int s3 = 0; s3 < 3; ++s3) {
+                        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * C::BUF_COLS + s3 * BN + col0;
+                        uint32_t r[C::NC];
+                        if constexpr (C::NC == 32) {
+                            tmem_ld_32x32(ta, r);
+                        } else {
+                            static_assert(C::NC == 16, "folded epilogue: 16 or 32 columns per thread");
+                            uint32_t r0[8], r1[8];
+                            tmem_ld_32x8(ta, r0);
+                            tmem_ld_32x8(ta + 8, r1);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                            for (int j = 0; j < 8; ++j) { r[j] = r0[j]; r[8 + j] = r1[j]; }
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < C::NC; ++j) {
+                            float v = __uint_as_float(r[j]);
+                            if (s3) v = __shfl_down_sync(0xffffffffu, v, s3);
+                            acc[j] += v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C::NC / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * C::BUF_COLS + col0 + c * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&cempty[buf]);
@@ -287,8 +372,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int cr = hb * p.Wb + wb;
 #pragma unroll
                 for (int c16 = 0; c16 < C::NC / 16; ++c16) {
-                    uint8_t* stg = out_stage + (grp * 2 + (c16 & 1)) * C::OUT_STAGE;
-                    if (row == 0) bulk_wait_read<1>();
+                    uint8_t* stg = out_stage + (grp * C::OUT_BUFS + (c16 & (C::OUT_BUFS - 1))) * C::OUT_STAGE;
+                    if (row == 0) { if constexpr (C::OUT_BUFS == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
                     named_bar_sync(1 + grp, 128);
                     if (inbox) {
 #pragma unroll
@@ -385,11 +470,11 @@ int halo_bn(int cout_g) {
     return 0;
 }
 
-template <int BN>
+template <int BN, bool FOLD = false>
 int launch_halo_bn(const CUtensorMap& tA, const CUtensorMap& tB2, const CUtensorMap& tO, const HaloArgs& u,
                    int grid, int smem, cudaStream_t s) {
-    SC_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv3x3_halo_kernel<BN><<<grid, 512, smem, s>>>(tA, tB2, tO, u);
+    SC_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv3x3_halo_kernel<BN, FOLD><<<grid, 512, smem, s>>>(tA, tB2, tO, u);
     SC_LAUNCH_CHECK();
     return 0;
 }
@@ -419,6 +504,10 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     u.bias = a.bias; u.res = a.res; u.out = a.out;
     u.B = a.B; u.H = a.H; u.W = a.W;
     choose_halo_tile(a.H, a.W, u.Wb, u.Hb);
+    // narrow outputs: taps folded into N (see the header); fixed 14 x 8 tiles = 8 patch lines of 16 rows
+    static bool no_fold = getenv("SCOUTER_HALO_NO_FOLD") != nullptr;
+    const bool fold = BN <= 64 && !no_fold && a.W >= 14 && a.H >= 8;
+    if (fold) { u.Wb = 14; u.Hb = 8; }
     u.PW = u.Wb + 2;
     const int PH = u.Hb + 2;
     u.tw = cdiv(a.W, u.Wb); u.th = cdiv(a.H, u.Hb);
@@ -431,20 +520,33 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     // the last tap starts at row 2*PW+2 and the MMA reads 128 rows from there
     // multiple of 2048: a stage is 2.5 patch buffers and the next stage's SWIZZLE_128B patch must start 1024-aligned
     u.patch_alloc = (int)align_up((size_t)std::max(PH * u.PW, 2 * u.PW + 2 + 128) * 128, 2048);
+    if (fold) u.patch_alloc = (int)align_up((size_t)PH * u.PW * 128, 2048);   // the last kernel row starts at 2*PW and reads 128 rows: exactly the patch
     static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
-    u.chunk = chunk_kb;
-    const int b_stage = BN * 192;   // HCfg<BN>::B_STAGE
+    u.chunk = fold ? 3 : chunk_kb;   // folded: one chunk = the three kernel rows of a channel block (18 accumulations)
+    const int b_stage = (fold ? 3 : 1) * BN * 192;   // HCfg<BN, FOLD>::B_STAGE
     static bool no_tma_store = getenv("SCOUTER_NO_TMA_STORE") != nullptr;
     u.tma_store = no_tma_store ? 0 : 1;
     const int scratch = (BN == 128 ? 2 : 1) * 2 * 128 * 64;   // HCfg<BN>::OUT_BYTES
     const int budget = 226 * 1024 - 1536 - scratch;
     // narrow tiles (small BN) do little MMA work per patch and are latency/bandwidth bound: deeper patch prefetch
     const int want_pst = BN == 128 ? 2 : (BN == 64 ? 3 : 4);
+    const int min_bst = fold ? 2 : 4;
     const int pslot = u.patch_alloc / 2 * 5;    // [raw | fp16 | bf16 | bf16 remainder]
     u.pst = 2;
     for (int pst = want_pst; pst >= 2; --pst)
-        if ((budget - pst * pslot) / b_stage >= 4) { u.pst = pst; break; }
+        if ((budget - pst * pslot) / b_stage >= min_bst) { u.pst = pst; break; }
     u.bst = std::min(8, (budget - u.pst * pslot) / b_stage);
+    u.wres = 0;
+    if (fold) {
+        static bool no_wres = getenv("SCOUTER_HALO_NO_WRES") != nullptr;
+        const int w_bytes = u.cblocks * 3 * b_stage;
+        const int fit = (budget - w_bytes) / pslot;
+        if (!no_wres && fit >= 2) {
+            u.wres = 1;
+            u.pst = std::min(want_pst, fit);
+            u.bst = u.cblocks * 3;
+        }
+    }
     SC_CHECK_ARG(u.bst >= 2, SCOUTER_E_UNSUPPORTED, "conv_halo: patch of %d bytes leaves no room for the weight ring", u.patch_alloc);
     const int smem = u.pst * pslot + u.bst * b_stage + 1024 + 512 + scratch;
 
@@ -490,8 +592,10 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     const long long total = (long long)u.m_tiles * u.n_tiles * u.groups;
     const int grid = (int)std::min<long long>(total, sms);
     switch (BN) {
-        case 32: return launch_halo_bn<32>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s);
-        case 64: return launch_halo_bn<64>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s);
+        case 32: return fold ? launch_halo_bn<32, true>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s)
+                             : launch_halo_bn<32>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s);
+        case 64: return fold ? launch_halo_bn<64, true>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s)
+                             : launch_halo_bn<64>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s);
         case 128: return launch_halo_bn<128>(plan.tmA, plan.tmB2, plan.tmO, u, grid, smem, s);
     }
     return SCOUTER_E_UNSUPPORTED;

@@ -34,6 +34,8 @@ CASES = [
     (2, 33, 33, 128, 256, 3, 2, False, False),
     (3, 9, 9, 512, 1024, 3, 2, False, True),
     (1, 17, 17, 1024, 256, 1, 1, False, True),
+    (1, 17, 23, 32, 32, 3, 1, True, False),        # folded-tap halo kernel: ragged 14 x 8 tiles, residual
+    (2, 20, 20, 64, 64, 3, 1, False, True),        # folded-tap halo kernel: two channel blocks = two accumulation chunks
     (1, 5, 3, 32, 32, 3, 1, False, False),         # tiny map, smaller than one box
     (300, 1, 1, 64, 64, 1, 1, False, False),       # M = 300: partial last flat tile
     (1, 17, 17, 64, 128, 1, 1, True, True),        # residual epilogue with a partial last tile (M = 289)

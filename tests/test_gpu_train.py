@@ -14,7 +14,8 @@ the largest gradient), on max-norm, L2 norm and (where stored) every element:
 The one-parameter allowance: the split-attention fc1 / fc2 gradients pass through a BatchNorm whose batch statistics are taken
 over just B = 4 values per channel (split_attn.py:66-67 on a (B,C,1,1) map), so they are almost pure amplified rounding noise
 (floors 2e-3 .. 2e-2 of the gradient's own maximum) and a single draw lands at ~15 x floor now and then -- measured:
-layer1.0.conv2.fc1.weight of cfg 3 at 3.1e-2 against a floor of 2.1e-3 with the fp16-main-product convs, 1.5e-2 with round 1's.
+layer1.0.conv2.fc1.weight of cfg 3 at 3.1e-2 against a floor of 2.1e-3 with the fp16-main-product convs (inside its bar with round 1's
+tf32 main product: a different draw of the same noise).
 Log-probs and losses are held to the forward's bar.  The conv gradients are merged with fp32 atomics (order not fixed).
 """
 import numpy as np
