@@ -208,7 +208,7 @@ typedef struct scouter_op {
     int32_t reserved;
     /* Folded parameters, device pointers, fp32:
      *   CONV / STEM_CONV: w = (cout, kh, kw, cin/groups) "OHWI", b = (cout); for SCOUTER_MATH_TC an optional
-     *     w2 = 16-bit [fp16(W) ; bf16(W) ; bf16(W - fp16(W))] ((3*cout, kh, kw, cin/groups) halves: the pre-split operand of the
+     *     w2 = 16-bit [fp16(W) ; bf16(W - fp16(W))] ((2*cout, kh, kw, cin/groups) halves: the pre-split operand of the
      *     error-compensated fp16 product, scouter_b200/plan.py split_weights_f16) lets the kernels skip the on-the-fly
      *     weight split and keep the activation operand in tensor memory
      */

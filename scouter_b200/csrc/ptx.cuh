@@ -279,28 +279,36 @@ __device__ __forceinline__ uint64_t desc_make(uint32_t hi, uint32_t lo) { return
 
 // Operand split of one 8-float group for the error-compensated product: x = h + r with h = fp16(x) (round to nearest, 11-bit
 // significand, saturating at +-65504) and r = x - h, which is EXACT in fp32 (the low 13 bits of x; below fp16's normal range
-// h is a multiple of 2^-24 and r still exact) and ~2^-12 |x|.  Three 16-bit forms, each packed as 4 x 16-bit pairs: fp16x8 of
-// h (`xh`, the main product's operand) and bf16x8 of x (`xb`) and of r (`rb`) for the two correction products -- bf16 keeps
-// fp32's exponent range, so neither tiny nor saturated values lose their correction; its 8-bit significand costs 2^-9 on
-// terms that are 2^-12 of the product.
-__device__ __forceinline__ void split2_hbr(float lo, float hi, uint32_t& h2, uint32_t& b2, uint32_t& r2) {
+// h is a multiple of 2^-24 and r still exact) and ~2^-12 |x|.  The product is  a*w ~= a_h*w_h + a_b*w_r + a_r*w_h  with
+//   ACTIVATIONS: a_h = fp16(a), a_b = bf16(a), a_r = fp16(a - a_h)   (three 16-bit forms), and
+//   WEIGHTS:     w_h = fp16(w), w_r = bf16(w - w_h)                  (two forms),
+// so the main product and one correction are fp16 x fp16 MMAs and the other correction is bf16 x bf16 (a kind::f16 MMA
+// cannot mix the two formats).  The weight remainder needs bf16's exponent range (weights are ~1e-2, their remainders ~1e-6);
+// the activation remainder in fp16 is exact to 2^-25 ABSOLUTE (fp16's subnormal spacing is 2^-24) and relative 2^-11 of
+// itself above |a| = 0.25 -- for activations of scale >= 0.06 that is below the 2^-21 the bf16 operands leave anyway; a
+// network whose activations are all below that degrades gracefully to an absolute error of 2^-25 |w| per product.
+__device__ __forceinline__ void unpack_f16x2(uint32_t h2, float& lo, float& hi) {
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(h2));
+}
+__device__ __forceinline__ void split2_act(float lo, float hi, uint32_t& h2, uint32_t& b2, uint32_t& r2) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(hi), "f"(lo));
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b2) : "f"(hi), "f"(lo));
     float fl, fh;
-    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(fl), "=f"(fh) : "r"(h2));
+    unpack_f16x2(h2, fl, fh);
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r2) : "f"(hi - fh), "f"(lo - fl));
+}
+__device__ __forceinline__ void split2_wgt(float lo, float hi, uint32_t& h2, uint32_t& r2) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(hi), "f"(lo));
+    float fl, fh;
+    unpack_f16x2(h2, fl, fh);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r2) : "f"(hi - fh), "f"(lo - fl));
 }
-__device__ __forceinline__ void split8_hbr(const float4& a, const float4& b, uint4& xh, uint4& xb, uint4& rb) {
-    split2_hbr(a.x, a.y, xh.x, xb.x, rb.x);
-    split2_hbr(a.z, a.w, xh.y, xb.y, rb.y);
-    split2_hbr(b.x, b.y, xh.z, xb.z, rb.z);
-    split2_hbr(b.z, b.w, xh.w, xb.w, rb.w);
-}
 
-// Converts rows of a SWIZZLE_128B fp32 tile (128-byte rows) into three SWIZZLE_64B 16-bit tiles (64-byte rows) `tile` bytes
-// apart: fp16(x), bf16(x), bf16(x - fp16(x)).  128 threads; thread `tid` owns the 8-float group p = tid % 4 of rows
-// tid/4 + 32*i, so its swizzled source / destination offsets are the same for every i up to a multiple of 4096 / 2048 bytes
-// (row % 8 and (row / 2) % 4 do not change when the row advances by 32): three offsets per thread, computed once per kernel.
+// Converts rows of a SWIZZLE_128B fp32 tile (128-byte rows) into SWIZZLE_64B 16-bit tiles (64-byte rows) `tile` bytes apart:
+// activations [fp16(x) | bf16(x) | fp16(x - fp16(x))], weights (WGT) [fp16(w) | bf16(w - fp16(w))].  128 threads; thread `tid`
+// owns the 8-float group p = tid % 4 of rows tid/4 + 32*i, so its swizzled source / destination offsets are the same for every
+// i up to a multiple of 4096 / 2048 bytes (row % 8 and (row / 2) % 4 do not change when the row advances by 32): three
+// offsets per thread, computed once per kernel.
 struct SplitLane {
     uint32_t src0, src1, dst;
     int row;
@@ -316,7 +324,7 @@ __device__ __forceinline__ SplitLane split_lane(int tid) {
 }
 // U groups of 32 rows starting at row group `g0`; all loads are issued before the first conversion so that their
 // shared-memory latency overlaps.  Rows >= rows are skipped (halo patches are not a multiple of 32 rows).
-template <int U, bool GUARD>
+template <int U, bool GUARD, bool WGT = false>
 __device__ __forceinline__ void split_groups(const uint8_t* src, uint8_t* dst, uint32_t tile, const SplitLane& l, int g0, int rows) {
     float4 a[U], b[U];
 #pragma unroll
@@ -329,20 +337,29 @@ __device__ __forceinline__ void split_groups(const uint8_t* src, uint8_t* dst, u
 #pragma unroll
     for (int i = 0; i < U; ++i) {
         if (!GUARD || l.row + 32 * (g0 + i) < rows) {
-            uint4 xh, xb, rb;
-            split8_hbr(a[i], b[i], xh, xb, rb);
+            const float v[8] = {a[i].x, a[i].y, a[i].z, a[i].w, b[i].x, b[i].y, b[i].z, b[i].w};
+            uint32_t xh[4], xb[4], rb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if constexpr (WGT) split2_wgt(v[2 * j], v[2 * j + 1], xh[j], rb[j]);
+                else split2_act(v[2 * j], v[2 * j + 1], xh[j], xb[j], rb[j]);
+            }
             uint8_t* d = dst + l.dst + 2048 * (g0 + i);
-            *reinterpret_cast<uint4*>(d) = xh;
-            *reinterpret_cast<uint4*>(d + tile) = xb;
-            *reinterpret_cast<uint4*>(d + 2 * tile) = rb;
+            *reinterpret_cast<uint4*>(d) = make_uint4(xh[0], xh[1], xh[2], xh[3]);
+            if constexpr (WGT) {
+                *reinterpret_cast<uint4*>(d + tile) = make_uint4(rb[0], rb[1], rb[2], rb[3]);
+            } else {
+                *reinterpret_cast<uint4*>(d + tile) = make_uint4(xb[0], xb[1], xb[2], xb[3]);
+                *reinterpret_cast<uint4*>(d + 2 * tile) = make_uint4(rb[0], rb[1], rb[2], rb[3]);
+            }
         }
     }
 }
 // Whole tile of ROWS rows (a multiple of 32).
-template <int ROWS>
+template <int ROWS, bool WGT = false>
 __device__ __forceinline__ void split_tile_hbr(const uint8_t* src, uint8_t* dst, uint32_t tile, const SplitLane& l) {
     static_assert(ROWS % 32 == 0, "split_tile_hbr: whole 32-row groups");
-    split_groups<ROWS / 32, false>(src, dst, tile, l, 0, ROWS);
+    split_groups<ROWS / 32, false, WGT>(src, dst, tile, l, 0, ROWS);
 }
 // Any number of rows (halo patches).
 __device__ __forceinline__ void split_rows_hbr(const uint8_t* src, uint8_t* dst, uint32_t tile, const SplitLane& l, int rows) {

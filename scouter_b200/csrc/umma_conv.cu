@@ -66,12 +66,12 @@ struct Cfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW = A_BYTES + B_BYTES;            // what TMA writes per stage
-    // SPLIT: [A fp32 | W fp32 (only when split in the kernel) | fp16 A_h | bf16 A_b | bf16 A_r | fp16 W_h | bf16 W_b | bf16 W_r]
+    // SPLIT: [A fp32 | W fp32 (only when split in the kernel) | fp16 A_h | bf16 A_b | fp16 A_r | fp16 W_h | bf16 W_r]
     static constexpr int A_TILE = A_BYTES / 2, B_TILE = B_BYTES / 2;   // 16-bit tiles: 64-byte rows
-    static constexpr int STAGE = SPLIT ? RAW + 3 * A_TILE + 3 * B_TILE : RAW;
+    static constexpr int STAGE = SPLIT ? RAW + 3 * A_TILE + 2 * B_TILE : RAW;
     static constexpr int OFF_A16 = RAW, OFF_W16 = RAW + 3 * A_TILE;
     static constexpr int OP_COL0 = 2 * BN;                   // TS: operand buffer b = 48 columns at OP_COL0 + 48*b
-    static constexpr int OP_COLS = 48;                       //     [fp16 A_h | bf16 A_b | bf16 A_r], 16 columns each
+    static constexpr int OP_COLS = 48;                       //     [fp16 A_h | bf16 A_b | fp16 A_r], 16 columns each
 
     static constexpr int TMEM_COLS = TS ? 512 : (2 * BN < 32 ? 32 : 2 * BN);
     // SPLIT: two epilogue warpgroups (warps 4-7 and 12-15) share the columns of a BN=128 tile so that the running
@@ -88,7 +88,7 @@ struct Cfg {
     // TS: two rings instead of stages.  The activation tile is dead as soon as the splitters hold it in registers, so its
     // ring (NA x 16 KB, fed from HBM) runs far ahead; the weight tiles (fp32 + bf16 pair, from L2) need NW slots; NO TMEM
     // operand buffers sit between the splitters and the MMAs.
-    static constexpr int W_SLOT = 3 * B_TILE;                // [fp16 W_h | bf16 W_b | bf16 W_r], BN x 64 bytes each
+    static constexpr int W_SLOT = 2 * B_TILE;                // [fp16 W_h | bf16 W_r], BN x 64 bytes each
     static constexpr int BUDGET = 224 * 1024 - OUT_BYTES;
     static constexpr int NW = (BUDGET - 4 * W_SLOT) / A_BYTES >= 5 ? 4 : 3;
     static constexpr int NA_FIT = (BUDGET - NW * W_SLOT) / A_BYTES;
@@ -216,7 +216,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (TS && warp == 3) {
         if (elect_one()) {
-            // ===== weight producer (TS): pre-split [fp16 W_h ; bf16 W ; bf16 W_r] tiles, NW slots =====
+            // ===== weight producer (TS): pre-split [fp16 W_h ; bf16 W_r] tiles, NW slots =====
             int ws = 0, gk = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const int sp = t % p.ksplit;
@@ -232,7 +232,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_arrive_expect_tx(&fullW[ws], (uint32_t)C::W_SLOT);
                     const int kbg = sp * p.kblocks + kb;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j)
+                    for (int j = 0; j < 2; ++j)
                         tma_load_2d(sw + j * C::B_TILE, &tmB2, &fullW[ws], kbg * 32, j * p.rem_rows + g * p.cout_g + nt * BN);
                     if (++ws == C::NW) ws = 0;
                 }
@@ -257,14 +257,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     const uint32_t acc = in_chunk != 0;
-                    const uint32_t a_tm = tmem_base + C::OP_COL0 + (uint32_t)C::OP_COLS * ob;   // [fp16 A_h | bf16 A_b | bf16 A_r]
-                    const uint32_t w_lo = w_lo0 + (uint32_t)ws * (C::W_SLOT >> 4);              // [fp16 W_h | bf16 W_b | bf16 W_r]
+                    const uint32_t a_tm = tmem_base + C::OP_COL0 + (uint32_t)C::OP_COLS * ob;   // [fp16 A_h | bf16 A_b | fp16 A_r]
+                    const uint32_t w_lo = w_lo0 + (uint32_t)ws * (C::W_SLOT >> 4);              // [fp16 W_h | bf16 W_r]
 #pragma unroll
                     for (uint32_t k = 0; k < 2; ++k)   // A_b * W_r   (bf16)
-                        umma_bf16_ts(d_tmem, a_tm + 16 + 8 * k, desc_make(DESC_HI_SW64, w_lo + ((2 * C::B_TILE) >> 4) + 2 * k), id_b, acc | k);
+                        umma_bf16_ts(d_tmem, a_tm + 16 + 8 * k, desc_make(DESC_HI_SW64, w_lo + (C::B_TILE >> 4) + 2 * k), id_b, acc | k);
 #pragma unroll
-                    for (uint32_t k = 0; k < 2; ++k)   // A_r * W_b   (bf16)
-                        umma_bf16_ts(d_tmem, a_tm + 32 + 8 * k, desc_make(DESC_HI_SW64, w_lo + (C::B_TILE >> 4) + 2 * k), id_b, 1);
+                    for (uint32_t k = 0; k < 2; ++k)   // A_r * W_h   (fp16)
+                        umma_bf16_ts(d_tmem, a_tm + 32 + 8 * k, desc_make(DESC_HI_SW64, w_lo + 2 * k), id_h, 1);
 #pragma unroll
                     for (uint32_t k = 0; k < 2; ++k)   // A_h * W_h   (fp16)
                         umma_bf16_ts(d_tmem, a_tm + 8 * k, desc_make(DESC_HI_SW64, w_lo + 2 * k), id_h, 1);
@@ -313,7 +313,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     PROF_T(empty, mbar_wait(&empty[stage], phase ^ 1));
                     uint8_t* sa = smem + stage * C::STAGE;
                     uint8_t* sb = sa + C::A_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + (SPLIT && p.rem_rows ? 3 * C::B_TILE : C::B_BYTES)));
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + C::B_BYTES));   // fp32 W, or the two 16-bit tiles
                     const int kbg = sp * p.kblocks + kb;   // k-block index in the full K
                     const int tap = kbg / p.cblocks;
                     const int c0 = p.cin_g * g + (kbg - tap * p.cblocks) * 32;
@@ -323,9 +323,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     } else {
                         tma_load_2d(sa, &tmA, &full[stage], c0, mt * 128);
                     }
-                    if (SPLIT && p.rem_rows) {  // host-pre-split weights: fp16 W_h, bf16 W and bf16 W_r tiles
+                    if (SPLIT && p.rem_rows) {  // host-pre-split weights: fp16 W_h and bf16 W_r tiles
 #pragma unroll
-                        for (int j = 0; j < 3; ++j)
+                        for (int j = 0; j < 2; ++j)
                             tma_load_2d(sa + C::OFF_W16 + j * C::B_TILE, &tmB2, &full[stage], kbg * 32, j * p.rem_rows + g * p.cout_g + nt * BN);
                     } else {
                         tma_load_2d(sb, &tmB, &full[stage], kbg * 32, g * p.cout_g + nt * BN);
@@ -370,13 +370,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if constexpr (SPLIT) {
                         constexpr uint32_t id_h = idesc_f16(128, BN), id_b = idesc_bf16(128, BN);
                         constexpr uint32_t AH = C::OFF_A16 >> 4, AB = (C::OFF_A16 + C::A_TILE) >> 4, AR = (C::OFF_A16 + 2 * C::A_TILE) >> 4;
-                        constexpr uint32_t WH = C::OFF_W16 >> 4, WB = (C::OFF_W16 + C::B_TILE) >> 4, WR = (C::OFF_W16 + 2 * C::B_TILE) >> 4;
+                        constexpr uint32_t WH = C::OFF_W16 >> 4, WR = (C::OFF_W16 + C::B_TILE) >> 4;
 #pragma unroll
                         for (uint32_t k = 0; k < 2; ++k)   // A_b * W_r   (bf16)
                             umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + AB + 2 * k), desc_make(DESC_HI_SW64, s_lo + WR + 2 * k), id_b, acc | k);
 #pragma unroll
-                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W_b   (bf16)
-                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + AR + 2 * k), desc_make(DESC_HI_SW64, s_lo + WB + 2 * k), id_b, 1);
+                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W_h   (fp16)
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + AR + 2 * k), desc_make(DESC_HI_SW64, s_lo + WH + 2 * k), id_h, 1);
 #pragma unroll
                         for (uint32_t k = 0; k < 2; ++k)   // A_h * W_h   (fp16)
                             umma_bf16(d_tmem, desc_make(DESC_HI_SW64, s_lo + AH + 2 * k), desc_make(DESC_HI_SW64, s_lo + WH + 2 * k), id_h, 1);
@@ -640,7 +640,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) split2_hbr(__uint_as_float(f[2 * i]), __uint_as_float(f[2 * i + 1]), xh[i], xb[i], rb[i]);
+                    for (int i = 0; i < 16; ++i) split2_act(__uint_as_float(f[2 * i]), __uint_as_float(f[2 * i + 1]), xh[i], xb[i], rb[i]);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&emptyA[sa_i]);          // the tile lives in registers now
                     if (gk >= (uint32_t)C::NO) {
@@ -668,7 +668,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     PROF_T(pfull, mbar_wait(&full[stage], phase));
                     uint8_t* st = smem + stage * C::STAGE;
                     split_tile_hbr<128>(st, st + C::OFF_A16, C::A_TILE, sl);
-                    if (!p.rem_rows) split_tile_hbr<BN>(st + C::A_BYTES, st + C::OFF_W16, C::B_TILE, sl);
+                    if (!p.rem_rows) split_tile_hbr<BN, true>(st + C::A_BYTES, st + C::OFF_W16, C::B_TILE, sl);
                     fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&split_done[stage]);
@@ -799,8 +799,8 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
         r = enc(&plan.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.w, dimsB, stridesB, boxB, esB, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SC_CHECK_ARG(r == CUDA_SUCCESS, SCOUTER_E_UNSUPPORTED, "conv_umma: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
-        if (presplit) {   // 16-bit [fp16 W_h ; bf16 W ; bf16 W_r]: (3*Cout) rows of Kt elements, moved as raw 16-bit words
-            cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)3 * a.Cout};
+        if (presplit) {   // 16-bit [fp16 W_h ; bf16 W_r]: (2*Cout) rows of Kt elements, moved as raw 16-bit words
+            cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)2 * a.Cout};
             cuuint64_t stridesB2[1] = {Kt * 2};
             r = enc(&plan.tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.w_rem, dimsB2, stridesB2, boxB, esB,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -9,15 +9,15 @@
 // The M dimension then walks 128 CONSECUTIVE patch rows, i.e. "virtual" output rows m' = hb*PW + wb' that include
 // the two halo columns of every line (computed and discarded: Wb/PW of the MMA rows are useful).
 //
-// Precision (round 2): x = h + r with h = fp16(x) and r = x - h exact in fp32 (ptx.cuh split2_hbr).  Per (channel block, tap)
-// the weights arrive as three host-made 16-bit TMA tiles -- fp16 W_h, bf16 W, bf16 W_r -- and four splitter warps turn each
-// fp32 patch into an fp16 patch A_h and bf16 patches A_b, A_r once per patch (not once per tap).  The issuer accumulates
-//     A_h*W_h  (fp16 x fp16)  +  A_b*W_r  +  A_r*W_b  (bf16 x bf16)        = 2 + 2 + 2 kind::f16 MMAs of K = 16
+// Precision (round 2): a*w ~= a_h*w_h + a_b*w_r + a_r*w_h (ptx.cuh split2_act / split2_wgt: h = fp16, r = x - h exact).  Per
+// (channel block, tap) the weights arrive as two host-made 16-bit TMA tiles -- fp16 W_h, bf16 W_r -- and four splitter warps
+// turn each fp32 patch into fp16 A_h, bf16 A_b and fp16 A_r patches once per patch (not once per tap).  The issuer accumulates
+//     A_b*W_r  (bf16 x bf16)  +  A_r*W_h  +  A_h*W_h  (fp16 x fp16)        = 2 + 2 + 2 kind::f16 MMAs of K = 16
 // in TMEM in chunks of `chunk` k-steps; epilogue threads merge the chunks in fp32 registers (the TMEM accumulator truncates
 // on every MMA -- profiles/r01_tmem_accumulator_truncation.txt).  Against round 1's tf32 main product (4 MMAs of K = 8 +
-// 2 + 2 bf16 corrections) this is 6 instead of 8 MMA times per 32 channels, 3/4 of the weight bytes through shared memory,
-// and a rounded (not truncated) 11-bit main operand.  (fp16 x bf16 in ONE kind::f16 MMA would save the two bf16 copies, but
-// is an illegal instruction on sm_100a -- tried.)
+// 2 + 2 bf16 corrections) this is 6 instead of 8 MMA times per 32 channels, half the weight bytes from L2 and through shared
+// memory, and a rounded (not truncated) 11-bit main operand.  (fp16 x bf16 in ONE kind::f16 MMA would save the bf16 copy of
+// A as well, but is an illegal instruction on sm_100a -- tried.)
 //
 // FOLD (narrow outputs, cout/groups <= 64): every MMA re-reads its 128 x 32-byte A slice from shared memory whatever N is,
 // so nine taps x three products x two K halves of N = 32 cost 216 KB of operand reads per 128-row tile -- these layers
@@ -68,7 +68,7 @@ struct HCfg {
     static constexpr int NB = FOLD ? 3 * BN : BN;   // N of one MMA = columns of one TMEM accumulator buffer
     static constexpr int STEPS = FOLD ? 3 : 9;      // k-steps (weight stages) per channel block: kernel rows / taps
     static constexpr int B_TILE = NB * 64;          // one 16-bit weight tile: NB rows x 64 bytes
-    static constexpr int B_STAGE = 3 * B_TILE;      // [fp16 W_h | bf16 W | bf16 W_r]
+    static constexpr int B_STAGE = 2 * B_TILE;      // [fp16 W_h | bf16 W_r]
     static constexpr int TMEM_COLS = 2 * NB <= 32 ? 32 : (2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512)));
     static constexpr int BUF_COLS = TMEM_COLS / 2;  // column stride of the two accumulator buffers (a power of two >= NB)
     static constexpr int EPI_GROUPS = (BN == 128 || FOLD) ? 2 : 1;   // FOLD: 3*BN accumulator columns + shuffles per output row
@@ -180,7 +180,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 const int kcol = ((st % 3) * 3 + s3) * p.cin_g + (st / 3) * 32;
                                 uint8_t* d = bt0 + st * C::B_STAGE + s3 * BN * 64;
 #pragma unroll
-                                for (int j = 0; j < 3; ++j) tma_load_2d(d + j * C::B_TILE, &tmB2, wfull, kcol, j * p.Cout + nrow);
+                                for (int j = 0; j < 2; ++j) tma_load_2d(d + j * C::B_TILE, &tmB2, wfull, kcol, j * p.Cout + nrow);
                             }
                         wkey = key;
                     }
@@ -199,9 +199,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const int tap = FOLD ? st * 3 + s3 : st;
                             const int kcol = tap * p.cin_g + cb * 32;
                             uint8_t* d = sb + s3 * BN * 64;
-                            tma_load_2d(d, &tmB2, &bfull[bs], kcol, nrow);                                  // fp16 W_h
-                            tma_load_2d(d + C::B_TILE, &tmB2, &bfull[bs], kcol, p.Cout + nrow);              // bf16 W
-                            tma_load_2d(d + 2 * C::B_TILE, &tmB2, &bfull[bs], kcol, 2 * p.Cout + nrow);      // bf16 W_r
+                            tma_load_2d(d, &tmB2, &bfull[bs], kcol, nrow);                      // fp16 W_h
+                            tma_load_2d(d + C::B_TILE, &tmB2, &bfull[bs], kcol, p.Cout + nrow);  // bf16 W_r
                         }
                         if (++bs == p.bst) { bs = 0; bphase ^= 1; }
                     }
@@ -217,7 +216,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // constant high word plus a low word advanced by 32-bit adds; barrier addresses are 32-bit shared-window
             // addresses; the nine taps are unrolled so that (r, s) and the k sub-steps are immediates.
             constexpr uint32_t id_h = idesc_f16(128, C::NB), id_b = idesc_bf16(128, C::NB);
-            constexpr uint32_t BSTEP = C::B_STAGE >> 4, WB_OFF = C::B_TILE >> 4, WR_OFF = (2 * C::B_TILE) >> 4;
+            constexpr uint32_t BSTEP = C::B_STAGE >> 4, WR_OFF = C::B_TILE >> 4;
             const uint32_t pa_lo0 = desc_lo(smem_u32(patch0)), b_lo0 = desc_lo(smem_u32(bt0));
             const uint32_t pstep = (uint32_t)pslot >> 4;
             const uint32_t ah_off = (uint32_t)p.patch_alloc >> 4, half = (uint32_t)(p.patch_alloc / 2) >> 4;
@@ -250,15 +249,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tc_fence_after();
                         const uint32_t r = FOLD ? tap : tap / 3, sx = FOLD ? 0 : tap % 3;   // immediates after unrolling
                         const uint32_t ah = pa_lo + ah_off + r * pw4 + sx * 4u;   // fp16 patch, tap row (r*PW + s) * 64 B
-                        const uint32_t ab = ah + half, ar = ab + half;            // bf16 patch, bf16 remainder patch
+                        const uint32_t ab = ah + half, ar = ab + half;            // bf16 patch, fp16 remainder patch
                         const uint32_t d_tmem = tmem_base + buf * C::BUF_COLS;
                         const uint32_t acc = in_chunk != 0;
 #pragma unroll
                         for (uint32_t k = 0; k < 2; ++k)   // A_b * W_r   (bf16)
                             umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ab + 2 * k), desc_make(DESC_HI_SW64, b_lo + WR_OFF + 2 * k), id_b, acc | k);
 #pragma unroll
-                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W_b   (bf16)
-                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ar + 2 * k), desc_make(DESC_HI_SW64, b_lo + WB_OFF + 2 * k), id_b, 1);
+                        for (uint32_t k = 0; k < 2; ++k)   // A_r * W_h   (fp16)
+                            umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ar + 2 * k), desc_make(DESC_HI_SW64, b_lo + 2 * k), id_h, 1);
 #pragma unroll
                         for (uint32_t k = 0; k < 2; ++k)   // A_h * W_h   (fp16)
                             umma_bf16(d_tmem, desc_make(DESC_HI_SW64, ah + 2 * k), desc_make(DESC_HI_SW64, b_lo + 2 * k), id_h, 1);
@@ -523,7 +522,7 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     if (fold) u.patch_alloc = (int)align_up((size_t)PH * u.PW * 128, 2048);   // the last kernel row starts at 2*PW and reads 128 rows: exactly the patch
     static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
     u.chunk = fold ? 3 : chunk_kb;   // folded: one chunk = the three kernel rows of a channel block (18 accumulations)
-    const int b_stage = (fold ? 3 : 1) * BN * 192;   // HCfg<BN, FOLD>::B_STAGE
+    const int b_stage = (fold ? 3 : 1) * BN * 128;   // HCfg<BN, FOLD>::B_STAGE
     static bool no_tma_store = getenv("SCOUTER_NO_TMA_STORE") != nullptr;
     u.tma_store = no_tma_store ? 0 : 1;
     const int scratch = (BN == 128 ? 2 : 1) * 2 * 128 * 64;   // HCfg<BN>::OUT_BYTES
@@ -564,8 +563,8 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
         const cuuint64_t Kt = (cuuint64_t)9 * cin_g;
         cuuint32_t boxB[2] = {32, (cuuint32_t)BN};
         cuuint32_t esB[2] = {1, 1};
-        // 16-bit [fp16 W_h ; bf16 W ; bf16 W_r]: (3*Cout) rows of 9*cin_g elements (moved as raw 16-bit words)
-        cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)3 * a.Cout};
+        // 16-bit [fp16 W_h ; bf16 W_r]: (2*Cout) rows of 9*cin_g elements (moved as raw 16-bit words)
+        cuuint64_t dimsB2[2] = {Kt, (cuuint64_t)2 * a.Cout};
         cuuint64_t stridesB2[1] = {Kt * 2};
         r = enc(&plan.tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.w_rem, dimsB2, stridesB2, boxB, esB,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -70,13 +70,13 @@ def split_weights_bf16(w: torch.Tensor) -> torch.Tensor:
 
 
 def split_weights_f16(w: torch.Tensor) -> torch.Tensor:
-    """(3*Cout, kh, kw, Cin/g) 16-bit words (int16 view): rows [0,Cout) = fp16(W) (round to nearest, saturating at +-65504),
-    rows [Cout,2Cout) = bf16(W), rows [2Cout,3Cout) = bf16(W - fp16(W)) -- the pre-split weight operand of the
-    error-compensated tcgen05 convs (csrc/umma_conv.cu, umma_halo.cu; ``w2`` of ``scouter_op_t``)."""
+    """(2*Cout, kh, kw, Cin/g) 16-bit words (int16 view): rows [0,Cout) = fp16(W) (round to nearest, saturating at +-65504),
+    rows [Cout,2Cout) = bf16(W - fp16(W)) -- the pre-split weight operand of the error-compensated tcgen05 convs
+    (csrc/ptx.cuh split2_wgt, umma_conv.cu, umma_halo.cu; ``w2`` of ``scouter_op_t``)."""
     w = w.contiguous()
     h = w.clamp(-65504.0, 65504.0).to(torch.float16)
     r = (w - h.float()).to(torch.bfloat16)
-    return torch.cat([h.view(torch.int16), w.to(torch.bfloat16).view(torch.int16), r.view(torch.int16)], dim=0).contiguous()
+    return torch.cat([h.view(torch.int16), r.view(torch.int16)], dim=0).contiguous()
 
 
 def dgrad_weights(w_ohwi: torch.Tensor, groups: int = 1) -> torch.Tensor:
@@ -130,7 +130,7 @@ class Program:
             w = round_tf32(w)        # 1-pass kind::tf32 reads the top 19 bits: make that a rounding, not a truncation
         w2 = None
         if self.math == L.MATH_TC and not self.fast and not stem:
-            # pre-split operand of the error-compensated kernels: [fp16 W ; bf16 W ; bf16 (W - fp16 W)]
+            # pre-split operand of the error-compensated kernels: [fp16 W ; bf16 (W - fp16 W)]
             w2 = split_weights_f16(w)
         flags = (L.F_RELU if relu else 0) | (L.F_RESIDUAL if residual >= 0 else 0)
         return self.emit(L.OP_STEM_CONV if stem else L.OP_CONV, src, self.buf(), src2=residual,

@@ -51,7 +51,7 @@ def run_conv(dev, x, w, b, res, k, groups, relu, math, presplit=False):
     xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
     wd = w.permute(0, 2, 3, 1).contiguous().to(dev)
     w2 = 0
-    if presplit:                                      # [fp16 W ; bf16 W ; bf16 (W - fp16 W)], like plan.py
+    if presplit:                                      # [fp16 W ; bf16 (W - fp16 W)], like plan.py
         keep = split_weights_f16(wd)
         w2 = keep.data_ptr()
     bd = b.to(dev)
@@ -103,6 +103,24 @@ def test_conv_vs_torch_cpu(case, math):
         # exact fp32 FMA, and error-compensated 3xTF32 on arbitrary fp32 operands: both fp32-class (the TMEM
         # accumulator truncates instead of rounding, which costs ~n_mma * 2^-24 relative on long K)
         assert err < (2e-5 if math == L.MATH_FP32 else 5e-5), err
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-2, 1e-4, 3e4])
+def test_conv_tc_activation_scale(scale):
+    """The activation remainder a - fp16(a) is carried in fp16 (csrc/ptx.cuh split2_act): exact to 2^-25 absolute, so the
+    compensated product keeps its ~8e-7 for activations of ordinary scale and degrades gracefully (absolute error 2^-25 |w| per
+    product) for tiny ones; values beyond fp16's range saturate the main operand and lose precision the same graceful way.
+    Measured on B200 and asserted here: 8e-7 at scale 1, ~3e-6 at 1e-2, ~2e-4 at 1e-4 (still below one-pass tf32's 7e-4)."""
+    dev = torch.device("cuda", 0)
+    r = np.random.RandomState(5)
+    x = torch.from_numpy((scale * r.standard_normal((2, 64, 28, 28))).astype(np.float32))
+    w = torch.from_numpy((r.standard_normal((128, 64, 3, 3)) * np.sqrt(2.0 / 576)).astype(np.float32))
+    b = torch.zeros(128)
+    ref = F.conv2d(x.double(), w.double(), None, 1, 1)
+    out, path = run_conv(dev, x, w, b, None, 3, 1, False, L.MATH_TC, presplit=True)
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    print(f"activation scale {scale:g}: err {err:.2e}")
+    assert err < {1.0: 2e-6, 1e-2: 1e-5, 1e-4: 6e-4, 3e4: 1e-3}[scale], err
 
 
 def test_head_projection_is_fp32_accurate_on_tensor_cores():
