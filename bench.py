@@ -72,12 +72,34 @@ def peaks():
     if os.path.exists(u):
         d = json.load(open(u))
         out.update(tf32=d["tf32_umma_tflops_sustained"], tf32_burst=d["tf32_umma_tflops"], ffma=d["fp32_ffma_tflops_sustained"],
+                   f16=d["bf16_umma_tflops_sustained"],
                    tf32_src="measured: scripts/probes/unit_peaks_probe.cu, tcgen05.mma.kind::tf32 M128 N256 K8 on all SMs, "
-                            "sustained (profiles/r02_unit_peaks.json)")
+                            "sustained (profiles/r02_unit_peaks.json)",
+                   f16_src="measured: scripts/probes/unit_peaks_probe.cu, tcgen05.mma.kind::f16 M128 N256 K16 on all SMs, "
+                           "sustained (profiles/r02_unit_peaks.json)")
     else:
-        out.update(tf32=out["bf16_sustained"] / 2, tf32_burst=out["bf16_burst"] / 2, ffma=None,
-                   tf32_src=out["src"] + " bf16 sustained / 2 (tf32 assumed half of bf16; profiles/r02_unit_peaks.json absent)")
+        out.update(tf32=out["bf16_sustained"] / 2, tf32_burst=out["bf16_burst"] / 2, ffma=None, f16=out["bf16_sustained"],
+                   tf32_src=out["src"] + " bf16 sustained / 2 (tf32 assumed half of bf16; profiles/r02_unit_peaks.json absent)",
+                   f16_src=out["src"] + " cuBLAS bf16 sustained (profiles/r02_unit_peaks.json absent)")
     return out
+
+
+def roofline_backbone(math, useful_tflops, ms, pk):
+    """Backbone op program against the tensor peak of the MMA kind it issues.  The default mode computes every product as three
+    kind::f16 MMAs (fp16 main + two corrections), so the ISSUED rate is 3 x the algorithmic one (SURVEY 8d: count the extra
+    GEMM FLOPs against the peak of the kind used); `useful` is the algorithmic rate."""
+    r = {"kernel": "backbone op program (convs + pools + split attention), one CUDA graph", "bound": "tensor", "unit": "TFLOP/s", "ms": ms,
+         "useful": useful_tflops}
+    if math == "tc":
+        r.update(achieved=3 * useful_tflops, peak=pk["f16"], frac=3 * useful_tflops / pk["f16"], peak_source=pk["f16_src"],
+                 note="achieved = 3 x algorithmic conv FLOPs (2*MACs, SURVEY App. B): the error-compensated product issues three kind::f16 "
+                      "MMAs per product; useful = the algorithmic rate.  Per layer the binding resource is the L2 -> SM operand stream "
+                      "and shared-memory bandwidth, not the tensor pipe (DESIGN.md 3.1)")
+    else:
+        peak = pk["tf32"] if math == "tc_fast" else pk.get("ffma") or pk["tf32"]
+        r.update(achieved=useful_tflops, peak=peak, frac=useful_tflops / peak,
+                 peak_source=pk["tf32_src"] if math == "tc_fast" else "fp32 FFMA, scripts/probes/unit_peaks_probe.cu")
+    return r
 
 
 def head_traffic(cfg, batch, size):
@@ -447,7 +469,7 @@ def main():
     emit(json.dumps({
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"tc": "tf32 + 2 bf16 correction products (error-compensated, fp32-class; fp32 accumulate)", "tc_fast": "tf32", "fp32": "f32"}[a.math], "data": "synthetic",
+        "dtype": {"tc": "fp16 main + fp16/bf16 correction products on fp32 data (error-compensated, fp32-class; fp32 accumulate)", "tc_fast": "tf32", "fp32": "f32"}[a.math], "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * a.batch, "parallelism": f"dp{world}",
                    "math": a.math, "timing": "CUDA events, max over ranks; whole forward = one CUDA-graph replay; inputs "
                    "(batch + GBs of activations) larger than the 126 MB L2, no explicit flush"},
@@ -472,11 +494,7 @@ def main():
                      "timing": "CUDA events around CUDA-graph replays of 4 back-to-back launches over a ring of 4 distinct feature "
                                "buffers (inputs 411 MB > 126 MB L2: every launch reads HBM; no flush needed); ms_single_flushed = one eager "
                                "call after a 256 MB memset (dirty L2 + host launch work inside the events), the round-1 method"},
-        "roofline_backbone": {"kernel": "backbone op program (convs + pools + split attention), one CUDA graph", "bound": "tensor",
-                              "achieved": bb_tflops, "peak": pk["tf32"], "unit": "TFLOP/s", "frac": bb_tflops / pk["tf32"],
-                              "ms": ms_bb, "peak_source": pk["tf32_src"],
-                              "note": "algorithmic conv FLOPs (2*MACs, SURVEY App. B); the error-compensated product issues 2x the tf32 "
-                                      "tensor time per FLOP by construction"},
+        "roofline_backbone": roofline_backbone(a.math, bb_tflops, ms_bb, pk),
         "cpu_baseline": {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": cpu_kind,
                          "sample": f"{a.cpu_sample} images/step x {cpu_steps} steps after 2 warm-ups of the same workload "
                                    f"({'unmodified reference from baseline/_ref' if cpu_kind == 'reference' else 'oracle port of the reference'}"
