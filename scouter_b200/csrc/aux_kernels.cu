@@ -31,6 +31,26 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
     SC_PIXEL_INDEX(ROWS);
     const float* base = in + (size_t)b * H * W * C + q * 4;
     float4 m[ROWS];
+    if (k == 3 && stride == 2 && pad == 1) {
+        // the stem pool (resnet.py:420): all nine loads of a row are issued before the first max (static window, indices clamped
+        // into the map -- a clamped index repeats an element of the same window, which a maximum does not notice)
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            const int ho = ho0 + j;
+            if (ho >= Ho) continue;
+            float4 v[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int hi = min(max(ho * 2 - 1 + t / 3, 0), H - 1), wi = min(max(wo * 2 - 1 + t % 3, 0), W - 1);
+                v[t] = ld4(base + ((size_t)hi * W + wi) * C);
+            }
+            float4 a = v[0];
+#pragma unroll
+            for (int t = 1; t < 9; ++t) { a.x = fmaxf(a.x, v[t].x); a.y = fmaxf(a.y, v[t].y); a.z = fmaxf(a.z, v[t].z); a.w = fmaxf(a.w, v[t].w); }
+            *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = a;
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) m[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int r = 0; r < k; ++r)
@@ -191,10 +211,10 @@ __global__ void __launch_bounds__(256) gap_kernel(const float* __restrict__ in, 
 // out[b,ho,wo,c] = pool3x3s2p1?( x[b,h,w,c]*a0[b,c] + x[b,h,w,C+c]*a1[b,c] ), (a0,a1) = softmax over the radix pair of
 // the fc2 output `logit` (B, 2C) (split_attn.py:14-28,74-79).  The pool divisor follows avg_pool2d with
 // count_include_pad=True (resnest.py:101): 9 wherever the padded window is full.
-template <int ROWS>
+template <int ROWS, bool AVD>
 __global__ void __launch_bounds__(256) splat_apply_kernel(const float* __restrict__ in, const float* __restrict__ logit,
-                                                          float* __restrict__ out, int H, int W, int C, int Ho, int Wo, int avd,
-                                                          int round_out) {
+                                                          float* __restrict__ out, int H, int W, int C, int Ho, int Wo, int round_out) {
+    constexpr bool avd = AVD;   // compile-time: the 18-register-quad window of the pooled form must not cost the plain form occupancy
     SC_PIXEL_INDEX(ROWS);
     const float4 l0 = ld4(logit + (size_t)b * 2 * C + q * 4), l1 = ld4(logit + (size_t)b * 2 * C + C + q * 4);
     const float* base = in + (size_t)b * H * W * 2 * C + q * 4;
@@ -329,10 +349,10 @@ int launch_splat_apply(const float* in, const float* logit, float* out, int B, i
     dim3 grid;
     if (avd) {
         if (int e = pixel_grid(B, Ho, Wo, C, 2, grid)) return e;
-        splat_apply_kernel<2><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, avd, round_out);
+        splat_apply_kernel<2, true><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, round_out);
     } else {
         if (int e = pixel_grid(B, Ho, Wo, C, 4, grid)) return e;
-        splat_apply_kernel<4><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, avd, round_out);
+        splat_apply_kernel<4, false><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, round_out);
     }
     SC_LAUNCH_CHECK();
     return 0;
