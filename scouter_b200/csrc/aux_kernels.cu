@@ -274,6 +274,90 @@ __global__ void __launch_bounds__(256) splat_apply_kernel(const float* __restric
     }
 }
 
+// The pooled form (first block of layers 2-4: AvgPool2d(3, 2, padding=1) after the re-weighting, resnest.py:101,131) as a
+// rolling window down the rows: thread = (output column, channel quad) walks RC output rows; per step it loads the two new
+// input rows of the window (3 columns x 2 radix halves = 12 quads issued together) and keeps the column-summed previous
+// row, so every input element is read once per column window instead of once per overlapping 3x3 window (the window form
+// above ran at 3.4-3.8 TB/s).  Sums run column-first, then rows (the reference's order inside a window is row-major; the
+// difference is fp32 rounding of a 9-term sum).
+template <int RC>
+__global__ void __launch_bounds__(256) splat_apply_pool_kernel(const float* __restrict__ in, const float* __restrict__ logit,
+                                                               float* __restrict__ out, int H, int W, int C, int Ho, int Wo, int round_out) {
+    const int cq = C >> 2;
+    const int i_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i_ >= Wo * cq) return;
+    const int wo = i_ / cq, q = i_ - wo * cq;
+    const int b = blockIdx.z;
+    const int ho_begin = blockIdx.y * RC, ho_end = min(ho_begin + RC, Ho);
+    const float4 l0 = ld4(logit + (size_t)b * 2 * C + q * 4), l1 = ld4(logit + (size_t)b * 2 * C + C + q * 4);
+    const float* base = in + (size_t)b * H * W * 2 * C + q * 4;
+    float a0[4], a1[4];
+    {
+        const float y0[4] = {l0.x, l0.y, l0.z, l0.w}, y1[4] = {l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float mx = fmaxf(y0[j], y1[j]);
+            const float e0 = expf(y0[j] - mx), e1 = expf(y1[j] - mx);
+            const float inv = 1.f / (e0 + e1);
+            a0[j] = e0 * inv;
+            a1[j] = e1 * inv;
+        }
+    }
+    // columns of the window: 2wo-1, 2wo, 2wo+1, clipped (a clipped column is loaded from a valid address and weighted 0)
+    int wc[3];
+    float wk[3];
+#pragma unroll
+    for (int s3 = 0; s3 < 3; ++s3) {
+        const int wi = 2 * wo - 1 + s3;
+        wk[s3] = (wi >= 0 && wi < W) ? 1.f : 0.f;
+        wc[s3] = min(max(wi, 0), W - 1);
+    }
+    const int ws = 2 * wo - 1, we_p = min(ws + 3, W + 1);
+    const float wspan = (float)(we_p - ws);            // count_include_pad=True: padded columns count, columns past W+pad do not
+    // column sum of input row hi (zeros when the row is outside the map); x0*a0 + x1*a1 per pixel like the reference
+    auto load_row = [&](int hi, float4 (&u)[6]) {
+        const int hc = min(max(hi, 0), H - 1);
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+            const float* p = base + ((size_t)hc * W + wc[s3]) * 2 * C;
+            u[2 * s3] = ld4(p);
+            u[2 * s3 + 1] = ld4(p + C);
+        }
+    };
+    auto row_sum = [&](int hi, const float4 (&u)[6]) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hi < 0 || hi >= H) return r;
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) {
+            const float4 &x0 = u[2 * s3], &x1 = u[2 * s3 + 1];
+            r.x += wk[s3] * (x0.x * a0[0] + x1.x * a1[0]);
+            r.y += wk[s3] * (x0.y * a0[1] + x1.y * a1[1]);
+            r.z += wk[s3] * (x0.z * a0[2] + x1.z * a1[2]);
+            r.w += wk[s3] * (x0.w * a0[3] + x1.w * a1[3]);
+        }
+        return r;
+    };
+    float4 prev;
+    {
+        float4 u[6];
+        load_row(2 * ho_begin - 1, u);
+        prev = row_sum(2 * ho_begin - 1, u);
+    }
+    for (int ho = ho_begin; ho < ho_end; ++ho) {
+        float4 ua[6], ub[6];
+        load_row(2 * ho, ua);
+        load_row(2 * ho + 1, ub);
+        const float4 ra = row_sum(2 * ho, ua), rb = row_sum(2 * ho + 1, ub);
+        const int hs = 2 * ho - 1, he_p = min(hs + 3, H + 1);
+        const float div = (float)(he_p - hs) * wspan;
+        float4 r = make_float4((prev.x + ra.x + rb.x) / div, (prev.y + ra.y + rb.y) / div, (prev.z + ra.z + rb.z) / div,
+                               (prev.w + ra.w + rb.w) / div);
+        prev = rb;
+        if (round_out) r = round4(r);
+        *reinterpret_cast<float4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * C + q * 4) = r;
+    }
+}
+
 // f2: uint8 HWC -> normalised fp32 NCHW, fp64 arithmetic with a single rounding (reference: float64 ToTensor/Normalize,
 // then .to(float32)).  One thread = one pixel (all channels), coalesced planar stores.
 struct NormConst { double mean[4], inv255, std[4]; };
@@ -348,8 +432,14 @@ int launch_splat_apply(const float* in, const float* logit, float* out, int B, i
                        int round_out, cudaStream_t s) {
     dim3 grid;
     if (avd) {
-        if (int e = pixel_grid(B, Ho, Wo, C, 2, grid)) return e;
-        splat_apply_kernel<2, true><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, round_out);
+        static bool window_form = getenv("SCOUTER_SPLAT_POOL_WINDOW") != nullptr;   // the round-1 kernel, for A/B
+        if (window_form) {
+            if (int e = pixel_grid(B, Ho, Wo, C, 2, grid)) return e;
+            splat_apply_kernel<2, true><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, round_out);
+        } else {
+            if (int e = pixel_grid(B, Ho, Wo, C, 7, grid)) return e;
+            splat_apply_pool_kernel<7><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, round_out);
+        }
     } else {
         if (int e = pixel_grid(B, Ho, Wo, C, 4, grid)) return e;
         splat_apply_kernel<4, false><<<grid, 256, 0, s>>>(in, logit, out, H, W, C, Ho, Wo, round_out);
