@@ -137,7 +137,8 @@ int scouter_vis_upsample_u8(const uint8_t* maps /* (count,h,w) */, int count, in
 #define SCOUTER_LAYOUT_NCHW 1 /* (B, ch, h*w): the reference backbone's flattened output (slot_model.py:108) */
 
 #define SCOUTER_MATH_FP32 0    /* CUDA-core fp32 FMA everywhere (exact mode) */
-#define SCOUTER_MATH_TC 1      /* tcgen05 tensor cores, error-compensated 3xTF32 (fp32-class results; default) */
+#define SCOUTER_MATH_TC 1      /* tcgen05 tensor cores, error-compensated products on fp32 data (convs: fp16 main + two 16-bit
+                                  corrections; head: tf32 main + bf16 corrections) -- fp32-class results; default */
 #define SCOUTER_MATH_TC_FAST 2 /* tcgen05 tensor cores, single tf32 pass on tf32-rounded activations/weights
                                   (cuDNN-TF32 class accuracy: ~3e-3 on the log-probs; opt-in) */
 

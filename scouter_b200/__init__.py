@@ -21,7 +21,7 @@ __all__ = ["SlotModel", "SlotAttention", "ScouterAttention", "load_backbone", "I
 
 
 def default_math() -> int:
-    """SCOUTER_MATH=tc (default): tcgen05 tensor cores, error-compensated 3xTF32 (fp32-class results);
+    """SCOUTER_MATH=tc (default): tcgen05 tensor cores, error-compensated products on fp32 data (fp32-class results);
     fp32: exact CUDA-core kernels; tc_fast: single-pass tf32 (cuDNN-TF32-class accuracy)."""
     v = os.environ.get("SCOUTER_MATH", "tc").lower()
     table = {"fp32": MATH_FP32, "tc": MATH_TC, "tc_fast": MATH_TC_FAST}
