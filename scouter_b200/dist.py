@@ -70,7 +70,10 @@ class GradientBuckets:
     about ``bucket_bytes``; ``mark_ready(name)`` launches the asynchronous all-reduce of a bucket as soon as its last
     gradient is in, ``finish()`` launches what is left, waits and turns the sums into means.  With NCCL each all-reduce
     is stream-ordered after the kernels already enqueued on the current stream; with gloo (CPU tests) it is a host
-    call.  Unused parameters (``slot.to_q.*``; ``find_unused_parameters=True`` in the reference) simply stay zero."""
+    call.  Unused parameters (``slot.to_q.*``; ``find_unused_parameters=True`` in the reference) and frozen ones never get
+    ``mark_ready``: their gradient stays zero for the exchange, and ``ready_ranges`` leaves them OUT of the optimizer pass --
+    the reference builds ``params = [p for p in ... if p.requires_grad]`` (train.py:145) and ``torch.optim.AdamW`` skips
+    ``grad is None``, so those tensors receive neither weight decay nor Adam state."""
 
     def __init__(self, named_shapes, device="cpu", bucket_bytes: int = 25 << 20):
         self.device = torch.device(device)
@@ -89,7 +92,7 @@ class GradientBuckets:
             cur_bytes += 4 * numel
         if cur:
             plan.append(cur)
-        self.flat, self.views, self.bucket_of, self._members = [], {}, {}, []
+        self.flat, self.views, self.bucket_of, self._members, self._layout = [], {}, {}, [], []
         for b, members in enumerate(plan):
             flat = torch.zeros(sum(m[2] for m in members), dtype=torch.float32, device=self.device)
             off = 0
@@ -99,9 +102,11 @@ class GradientBuckets:
                 off += numel
             self.flat.append(flat)
             self._members.append({m[0] for m in members})
+            self._layout.append([(m[0], m[2]) for m in members])
         self._pending = [set(m) for m in self._members]
         self._work = [None] * len(self.flat)
         self._launched = [False] * len(self.flat)
+        self._written = set()
 
     def grad(self, name: str) -> torch.Tensor:
         """The gradient view of one parameter (aliases the bucket's flat buffer)."""
@@ -114,6 +119,7 @@ class GradientBuckets:
         self._pending = [set(m) for m in self._members]
         self._work = [None] * len(self.flat)
         self._launched = [False] * len(self.flat)
+        self._written = set()
 
     def _launch(self, b: int):
         if self._launched[b]:
@@ -128,6 +134,7 @@ class GradientBuckets:
         if self._launched[b]:
             raise RuntimeError(f"GradientBuckets: {name} marked ready after its bucket was reduced (missing zero_()?)")
         self._pending[b].discard(name)
+        self._written.add(name)
         if not self._pending[b]:
             self._launch(b)
 
@@ -141,6 +148,20 @@ class GradientBuckets:
                 w.wait()
             if world > 1:
                 self.flat[b].mul_(1.0 / world)
+
+    def ready_ranges(self, b: int):
+        """[(offset, numel)] of bucket ``b``: maximal runs of parameters that received a gradient this step (``mark_ready``).
+        The optimizer pass runs over these ranges only -- parameters without a gradient (unused, frozen) are not decayed and
+        get no Adam state, like ``torch.optim.AdamW`` with ``grad is None``.  Every rank marks the same set."""
+        out, off = [], 0
+        for name, numel in self._layout[b]:
+            if name in self._written:
+                if out and out[-1][0] + out[-1][1] == off:
+                    out[-1] = (out[-1][0], out[-1][1] + numel)
+                else:
+                    out.append((off, numel))
+            off += numel
+        return out
 
     @property
     def total_bytes(self) -> int:

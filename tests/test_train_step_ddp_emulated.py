@@ -72,20 +72,28 @@ def _worker(rank, world, port, out):
     for n, _ in names:
         pb.grad(n).copy_(sd[n])
     opt = torch.optim.AdamW(list(params.values()), lr=1e-4)             # train.py:146
-    for n, _ in names:
-        params[n].grad = gb.grad(n).clone()                             # identical gradients on both sides
+    for n, _ in names:                                                  # identical gradients on both sides; parameters the
+        params[n].grad = gb.grad(n).clone() if refs[0][n] is not None else None   # backward never reached keep grad = None
     opt.step()
     lib = E.lib()
     d = opt.defaults
     b1, b2 = d["betas"]
     _f = C.POINTER(C.c_float)
-    for flat_p, flat_g in zip(pb.flat, gb.flat):
-        pn, gn = flat_p.numpy(), flat_g.numpy()
-        mom, var = np.zeros_like(pn), np.zeros_like(pn)
-        a = AdamArgs(decay=1 - 1e-4 * d["weight_decay"], one_minus_beta1=1 - b1, beta2=b2, one_minus_beta2=1 - b2, eps=d["eps"],
-                     step_size=1e-4 / (1 - b1), bias_correction2_sqrt=math.sqrt(1 - b2), n=pn.size, p=pn.ctypes.data_as(_f),
-                     g=gn.ctypes.data_as(_f), m=mom.ctypes.data_as(_f), v=var.ctypes.data_as(_f))
-        lib.adamw_host(C.byref(a))
+    skipped = 0
+    for b, (flat_p, flat_g) in enumerate(zip(pb.flat, gb.flat)):
+        mom_b, var_b = np.zeros(flat_p.numel(), np.float32), np.zeros(flat_p.numel(), np.float32)
+        skipped += flat_p.numel() - sum(k for _, k in gb.ready_ranges(b))
+        for off, k in gb.ready_ranges(b):                              # only what received a gradient (train.py:145, AdamW: grad is None)
+            pn, gn = flat_p.numpy()[off:off + k], flat_g.numpy()[off:off + k]
+            mom, var = mom_b[off:off + k], var_b[off:off + k]
+            a = AdamArgs(decay=1 - 1e-4 * d["weight_decay"], one_minus_beta1=1 - b1, beta2=b2, one_minus_beta2=1 - b2, eps=d["eps"],
+                         step_size=1e-4 / (1 - b1), bias_correction2_sqrt=math.sqrt(1 - b2), n=k, p=pn.ctypes.data_as(_f),
+                         g=gn.ctypes.data_as(_f), m=mom.ctypes.data_as(_f), v=var.ctypes.data_as(_f))
+            lib.adamw_host(C.byref(a))
+    assert skipped == sum(sd[n].numel() for n, _ in names if refs[0][n] is None) > 0     # slot.to_q.*: no decay, no Adam state
+    for n, _ in names:
+        if refs[0][n] is None:
+            assert torch.equal(pb.grad(n), sd[n]) and torch.equal(params[n].detach(), sd[n])
     worst = max(float((pb.grad(n) - params[n].detach()).abs().max()) for n, _ in names)
     assert worst <= 2e-7, worst
     moved = max(float((pb.grad(n) - sd[n]).abs().max()) for n, _ in names)
