@@ -180,7 +180,9 @@ class TrainEngine:
         grads = {}
         z = lambda p: torch.zeros(p.shape, **f32)
         need_backbone = any(p.requires_grad for p in m.backbone.parameters())
-        d_feat = torch.zeros(B, n, ch, **f32)
+        # the two ch-sized products of the head backward (d feat = d pre . W and d W = d pre^T . feat, ch = 2048) leave the
+        # one-CTA-per-image kernel: it hands d pre (B, n, 64) over and the GEMMs run on the conv kernels below
+        d_pre = torch.empty(B, n, 64, **f32)
         g = {"conv1x1.weight": z(m.conv1x1.weight), "conv1x1.bias": z(m.conv1x1.bias),
              "slot.gru.weight_ih_l0": z(m.slot.gru.weight_ih_l0), "slot.gru.weight_hh_l0": z(m.slot.gru.weight_hh_l0),
              "slot.gru.bias_ih_l0": z(m.slot.gru.bias_ih_l0), "slot.gru.bias_hh_l0": z(m.slot.gru.bias_hh_l0),
@@ -190,7 +192,7 @@ class TrainEngine:
                           w_ih=m.slot.gru.weight_ih_l0.data_ptr(), w_hh=m.slot.gru.weight_hh_l0.data_ptr(),
                           b_ih=m.slot.gru.bias_ih_l0.data_ptr(), b_hh=m.slot.gru.bias_hh_l0.data_ptr(),
                           slots0=m.slot.initial_slots.data_ptr(), g_logits=g_logits.data_ptr(), attn_coef=coef.data_ptr(),
-                          d_feat=d_feat.data_ptr(), d_pre=0, g_conv_w=g["conv1x1.weight"].data_ptr(), g_conv_b=g["conv1x1.bias"].data_ptr(),
+                          d_feat=0, d_pre=d_pre.data_ptr(), g_conv_w=g["conv1x1.weight"].data_ptr(), g_conv_b=g["conv1x1.bias"].data_ptr(),
                           g_w_ih=g["slot.gru.weight_ih_l0"].data_ptr(), g_w_hh=g["slot.gru.weight_hh_l0"].data_ptr(),
                           g_b_ih=g["slot.gru.bias_ih_l0"].data_ptr(), g_b_hh=g["slot.gru.bias_hh_l0"].data_ptr(),
                           g_slots0=g["slot.initial_slots"].data_ptr())
@@ -202,9 +204,22 @@ class TrainEngine:
         scratch = torch.empty(B * per, **f32)
         a.scratch, a.scratch_per_image = scratch.data_ptr(), per
         L.check(lib.scouter_train_head_backward(C.byref(a), st), "scouter_train_head_backward")
+        # d conv1x1.weight (64, ch) = d pre^T . feat: the weight gradient of a 1x1 conv ch -> 64 on the (B, fh, fw) map
+        wa = L.WgradArgs(B=B, H=fh, W=fw, Cin=ch, Ho=fh, Wo=fw, Cout=64, k=1, stride=1, pad=0, groups=1, x=feat.data_ptr(),
+                         dy=d_pre.data_ptr(), dw=g["conv1x1.weight"].data_ptr(), db=0)
+        L.check(lib.scouter_train_conv_wgrad(C.byref(wa), st), "scouter_train_conv_wgrad(conv1x1)")
         grads.update(g)
         if not need_backbone:
             return grads
+        # d feat (B, n, ch) = d pre . W: a 1x1 conv 64 -> ch with the transposed weights, on the forward tcgen05 kernel
+        math_mode = m._math()
+        wt = m.conv1x1.weight.detach().reshape(64, ch).t().contiguous()                # (ch, 64) = OHWI (ch, 1, 1, 64)
+        wt2 = split_weights_f16(wt) if math_mode == L.MATH_TC else None
+        d_feat = torch.empty(B, n, ch, **f32)
+        op = L.Op(kind=L.OP_CONV, src=0, src2=-1, dst=1, cin=64, cout=ch, kh=1, kw=1, stride=1, pad=0, groups=1, flags=0, mid=0,
+                  reserved=0, w=wt.data_ptr(), b=0, w2=_p(wt2), b2=0)
+        L.check(lib.scouter_conv_forward(C.byref(op), d_pre.data_ptr(), 0, d_feat.data_ptr(), B, fh, fw, math_mode, st),
+                "scouter_conv_forward(d feat)")
         # ---- backbone: the reverse schedule ------------------------------------------------------------------
         d = {self.feat: d_feat.reshape(B, fh, fw, ch)}
 
