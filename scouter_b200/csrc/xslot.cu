@@ -107,7 +107,10 @@ __global__ void xslot_pack_kernel(scouter_xslot_desc_t d, float* __restrict__ ou
 // (CUB-200 x 2 slots) fits: pass 1 gets every row sum r_i and the total t, pass 2 re-derives the
 // chunk's dots (only when there is more than one chunk), forms the attention, the update and the GRU.
 // ------------------------------------------------------------------------------------------------
-constexpr int NT = 256, NW = NT / 32, NRG = NT / XD;
+#ifndef SCOUTER_XSLOT_NT
+#define SCOUTER_XSLOT_NT 512
+#endif
+constexpr int NT = SCOUTER_XSLOT_NT, NW = NT / 32, NRG = NT / XD;
 constexpr int LDX = XD + 4;
 
 // Kb holds the MLP ping-pong buffer first and {dots[SC][n] (rounded up to 4 floats), upd[SC][64]} afterwards.
