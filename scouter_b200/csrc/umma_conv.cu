@@ -3,13 +3,14 @@
 //   D[M = B*H*W, N = Cout/groups] = A[M, K = kh*kw*Cin/groups] * W[N, K]^T     (stride 1, 1x1 or 3x3 pad 1)
 //
 // * Two precisions of the same kernel (template SPLIT):
-//     SPLIT=true  (SCOUTER_MATH_TC, default): error-compensated 16-bit product.  x = h + r with h = fp16(x) (rounded,
-//       11-bit significand, saturating) and r = x - h, exact in fp32 and ~2^-12 |x|.  The issuer accumulates, in the fp32
-//       TMEM accumulator,  A_h*W_h (fp16 x fp16) + A_b*W_r + A_r*W_b (bf16 x bf16: bf16 keeps fp32's exponent range for the
-//       small terms) as 2 + 2 + 2 kind::f16 MMAs (K = 16) per 32-channel k-block.  Four splitter warps derive A_h / A_b /
-//       A_r from the TMA-written fp32 tile; weights come pre-split from the host ([fp16 W_h ; bf16 W ; bf16 W_r]) or are
-//       split in the kernel.  Operands stay plain fp32 in HBM.  Round 1 ran the main product as kind::tf32 on trunc19(x)
-//       (4 MMAs of K = 8 + 2 + 2 bf16 corrections): 8 MMA times per k-block against 6 now.
+//     SPLIT=true  (SCOUTER_MATH_TC, default): error-compensated 16-bit product (ptx.cuh split2_act / split2_wgt).  x = h + r
+//       with h = fp16(x) (rounded, 11-bit significand, saturating) and r = x - h, exact in fp32 and ~2^-12 |x|.  The issuer
+//       accumulates, in the fp32 TMEM accumulator,
+//           A_b*W_r (bf16 x bf16)  +  A_r*W_h  +  A_h*W_h (fp16 x fp16)         2 + 2 + 2 kind::f16 MMAs (K = 16) per k-block
+//       with A_b = bf16(a), A_r = fp16(a - a_h), W_r = bf16(w - w_h).  Four splitter warps derive A_h / A_b / A_r from the
+//       TMA-written fp32 tile; weights come pre-split from the host ([fp16 W_h ; bf16 W_r]) or are split in the kernel.
+//       Operands stay plain fp32 in HBM.  Round 1 ran the main product as kind::tf32 on trunc19(x) (4 MMAs of K = 8 + 2 + 2
+//       bf16 corrections): 8 MMA times per k-block against 6 now.
 //     SPLIT=false (SCOUTER_MATH_TC_FAST): one tf32 MMA; producers round stored activations with cvt.rna and
 //       weights are pre-rounded on the host, so the MMA multiplies exactly the stored values (cuDNN-TF32 class).
 // * No im2col buffer: for a 3x3 conv the K loop walks the 9 taps and each tap is ONE 4-D TMA box load
@@ -18,7 +19,7 @@
 //   layout, i.e. a K-major UMMA operand tile of 128 rows x 32 tf32.
 // * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
 //   thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> bias/residual/ReLU -> global),
-//   warps 8-11 = operand splitters (SPLIT only).  smem ring of STAGES {A 16 KB, B BN*128 B [, A_r, B_r]}; two TMEM
+//   warps 8-11 = operand splitters (SPLIT only).  smem ring of STAGES {A 16 KB, W [, the 16-bit tiles]} (TS: see Cfg); two TMEM
 //   accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Reference ops replaced: the nn.Conv2d+BatchNorm2d(+ReLU)(+residual) chains of timm/models/resnest.py:111-143,

@@ -88,7 +88,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int pslot = p.patch_alloc / 2 * 5;                     // one patch stage: [raw fp32 | fp16 A_h | bf16 A_b | bf16 A_r]
     uint8_t* patch0 = smem;
-    uint8_t* bt0 = smem + p.pst * pslot;                         // bst x [W_h | W_b | W_r]
+    uint8_t* bt0 = smem + p.pst * pslot;                         // bst x [W_h | W_r]
     uint8_t* out_stage = bt0 + p.bst * C::B_STAGE;               // [EPI_GROUPS][2][OUT_STAGE], 1024-aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + C::OUT_BYTES);
     uint64_t* pfull = bars;                  // [MAX_ST] patch landed (TMA)
