@@ -44,6 +44,8 @@ struct scouter_plan {
     size_t scratch_off = 0;  // shared scratch at the end of the arena (split-attention GAP partial sums)
     int launches = 0;
     std::vector<UmmaConvPlan> umma;  // per op; .valid says whether the tcgen05 kernel takes it
+    std::vector<int> gap_slots;      // per op: > 0 on a conv whose epilogue writes the GAP partial sums of the SPLAT_GAP op that
+                                     // follows it, and on that SPLAT_GAP op (which then only runs the finish kernel)
     std::vector<std::vector<float>> host_w, host_b;  // per op: host copies of small stem filter banks
 };
 
@@ -207,13 +209,30 @@ extern "C" int scouter_plan_bind(scouter_plan_t* plan, int batch, int cin, int h
     }
     size_t scratch = 0;
     int launches = 0;
+    plan->gap_slots.assign(n_ops, 0);
+    static const bool no_gap_fuse = getenv("SCOUTER_NO_GAP_FUSE") != nullptr;
     for (int i = 0; i < n_ops; ++i) {
         const scouter_op_t& o = plan->ops[i];
         ++launches;
         if (o.kind == SCOUTER_OP_SPLAT_GAP) {
             const Buf& sb = plan->bufs[o.src];
-            scratch = std::max(scratch, (size_t)sb.B * splat_gap_splits(sb.B, sb.H * sb.W) * 2 * o.cout * sizeof(float));
-            ++launches;  // partial + finish
+            // the conv right before it writes this buffer: if the halo kernel takes it, its epilogue delivers the partial sums
+            int slots = 0;
+            if (i > 0 && !no_gap_fuse && plan->math == SCOUTER_MATH_TC && plan->ops[i - 1].kind == SCOUTER_OP_CONV &&
+                plan->ops[i - 1].dst == o.src && !(plan->ops[i - 1].flags & SCOUTER_F_TF32_1PASS) && plan->ops[i - 1].w2) {
+                const scouter_op_t& c = plan->ops[i - 1];
+                const Buf& cb = plan->bufs[c.src];
+                ConvArgs a{nullptr, c.w, c.b, nullptr, nullptr, cb.B, cb.H, cb.W, cb.C, sb.H, sb.W, sb.C, c.kh, c.kw, c.stride, c.pad,
+                           c.groups, (c.flags & SCOUTER_F_RELU) ? 1 : 0, 0, 1, c.w2};
+                slots = halo_gap_slots(a);
+            }
+            if (slots > 0) {
+                plan->gap_slots[i - 1] = plan->gap_slots[i] = slots;
+                scratch = std::max(scratch, (size_t)sb.B * slots * 2 * o.cout * sizeof(float));
+            } else {
+                scratch = std::max(scratch, (size_t)sb.B * splat_gap_splits(sb.B, sb.H * sb.W) * 2 * o.cout * sizeof(float));
+                ++launches;  // partial + finish
+            }
         }
     }
     plan->scratch_off = high;
@@ -274,6 +293,10 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
                 ConvArgs a{ptr(o.src), o.w, o.b, (o.flags & SCOUTER_F_RESIDUAL) ? ptr(o.src2) : nullptr, ptr(o.dst),
                            sb.B, sb.H, sb.W, sb.C, db.H, db.W, db.C, o.kh, o.kw, o.stride, o.pad, o.groups,
                            (o.flags & SCOUTER_F_RELU) ? 1 : 0, (rnd && db.H * db.W > 1) ? 1 : 0, split, split ? o.w2 : nullptr};
+                if (plan->gap_slots[i] > 0) {   // this conv's epilogue also writes the GAP partial sums of the next op
+                    a.gap_part = (float*)(base + plan->scratch_off);
+                    a.gap_slots = plan->gap_slots[i];
+                }
                 if (plan->math != SCOUTER_MATH_FP32 && tc_conv_supported(a)) rc = launch_conv_tc(a, plan->umma[i], s);
                 else rc = launch_conv_simt(a, s);
                 break;
@@ -286,7 +309,10 @@ extern "C" int scouter_plan_run(scouter_plan_t* plan, const float* input_nchw, v
                                     (o.flags & SCOUTER_F_COUNT_INCLUDE_PAD) ? 1 : 0, rnd, s);
                 break;
             case SCOUTER_OP_SPLAT_GAP:
-                rc = launch_splat_gap(ptr(o.src), (float*)(base + plan->scratch_off), ptr(o.dst), sb.B, sb.H * sb.W, o.cout, s);
+                if (plan->gap_slots[i] > 0)
+                    rc = launch_splat_gap_finish((float*)(base + plan->scratch_off), ptr(o.dst), sb.B, sb.H * sb.W, o.cout, plan->gap_slots[i], s);
+                else
+                    rc = launch_splat_gap(ptr(o.src), (float*)(base + plan->scratch_off), ptr(o.dst), sb.B, sb.H * sb.W, o.cout, s);
                 break;
             case SCOUTER_OP_SPLAT_APPLY:
                 rc = launch_splat_apply(ptr(o.src), ptr(o.src2), ptr(o.dst), sb.B, sb.H, sb.W, o.cout, db.H, db.W,

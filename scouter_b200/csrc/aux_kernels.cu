@@ -409,6 +409,12 @@ int splat_gap_splits(int B, int HW) {
     return std::min(n, 64);
 }
 
+int launch_splat_gap_finish(const float* part, float* gap, int B, int HW, int C, int nslots, cudaStream_t s) {
+    splat_gap_finish_kernel<<<cdiv(B * C, 256), 256, 0, s>>>(part, gap, B, C, nslots, 1.0f / (float)HW);
+    SC_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_splat_gap(const float* in, float* part, float* gap, int B, int HW, int C, cudaStream_t s) {
     SC_CHECK_ARG(C % 2 == 0 && (2 * C / 4) <= 256 && 256 % (2 * C / 4) == 0, SCOUTER_E_UNSUPPORTED,
                  "splat gap: C = %d (2C/4 must divide 256)", C);

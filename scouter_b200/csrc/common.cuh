@@ -74,9 +74,11 @@ struct ConvArgs {
     float* out;         // NHWC (B,Ho,Wo,Cout)
     int B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, groups, relu;
     int round_out;  // round the stored activations to tf32 (SCOUTER_MATH_TC: the next conv's MMA reads them as tf32)
-    int split;      // tcgen05 only: error-compensated 3xTF32 (operands split into trunc19 + remainder)
-    const void* w_rem;   // optional host-pre-split correction weights: bf16 [W ; W - trunc19(W)], (2*Cout, kh, kw, Cin/g)
+    int split;      // tcgen05 only: error-compensated product (operands split into fp16 + remainder)
+    const void* w_rem;   // optional host-pre-split 16-bit weights [fp16 W ; bf16 (W - fp16 W)], (2*Cout, kh, kw, Cin/g)
     int ksplit;          // tcgen05 flat kernel only: > 1 writes `ksplit` raw partial-sum slabs (M*Cout floats apart) to out
+    float* gap_part;     // halo kernel only, optional: per-(image, tile, epilogue warp) column sums of the stored output,
+    int gap_slots;       //   (B, gap_slots, Cout) -- the split-attention GAP's partial sums (split_attn.py:64-66), see halo_gap_slots()
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 
@@ -101,6 +103,8 @@ int launch_avgpool(const float* in, float* out, int B, int H, int W, int C, int 
                    int pad, int count_include_pad, int round_out, cudaStream_t s);
 int splat_gap_splits(int B, int HW);  // pixel slices of the split-attention GAP (workspace = B * splits * 2C floats)
 int launch_splat_gap(const float* in, float* part, float* gap, int B, int HW, int C /*per radix*/, cudaStream_t s);
+// finish only: `part` (B, nslots, 2C) was written by the producing conv's epilogue (ConvArgs::gap_part)
+int launch_splat_gap_finish(const float* part, float* gap, int B, int HW, int C /*per radix*/, int nslots, cudaStream_t s);
 int launch_splat_apply(const float* in, const float* logit, float* out, int B, int H, int W, int C, int Ho, int Wo,
                        int avd, int round_out, cudaStream_t s);
 int launch_gap(const float* in, float* out, int B, int HW, int C, cudaStream_t s);

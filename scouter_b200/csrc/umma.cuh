@@ -29,6 +29,8 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s);
 // 3x3 from one halo tile per channel block (umma_halo.cu); needs a.split and a.w_rem
 bool halo_conv_supported(const ConvArgs& a);
 int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s);
+// slots per image of ConvArgs::gap_part when the halo kernel takes this conv (tiles per image x 4 epilogue warps), else 0
+int halo_gap_slots(const ConvArgs& a);
 // dispatch: halo kernel when it applies, else the tap-reload / flat kernel
 inline bool tc_conv_supported(const ConvArgs& a) { return halo_conv_supported(a) || umma_conv_supported(a); }
 inline int launch_conv_tc(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {

@@ -58,6 +58,8 @@ struct HaloArgs {
     int pst, bst;      // ring depths
     int chunk;         // k-steps (cb,tap pairs) per accumulation chunk
     int tma_store;     // epilogue leaves through swizzled staging + 4-D TMA stores (box {16 ch, Wb, Hb, 1})
+    float* gap_part;   // optional (B, gap_slots, Cout): column sums of the stored tile per epilogue warp (slot = tile-in-image * 4 + q)
+    int gap_slots;
     int wres;          // FOLD: the weights of one (group, n-tile) stay RESIDENT in shared memory (bst = cblocks*3 stages, loaded
                        // when the key changes) -- streamed per tile they are 108 KB from L2 against a 20 KB patch (L2-bound)
 };
@@ -363,6 +365,32 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < C::NC; ++j) acc[j] = fmaxf(acc[j], 0.f);
             }
+            if (p.gap_part) {
+                // Split-attention GAP partial sums (split_attn.py:64-66) while the tile is in registers: per 32 columns a
+                // butterfly over the warp's 32 rows (31 shuffles: each step halves the columns a lane holds) leaves lane l with
+                // the sum of column l.  Fixed order; the finish kernel adds the slots in order.  Rows outside the image add 0.
+                if constexpr (C::NC % 32 == 0) {
+                    const int mt_img = ((t / p.n_tiles) % p.m_tiles) % (p.tw * p.th);
+                    float* gp = p.gap_part + ((size_t)b * p.gap_slots + mt_img * 4 + q) * p.Cout + ch0 + lane;
+#pragma unroll
+                    for (int c = 0; c < C::NC / 32; ++c) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = valid ? acc[c * 32 + j] : 0.f;
+#pragma unroll
+                        for (int off = 16, nn = 32; off >= 1; off >>= 1, nn >>= 1) {
+                            const bool upper = (lane & off) != 0;
+#pragma unroll
+                            for (int j = 0; j < nn / 2; ++j) {
+                                const float send = upper ? v[j] : v[j + nn / 2];
+                                const float keep = upper ? v[j + nn / 2] : v[j];
+                                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                        gp[c * 32] = v[0];
+                    }
+                }
+            }
             if (p.tma_store) {
                 // 16 columns of every tile pixel go through a swizzled staging buffer (rows = compact pixel index
                 // hb*Wb + wb, the order of the TMA box) and leave as one 4-D bulk tensor store; pixels outside the
@@ -480,6 +508,18 @@ int launch_halo_bn(const CUtensorMap& tA, const CUtensorMap& tB2, const CUtensor
 
 }  // namespace
 
+int halo_gap_slots(const ConvArgs& a) {
+    if (!halo_conv_supported(a)) return 0;
+    const int BN = halo_bn(a.Cout / a.groups);
+    static bool no_fold = getenv("SCOUTER_HALO_NO_FOLD") != nullptr;
+    const bool fold = BN <= 64 && !no_fold && a.W >= 14 && a.H >= 8;
+    if (BN == 32) return 0;                       // the shuffle reduction works on 32-column groups per thread
+    int wb, hb;
+    choose_halo_tile(a.H, a.W, wb, hb);
+    if (fold) { wb = 14; hb = 8; }
+    return cdiv(a.W, wb) * cdiv(a.H, hb) * 4;
+}
+
 bool halo_conv_supported(const ConvArgs& a) {
     static bool off = getenv("SCOUTER_NO_HALO") != nullptr;
     if (off || !a.split || !a.w_rem) return false;
@@ -502,6 +542,9 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     HaloArgs u;
     u.bias = a.bias; u.res = a.res; u.out = a.out;
     u.B = a.B; u.H = a.H; u.W = a.W;
+    u.gap_part = a.gap_part; u.gap_slots = a.gap_slots;
+    SC_CHECK_ARG(!a.gap_part || a.gap_slots == halo_gap_slots(a), SCOUTER_E_INVALID, "conv_halo: gap_slots=%d, this geometry has %d",
+                 a.gap_slots, halo_gap_slots(a));
     choose_halo_tile(a.H, a.W, u.Wb, u.Hb);
     // narrow outputs: taps folded into N (see the header); fixed 14 x 8 tiles = 8 patch lines of 16 rows
     static bool no_fold = getenv("SCOUTER_HALO_NO_FOLD") != nullptr;
