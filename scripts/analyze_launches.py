@@ -51,7 +51,8 @@ for op in prog.ops:
     elif kind == L.OP_SPLAT_GAP:
         Ho, Wo, Co = 1, 1, op.cout
         flops, byts = 0, 4.0 * B * H * W * C
-        nk = 2
+        # two kernels (partial + finish), or the finish kernel alone when the producing conv's epilogue wrote the partial sums
+        nk = 2 if (li < len(launches) and "partial" in launches[li][0]) else 1
     elif kind == L.OP_SPLAT_APPLY:
         avd = bool(op.flags & L.F_AVD_POOL)
         Ho, Wo, Co = ((H + 1) // 2, (W + 1) // 2, op.cout) if avd else (H, W, op.cout)
@@ -68,5 +69,6 @@ for op in prog.ops:
             li += 1
     tot += us
     kn = {1: "stem", 2: "conv", 3: "maxpool", 4: "avgpool", 5: "splat_gap", 7: "splat_apply", 8: "gap", 9: "to_nchw"}.get(kind, str(kind))
-    print(f"{kn:12s} {str((H, W, C)):>18s} {str((Ho, Wo, Co)):>18s} {k} {s} {op.groups} {us:8.1f} {byts / us / 1e3:7.0f} {flops / us / 1e6:7.1f}  {','.join(names)}")
+    us_ = max(us, 1e-9)
+    print(f"{kn:12s} {str((H, W, C)):>18s} {str((Ho, Wo, Co)):>18s} {k} {s} {op.groups} {us:8.1f} {byts / us_ / 1e3:7.0f} {flops / us_ / 1e6:7.1f}  {','.join(names)}")
 print("backbone total us", round(tot), "| remaining launches:", [(n[:24], round(v, 1)) for n, v in launches[li:]])
