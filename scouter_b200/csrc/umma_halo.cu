@@ -71,8 +71,12 @@ struct HCfg {
     static constexpr int STEPS = FOLD ? 3 : 9;      // k-steps (weight stages) per channel block: kernel rows / taps
     static constexpr int B_TILE = NB * 64;          // one 16-bit weight tile: NB rows x 64 bytes
     static constexpr int B_STAGE = 2 * B_TILE;      // [fp16 W_h | bf16 W_r]
-    static constexpr int TMEM_COLS = 2 * NB <= 32 ? 32 : (2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512)));
-    static constexpr int BUF_COLS = TMEM_COLS / 2;  // column stride of the two accumulator buffers (a power of two >= NB)
+    static constexpr int BUF_COLS = NB <= 32 ? 32 : (NB <= 64 ? 64 : (NB <= 128 ? 128 : 256));   // column stride of the accumulator buffers
+    // Accumulator buffers (one per accumulation chunk in flight).  Four where tensor memory allows: the store phase of a tile
+    // takes ~3.4k clk during which the issuer can only run NBUF chunks ahead -- with two buffers of 2 k-steps it stalled on
+    // `cempty` for 30 % of its time (role profile, layer2.0 conv2).
+    static constexpr int NBUF = 4 * BUF_COLS <= 512 ? 4 : 2;
+    static constexpr int TMEM_COLS = NBUF * BUF_COLS < 32 ? 32 : NBUF * BUF_COLS;
     static constexpr int EPI_GROUPS = (BN == 128 || FOLD) ? 2 : 1;   // FOLD: 3*BN accumulator columns + shuffles per output row
     static constexpr int NC = BN / EPI_GROUPS;
     static constexpr int MAX_ST = 8;
@@ -98,9 +102,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* pempty = pready + C::MAX_ST;   // [MAX_ST] all MMAs that read the patch retired
     uint64_t* bfull = pempty + C::MAX_ST;    // [MAX_ST]
     uint64_t* bempty = bfull + C::MAX_ST;    // [MAX_ST]
-    uint64_t* cfull = bempty + C::MAX_ST;    // [2]
-    uint64_t* cempty = cfull + 2;            // [2]
-    uint64_t* wfull = cempty + 2;            // resident weights landed
+    uint64_t* cfull = bempty + C::MAX_ST;    // [<= 4] accumulator chunk complete
+    uint64_t* cempty = cfull + 4;            // [<= 4]
+    uint64_t* wfull = cempty + 4;            // resident weights landed
     uint64_t* wempty = wfull + 1;            // every MMA that read the resident weights retired (before a reload)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wempty + 1);
 
@@ -117,7 +121,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(&bfull[i], 1);
             mbar_init(&bempty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < C::NBUF; ++i) {
             mbar_init(&cfull[i], 1);
             mbar_init(&cempty[i], 128 * C::EPI_GROUPS);
         }
@@ -245,8 +249,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     PROF_T(pready, mbar_wait_a(pready_a + 8 * ps, pphase));
 #pragma unroll
                     for (int tap = 0; tap < C::STEPS; ++tap) {
-                        const uint32_t buf = cc & 1;
-                        if (in_chunk == 0) PROF_T(cempty, mbar_wait_a(cempty_a + 8 * buf, ((cc >> 1) & 1) ^ 1));
+                        const uint32_t buf = cc % C::NBUF;
+                        if (in_chunk == 0) PROF_T(cempty, mbar_wait_a(cempty_a + 8 * buf, ((cc / C::NBUF) & 1) ^ 1));
                         if (!wres) PROF_T(bfull, mbar_wait_a(bfull_a + 8 * bs, bphase));
                         tc_fence_after();
                         const uint32_t r = FOLD ? tap : tap / 3, sx = FOLD ? 0 : tap % 3;   // immediates after unrolling
@@ -317,8 +321,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 acc[4 * j] = v.x; acc[4 * j + 1] = v.y; acc[4 * j + 2] = v.z; acc[4 * j + 3] = v.w;
             }
             for (int ch = 0; ch < nchunks; ++ch, ++cc) {
-                const int buf = cc & 1;
-                PROF_T(cfull, mbar_wait(&cfull[buf], (cc >> 1) & 1));
+                const int buf = cc % C::NBUF;
+                PROF_T(cfull, mbar_wait(&cfull[buf], (cc / C::NBUF) & 1));
                 tc_fence_after();
                 if constexpr (FOLD) {
                     // out[m] = sum_s D[m + s, block s]: lane m takes block s from lane m + s of its own warp (a patch line is 16
