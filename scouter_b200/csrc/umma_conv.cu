@@ -763,7 +763,7 @@ int launch_conv_umma(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     u.cblocks = cin_g / 32;
     u.kblocks = a.kh * a.kw * u.cblocks;
     u.relu = a.relu; u.round_out = a.round_out;
-    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : v; }();
     u.chunk = a.split ? chunk_kb : u.kblocks;
     const bool presplit = a.split && a.w_rem != nullptr;
     u.rem_rows = presplit ? a.Cout : 0;

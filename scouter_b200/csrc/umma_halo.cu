@@ -567,7 +567,7 @@ int launch_conv_halo(const ConvArgs& a, UmmaConvPlan& plan, cudaStream_t s) {
     // multiple of 2048: a stage is 2.5 patch buffers and the next stage's SWIZZLE_128B patch must start 1024-aligned
     u.patch_alloc = (int)align_up((size_t)std::max(PH * u.PW, 2 * u.PW + 2 + 128) * 128, 2048);
     if (fold) u.patch_alloc = (int)align_up((size_t)PH * u.PW * 128, 2048);   // the last kernel row starts at 2*PW and reads 128 rows: exactly the patch
-    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    static int chunk_kb = [] { const char* e = getenv("SCOUTER_UMMA_CHUNK"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : v; }();
     u.chunk = fold ? 3 : chunk_kb;   // folded: one chunk = the three kernel rows of a channel block (18 accumulations)
     const int b_stage = (fold ? 3 : 1) * BN * 128;   // HCfg<BN, FOLD>::B_STAGE
     static bool no_tma_store = getenv("SCOUTER_NO_TMA_STORE") != nullptr;
