@@ -83,7 +83,9 @@ struct Cfg {
     static constexpr int OUT_STAGE = 128 * 64;              // TMA-store staging: 128 rows x 16 fp32, SWIZZLE_64B
     // RES: the whole 128 x BN residual tile is TMA-loaded into BN/16 slabs; the epilogue adds it in place and the
     // same slabs are the source of the TMA stores (no staging double buffer, no row-per-thread residual loads).
-    static constexpr int OUT_BYTES = RES ? (BN / 16) * OUT_STAGE : EPI_GROUPS * 2 * OUT_STAGE;
+    // SPLIT: one slab per 16 output columns of the tile (RES: they first receive the residual), so a tile leaves with ONE proxy
+    // fence + barrier per epilogue group; the single-pass kernel keeps the two-buffer ping-pong.
+    static constexpr int OUT_BYTES = SPLIT ? (BN / 16) * OUT_STAGE : EPI_GROUPS * 2 * OUT_STAGE;
     static constexpr int FIT = (224 * 1024 - OUT_BYTES) / STAGE;
     static constexpr int STAGES = TS ? 1 : (FIT > 8 ? 8 : FIT);
     // TS: two rings instead of stages.  The activation tile is dead as soon as the splitters hold it in registers, so its
@@ -249,12 +251,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int kblocks = p.kblocks, chunk = p.chunk;
             int ws = 0, in_chunk = 0;
             uint32_t wphase = 0, gk = 0, cc = 0;
+            PROF_DECL(cempty); PROF_DECL(full); PROF_DECL(opf); PROF_DECL(iss); PROF_DECL(nkb); PROF_BEGIN(iss);
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
+#ifdef SCOUTER_PROF
+                prof_nkb += kblocks;
+#endif
                 for (int kb = 0; kb < kblocks; ++kb, ++gk) {
                     const uint32_t buf = cc & 1, ob = gk & 3;
-                    if (in_chunk == 0) mbar_wait_a(cempty_a + 8 * buf, ((cc >> 1) & 1) ^ 1);
-                    mbar_wait_a(opfull_a + 8 * ob, (gk >> 2) & 1);
-                    mbar_wait_a(fullw_a + 8 * ws, wphase);
+                    if (in_chunk == 0) PROF_T(cempty, mbar_wait_a(cempty_a + 8 * buf, ((cc >> 1) & 1) ^ 1));
+                    PROF_T(opf, mbar_wait_a(opfull_a + 8 * ob, (gk >> 2) & 1));
+                    PROF_T(full, mbar_wait_a(fullw_a + 8 * ws, wphase));
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     const uint32_t acc = in_chunk != 0;
@@ -278,6 +284,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
+            PROF_END(iss);
+            PROF_STORE(g_prof_flat, 4, iss); PROF_STORE(g_prof_flat, 6, cempty); PROF_STORE(g_prof_flat, 7, full);
+            PROF_STORE(g_prof_flat, 5, opf); PROF_STORE(g_prof_flat, 8, nkb);
         }
     } else if (warp == 0) {
         if (elect_one()) {
@@ -560,6 +569,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (p.round_out) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
                             *cell = v;
                         }
+                        // per slab: its store starts while the next slab is still being added (batching the fences was measured
+                        // SLOWER on the HBM-bound residual convs: 355 -> 382 us on layer 1)
                         fence_proxy_async();
                         named_bar_sync(1 + grp, 128);
                         if (row == 0) {
@@ -575,8 +586,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     prof_store += clock64() - _ts;
 #endif
                 } else if (p.tma_store) {
+                    // all NC columns of the row go to the group's slabs, then one fence + barrier and the stores (bias and the
+                    // register-path residual are already in acc)
+                    if (row == 0) bulk_wait_read<0>();            // the previous tile's stores have read the slabs
+                    named_bar_sync(1 + grp, 128);
 #pragma unroll
-                    for (int c = 0; c < C::NC / 16; ++c) emit_tma16(&acc[c * 16], c);
+                    for (int c = 0; c < C::NC / 16; ++c) {
+                        uint8_t* stg = out_stage + (col0 / 16 + c) * C::OUT_STAGE + row * 64;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float4 v = make_float4(acc[c * 16 + 4 * j], acc[c * 16 + 4 * j + 1], acc[c * 16 + 4 * j + 2], acc[c * 16 + 4 * j + 3]);
+                            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            if (p.round_out) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                            *reinterpret_cast<float4*>(stg + ((j ^ ((row >> 1) & 3)) << 4)) = v;   // SWIZZLE_64B
+                        }
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(1 + grp, 128);
+                    if (row == 0) {
+#pragma unroll
+                        for (int c = 0; c < C::NC / 16; ++c)
+                            tma_store_3d(&tmO, out_stage + (col0 / 16 + c) * C::OUT_STAGE, ch0 + c * 16, mt * 128, sp);
+                        bulk_commit();
+                    }
 #ifdef SCOUTER_PROF
                     prof_store += clock64() - _ts;
 #endif
