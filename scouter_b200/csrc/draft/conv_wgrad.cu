@@ -79,7 +79,64 @@ __global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(WgradArgs a) {
         }
 }
 
+// Few input channels (the stem: Cin = 3 or 1, k = 3): the flattened (r, s, c) index j < 32 plays the channel role.  CTA = 32 output
+// channels x all taps, 64 pixels per shared-memory stage; thread = (output channel, taps jj, jj+8, jj+16, jj+24).  The naive kernel
+// had 864 threads' worth of parallelism for 401k pixels (2.1 ms of a 34 ms step).
+__global__ void __launch_bounds__(256) conv_wgrad_smallc_kernel(WgradArgs a, int pix_per_cta) {
+    __shared__ float dy_s[64][33];
+    __shared__ float x_s[64][33];
+    const int taps = a.k * a.k * a.Cin;                 // <= 32
+    const int o0 = blockIdx.y * 32;
+    const long long M = (long long)a.B * a.Ho * a.Wo;
+    const long long m0 = (long long)blockIdx.x * pix_per_cta, m1 = m0 + pix_per_cta < M ? m0 + pix_per_cta : M;
+    const int tid = threadIdx.x, o = tid & 31, jj = tid >> 5;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long mb = m0; mb < m1; mb += 64) {
+        for (int i = tid; i < 64 * 32; i += 256) {
+            const int pl = i >> 5, q = i & 31;
+            const long long m = mb + pl;
+            float dv = 0.f, xv = 0.f;
+            if (m < m1) {
+                dv = __ldg(a.dy + (size_t)m * a.Cout + o0 + q);
+                if (q < taps) {
+                    const int c = q % a.Cin, rs = q / a.Cin, sx = rs % a.k, r = rs / a.k;
+                    const int xo = (int)(m % a.Wo);
+                    const long long t = m / a.Wo;
+                    const int yo = (int)(t % a.Ho), b = (int)(t / a.Ho);
+                    const int yi = yo * a.stride + r - a.pad, xi = xo * a.stride + sx - a.pad;
+                    if (yi >= 0 && yi < a.H && xi >= 0 && xi < a.W) xv = __ldg(a.x + (((size_t)b * a.H + yi) * a.W + xi) * a.Cin + c);
+                }
+            }
+            dy_s[pl][q] = dv;
+            x_s[pl][q] = xv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int pl = 0; pl < 64; ++pl) {
+            const float d = dy_s[pl][o];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fmaf(d, x_s[pl][jj + 8 * q], acc[q]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = jj + 8 * q;
+        if (j < taps) atomicAdd(a.dw + (size_t)(o0 + o) * taps + j, acc[q]);
+    }
+}
+
 int conv_wgrad_launch(const WgradArgs& a, int sms, cudaStream_t stream) {
+    if (!a.db && a.groups == 1 && a.k * a.k * a.Cin <= 32 && a.Cout % 32 == 0) {
+        const long long M = (long long)a.B * a.Ho * a.Wo;
+        const int o_tiles = a.Cout / 32;
+        long long ctas = (8LL * sms + o_tiles - 1) / o_tiles;
+        long long per = ((M + ctas - 1) / ctas + 63) / 64 * 64;
+        if (per < 256) per = 256;
+        const int gx = (int)((M + per - 1) / per);
+        conv_wgrad_smallc_kernel<<<dim3(gx, o_tiles), 256, 0, stream>>>(a, (int)per);
+        return (int)cudaGetLastError();
+    }
     {
         const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
         const long long M = (long long)a.B * a.Ho * a.Wo;

@@ -1,12 +1,17 @@
-// DRAFT (row f1) -- see head_backward.cuh.  Not listed in scouter_b200/_lib.py SOURCES: the library does not contain it.
-// Compiles for sm_100a (`nvcc -gencode arch=compute_100a,code=sm_100a -c`); has not run on a GPU yet.
+// Row f1 -- see head_backward.cuh.
+// Part of libscouter_b200.so through csrc/train.cu (scouter_train_head_backward).
 #include <cuda_runtime.h>
 
 #include "head_backward.cuh"
 
 namespace scouter_draft {
 
-__global__ void __launch_bounds__(256) head_backward_kernel(HeadBwdArgs a) {
+// threads per image (the phases are element loops strided by the block size); 512 / 1024 were measured: no change of the step time,
+// which at B = 32 is bound by the ~1300 launches the Python driver issues, not by this kernel
+#ifndef SCOUTER_HB_THREADS
+#define SCOUTER_HB_THREADS 256
+#endif
+__global__ void __launch_bounds__(SCOUTER_HB_THREADS) head_backward_kernel(HeadBwdArgs a) {
     head_backward_image(a, blockIdx.x, threadIdx.x, blockDim.x);
 }
 
@@ -24,7 +29,7 @@ __global__ void head_backward_coef_kernel(const float* __restrict__ attn_sum, in
 size_t head_backward_scratch_floats(int n, int S, int L, int iters) { return head_bwd_layout(n, S, L, iters).total; }
 
 int head_backward_launch(const HeadBwdArgs& a, cudaStream_t stream) {
-    head_backward_kernel<<<a.B, 256, 0, stream>>>(a);
+    head_backward_kernel<<<a.B, SCOUTER_HB_THREADS, 0, stream>>>(a);
     return (int)cudaGetLastError();
 }
 
