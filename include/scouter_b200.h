@@ -367,6 +367,12 @@ typedef struct scouter_adamw_args {      /* torch.optim.AdamW single-tensor step
 } scouter_adamw_args_t;
 int scouter_train_adamw_step(const scouter_adamw_args_t* a, scouter_stream_t stream);
 
+/* The pre-split weight operand `w2` of scouter_op_t for SCOUTER_MATH_TC, made on the device in ONE launch: for n fp32 weights
+ * out16[0..n) = fp16(w) (round to nearest, saturating) and out16[n..2n) = bf16(w - fp16(w)).  The training step re-splits every
+ * conv's weights each step (the parameters change); scouter_b200/plan.py split_weights_f16 is the torch-op equivalent the
+ * eval path runs once per parameter version. */
+int scouter_split_weights_f16(const float* w, void* out16, size_t n, scouter_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a1  SlotModel.forward from HOST buffers in one call (sloter/slot_model.py:105-127 as driven by
  *     engine.py:25-30: H2D copy of the batch, forward, read-back of the result).

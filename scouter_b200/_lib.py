@@ -125,6 +125,7 @@ SIGNATURES = {
     "scouter_train_head_backward_scratch_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "scouter_train_head_backward": (C.c_int, [C.c_void_p, _fp]),
     "scouter_train_adamw_step": (C.c_int, [C.c_void_p, _fp]),
+    "scouter_split_weights_f16": (C.c_int, [_fp, _fp, C.c_size_t, _fp]),
 }
 
 

@@ -8,6 +8,11 @@
 #include "draft/adamw.cuh"
 #include "draft/bn_train.cuh"
 #include "draft/conv_wgrad.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
 #include "draft/head_backward.cuh"
 #include "draft/pool_splat_bwd.cuh"
 
@@ -144,6 +149,25 @@ extern "C" int scouter_train_head_backward(const scouter_head_bwd_args_t* a, sco
     SC_CHECK_ARG(a->g_conv_w && a->g_conv_b && a->g_w_ih && a->g_w_hh && a->g_b_ih && a->g_b_hh && a->g_slots0 && (a->d_feat || a->d_pre),
                  SCOUTER_E_INVALID, "train_head_backward: NULL gradient output");
     return done(sd::head_backward_launch(*reinterpret_cast<const sd::HeadBwdArgs*>(a), (cudaStream_t)stream), "train_head_backward");
+}
+
+namespace {
+__global__ void __launch_bounds__(256) split_weights_f16_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = w[i];
+        const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+        const __nv_bfloat16 r = __float2bfloat16_rn(x - __half2float(h));
+        out[i] = __half_as_ushort(h);
+        out[n + i] = __bfloat16_as_ushort(r);
+    }
+}
+}  // namespace
+
+extern "C" int scouter_split_weights_f16(const float* w, void* out16, size_t n, scouter_stream_t stream) {
+    SC_CHECK_ARG(w && out16 && n > 0, SCOUTER_E_INVALID, "split_weights_f16: NULL pointer / empty tensor");
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    split_weights_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)out16, n);
+    return done((int)cudaGetLastError(), "split_weights_f16");
 }
 
 extern "C" int scouter_train_adamw_step(const scouter_adamw_args_t* a, scouter_stream_t stream) {

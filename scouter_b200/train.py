@@ -37,6 +37,14 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
+def _split_f16(w: torch.Tensor) -> torch.Tensor:
+    """``plan.split_weights_f16`` in ONE launch (the step re-splits ~100 weight tensors; as torch ops that was ~750 launches)."""
+    w = w.contiguous()
+    out = torch.empty((2 * w.shape[0],) + tuple(w.shape[1:]), dtype=torch.int16, device=w.device)
+    L.check(L.lib().scouter_split_weights_f16(w.data_ptr(), out.data_ptr(), w.numel(), L.stream_ptr()), "scouter_split_weights_f16")
+    return out
+
+
 class TrainEngine:
     def __init__(self, model):
         if not model.use_slot:
@@ -74,7 +82,7 @@ class TrainEngine:
             if k == "conv":
                 conv = self._mod(op["key"])
                 w = conv.weight.detach().permute(0, 2, 3, 1).contiguous()           # OHWI
-                w2 = split_weights_f16(w) if math_mode == L.MATH_TC else None
+                w2 = _split_f16(w) if math_mode == L.MATH_TC else None
                 kh = conv.kernel_size[0]
                 Ho = (H + 2 * op["pad"] - kh) // op["stride"] + 1
                 Wo = (W + 2 * op["pad"] - kh) // op["stride"] + 1
@@ -214,7 +222,7 @@ class TrainEngine:
         # d feat (B, n, ch) = d pre . W: a 1x1 conv 64 -> ch with the transposed weights, on the forward tcgen05 kernel
         math_mode = m._math()
         wt = m.conv1x1.weight.detach().reshape(64, ch).t().contiguous()                # (ch, 64) = OHWI (ch, 1, 1, 64)
-        wt2 = split_weights_f16(wt) if math_mode == L.MATH_TC else None
+        wt2 = _split_f16(wt) if math_mode == L.MATH_TC else None
         d_feat = torch.empty(B, n, ch, **f32)
         op = L.Op(kind=L.OP_CONV, src=0, src2=-1, dst=1, cin=64, cout=ch, kh=1, kw=1, stride=1, pad=0, groups=1, flags=0, mid=0,
                   reserved=0, w=wt.data_ptr(), b=0, w2=_p(wt2), b2=0)
@@ -252,7 +260,7 @@ class TrainEngine:
                         # padding k-1-pad): it runs on the forward kernels -- tcgen05 in the tensor-core mode
                         math_mode = m._math()
                         wt = dgrad_weights(w, e["groups"])
-                        wt2 = split_weights_f16(wt) if math_mode == L.MATH_TC else None
+                        wt2 = _split_f16(wt) if math_mode == L.MATH_TC else None
                         o = L.Op(kind=L.OP_CONV, src=0, src2=-1, dst=1, cin=Cout, cout=Cin, kh=kk, kw=kk, stride=1, pad=kk - 1 - e["pad"],
                                  groups=e["groups"], flags=0, mid=0, reserved=0, w=wt.data_ptr(), b=0, w2=_p(wt2), b2=0)
                         L.check(lib.scouter_conv_forward(C.byref(o), dy.data_ptr(), 0, dx.data_ptr(), B, Ho, Wo, math_mode, st), "scouter_conv_forward (dgrad)")
