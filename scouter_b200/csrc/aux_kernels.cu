@@ -409,7 +409,40 @@ int splat_gap_splits(int B, int HW) {
     return std::min(n, 64);
 }
 
+// Many slots (the conv epilogue writes one per tile and epilogue warp: 112 on the 56x56 maps): CTA = image, the slots are spread
+// over thread lanes and merged through shared memory in lane order (fixed order) -- the thread-per-channel kernel above walked
+// them serially with 64 CTAs in flight (35 us per call on layer 1).
+__global__ void __launch_bounds__(512) splat_gap_finish_wide_kernel(const float* __restrict__ part, float* __restrict__ gap, int C, int nslots,
+                                                                    float inv_hw) {
+    __shared__ float red[512];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int cw = C < 512 ? C : 512;          // channels handled per pass (C is a power of two here: 64..512)
+    const int lanes = 512 / cw;
+    const int cl = tid % cw, sl = tid / cw;
+    for (int c0 = 0; c0 < C; c0 += cw) {
+        const int c = c0 + cl;
+        float s = 0.f;
+        for (int sp = sl; sp < nslots; sp += lanes) {
+            const float* p = part + ((size_t)b * nslots + sp) * 2 * C;
+            s += __ldg(p + c) + __ldg(p + C + c);       // radix sum (split_attn.py:64-65)
+        }
+        red[tid] = s;
+        __syncthreads();
+        if (sl == 0) {
+            float t = red[cl];
+            for (int l = 1; l < lanes; ++l) t += red[l * cw + cl];
+            gap[(size_t)b * C + c] = t * inv_hw;
+        }
+        __syncthreads();
+    }
+}
+
 int launch_splat_gap_finish(const float* part, float* gap, int B, int HW, int C, int nslots, cudaStream_t s) {
+    if (nslots >= 16 && (C & (C - 1)) == 0 && C >= 32 && 512 % (C < 512 ? C : 512) == 0) {
+        splat_gap_finish_wide_kernel<<<B, 512, 0, s>>>(part, gap, C, nslots, 1.0f / (float)HW);
+        SC_LAUNCH_CHECK();
+        return 0;
+    }
     splat_gap_finish_kernel<<<cdiv(B * C, 256), 256, 0, s>>>(part, gap, B, C, nslots, 1.0f / (float)HW);
     SC_LAUNCH_CHECK();
     return 0;
