@@ -178,3 +178,46 @@ def test_invalidate_covers_data_writes():
     m._states["k"] = object()
     m.release_states()
     assert not m._states
+
+
+def test_split_weights_f16_reconstructs_fp32():
+    """The pre-split conv operand [fp16(W) ; bf16(W - fp16(W))] (plan.split_weights_f16, csrc/ptx.cuh split2_wgt): the two
+    halves add back to W within bf16's rounding of a 2^-12 remainder, tiny values keep their remainder (bf16 has fp32's
+    exponent range) and values beyond fp16's range saturate the first half while the second carries the excess."""
+    from scouter_b200.plan import split_weights_f16
+    w = torch.randn(8, 3, 3, 32) * 0.05
+    w[0, 0, 0, 0], w[0, 0, 0, 1], w[0, 0, 0, 2] = 1e-7, 70000.0, -3.0e-5
+    s = split_weights_f16(w)
+    assert s.dtype == torch.int16 and s.shape == (16, 3, 3, 32)
+    h = s[:8].view(torch.float16).float()
+    r = s[8:].view(torch.bfloat16).float()
+    assert float(h[0, 0, 0, 1]) == 65504.0 and abs(float(r[0, 0, 0, 1]) - (70000.0 - 65504.0)) < 32.0
+    err = (h + r - w).abs()
+    err[0, 0, 0, 1] = 0.0
+    # |remainder| <= max(2^-12 |w|, 2^-25) (half an fp16 ulp; 2^-25 below fp16's normal range), stored with bf16's 2^-9 rounding
+    bound = 2.0 ** -8 * torch.maximum(2.0 ** -11 * w.abs(), torch.full_like(w, 2.0 ** -24))
+    assert bool((err <= bound).all())
+    assert float((err / w.abs().clamp_min(1e-30))[w.abs() > 1e-3].max()) < 2.0 ** -19
+
+
+def test_precision_policy_flags_only_the_listed_stages(monkeypatch):
+    """SCOUTER_TC_FAST_STAGES / SlotModel.fast_stages (the measured-and-rejected per-stage policy): ops of the listed
+    stages carry F_TF32_1PASS and no pre-split operand; every other conv keeps w2; other math modes ignore the policy."""
+    from scouter_b200 import plan as P
+    m = sb.SlotModel(make_args(model="resnest26d"))
+    prog, _ = P.lower_backbone(m.backbone, L.MATH_TC, ("stem", "layer1"))
+    flagged = [o for o in prog.ops if o.flags & L.F_TF32_1PASS]
+    convs = [o for o in prog.ops if o.kind == L.OP_CONV]
+    assert flagged and all(not o.w2 for o in flagged if o.kind == L.OP_CONV)
+    assert any(o.w2 for o in convs) and all(bool(o.w2) != bool(o.flags & L.F_TF32_1PASS) for o in convs)
+    # stem (3 convs + max-pool) + layer1 (2 blocks): the first op after them is layer2's conv1 and is not flagged
+    n_flagged = len(flagged)
+    prog2, _ = P.lower_backbone(m.backbone, L.MATH_TC, ("stem",))
+    assert 0 < sum(1 for o in prog2.ops if o.flags & L.F_TF32_1PASS) < n_flagged
+    prog3, _ = P.lower_backbone(m.backbone, L.MATH_FP32, ("stem", "layer1"))
+    assert not any(o.flags & L.F_TF32_1PASS for o in prog3.ops)
+    monkeypatch.setenv("SCOUTER_TC_FAST_STAGES", "layer4, stem")
+    assert P.default_fast_stages() == ("layer4", "stem")
+    monkeypatch.setenv("SCOUTER_TC_FAST_STAGES", "layer9")
+    with pytest.raises(L.ScouterError):
+        P.default_fast_stages()
